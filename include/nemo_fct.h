@@ -1,0 +1,163 @@
+/*
+ * nemo_fct.h -- C ABI of the B200-native FCT tracer-advection path (libnemo_fct.so).
+ *
+ * This is the drop-in boundary: exactly the entry points a NEMO host (Fortran, through ISO_C_BINDING) binds to
+ * replace its own routines on the tra_adv_fct path.  Plain pointers and sizes only, no torch / C++ types.
+ * Every entry point cites the reference interface it replaces (paths relative to the NEMO tree).
+ *
+ *   reference routine                                             ->  entry point here
+ *   ---------------------------------------------------------------------------------------------------------
+ *   mpp_init              src/OCE/LBC/mppini.F90:110-692          ->  nemo_mpp_init            (host only)
+ *   nemo_alloc/dom_init   src/OCE/nemogcm.F90:640-673 (+dom_oce)  ->  nemo_fct_create / nemo_fct_set_domain_arrays
+ *   dom_vvl_sf_swp        src/OCE/DOM/domvvl.F90:620 (e3t swap)    ->  nemo_fct_set_e3t
+ *   tra_adv_fct           src/OCE/TRA/traadv_fct.F90:54-80        ->  nemo_tra_adv_fct[_dev]
+ *     (call sites         src/OCE/TRA/traadv.F90:150, src/TOP/TRP/trcadv.F90:127)
+ *   interp_4th_cpt        src/OCE/TRA/traadv_fct.F90:517-527      ->  nemo_interp_4th_cpt[_dev]
+ *   tra_adv transports    src/OCE/TRA/traadv.F90:100-124          ->  nemo_tra_adv_transports_dev
+ *   lbc_lnk_multi         src/OCE/LBC/lbc_lnk_multi_generic.h90:16-29 -> nemo_lbc_lnk_multi[_dev]
+ *   mynode / MPI_Init     src/OCE/LBC/lib_mpp.F90:197-331         ->  nemo_fct_comm_unique_id / nemo_fct_comm_init
+ *   ctl_stop              src/OCE/LBC/lib_mpp.F90:1868-1907       ->  non-zero return + nemo_fct_last_error
+ *
+ * Conventions
+ *   - All arrays are Fortran column-major REAL(wp)=fp64: a(jpi,jpj,jpk[,kjpt]) == double[kjpt][jpk][jpj][jpi].
+ *     INTEGER arrays are 32-bit.  Indices documented 1-based as in the reference.
+ *   - "host" pointers are ordinary CPU memory (pageable or pinned); "_dev" variants take CUDA device pointers
+ *     valid on the context's device and are asynchronous on the context's stream.
+ *   - Every function returns 0 on success, non-zero on error; nemo_fct_last_error() gives the message.  The
+ *     Fortran shim maps non-zero to CALL ctl_stop('STOP', msg).  There is NO CPU fallback: if no CUDA device is
+ *     usable, nemo_fct_create fails.
+ *   - SPMD contract as in the reference (lib_mpp.F90:1497-1506): with jpnij > 1 every rank calls the same
+ *     entry points in the same order.
+ */
+#ifndef NEMO_FCT_H
+#define NEMO_FCT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEMO_FCT_ABI_VERSION 1
+#define NEMO_FCT_JPMAXNGH 3            /* lbcnfd.F90:53 */
+#define NEMO_FCT_UNIQUE_ID_BYTES 128   /* sizeof(ncclUniqueId) */
+
+typedef struct nemo_fct_ctx *nemo_fct_handle;
+
+/* Decomposition scalars of one subdomain: the PUBLIC variables of par_oce.F90 / dom_oce.F90 that mpp_init sets
+ * (mppini.F90:548-580, 621-628) plus the global description.  Filled by nemo_mpp_init, or by the host from its
+ * own mpp_init -- nemo_fct_create cross-checks them against its own decomposition and fails on mismatch.       */
+typedef struct nemo_fct_domain {
+    int jpiglo, jpjglo, jpk;          /* global horizontal size, number of levels                               */
+    int jperio;                       /* lateral boundary type 0..7 (dom_oce.F90, chap_LBC.tex:149-260)         */
+    int jpni, jpnj;                   /* processor grid                                                         */
+    int narea;                        /* this rank, 1-based (nproc = narea-1)                                   */
+    int jpi, jpj;                     /* local array extents (= nlci, nlcj)                                     */
+    int jpimax, jpjmax;
+    int nimpp, njmpp;                 /* global index of local (1,1)                                            */
+    int nlci, nlcj, nldi, nlei, nldj, nlej;
+    int nbondi, nbondj;               /* -1 / 0 / 1 / 2 neighbour flags                                         */
+    int noea, nowe, noso, nono;       /* neighbour ranks (0-based), -1 if none                                  */
+    int npolj;                        /* north fold type of this rank: 0 / 3,4 (T pivot) / 5,6 (F pivot)        */
+    int l_Iperio, l_Jperio;           /* periodicity handled locally (mppini.F90:345-346)                       */
+    int nsndto, isendto[NEMO_FCT_JPMAXNGH];   /* no-gather fold partners (mppini.F90:1180-1240)                  */
+    int key_mpp_mpi;                  /* 0: single-domain build semantics (mppini.F90:53-102, npolj = jperio)   */
+} nemo_fct_domain;
+
+/* ---- decomposition (host only, no GPU needed) -------------------------------------------------------------- */
+/* mpp_init for rank `narea` of a jpni x jpnj layout (all-ocean: no land-subdomain elimination).                 */
+int nemo_mpp_init(int jpiglo, int jpjglo, int jpk, int jperio, int jpni, int jpnj, int narea, int key_mpp_mpi,
+                  nemo_fct_domain *out);
+/* mpp_basic_decomposition (mppini.F90:695-798): tables are (jpni,jpnj) column-major; any may be NULL.           */
+int nemo_mpp_basic_decomposition(int jpiglo, int jpjglo, int jperio, int jpni, int jpnj, int *jpimax, int *jpjmax,
+                                 int *nimppt, int *njmppt, int *nlcit, int *nlcjt);
+/* The compiled lbc_lnk exchange plan of one rank for grid-point type cd_nat in "TUVWF": number of halo / fold
+ * cells this rank receives from `peer` (0-based; peer == own rank counts local copies), or fills with the land
+ * value when peer == -1.  With non-NULL outputs (each sized to the returned count) also returns, per cell and
+ * in message order: the destination local index (i-1)+(j-1)*jpi, the source local index on the peer, and the
+ * power of psgn applied.  Host only; used by the CPU tests to execute the plan over gloo and compare with the
+ * oracle's mpp_lnk.                                                                                             */
+int nemo_lbc_plan_query(const nemo_fct_domain *dom, char cd_nat, int peer, int *dst_index, int *src_index,
+                        int *sgn_power);
+
+/* ---- life cycle ------------------------------------------------------------------------------------------------ */
+/* Create the device context of one subdomain on CUDA device `device` (-1: use LOCAL_RANK, else 0).  Allocates
+ * streams, the lbc_lnk plans and (lazily, sized by the first call) the work arrays, ONCE, as nemo_alloc does
+ * (nemogcm.F90:640-673).  Fails if no CUDA device is available.                                                  */
+int nemo_fct_create(const nemo_fct_domain *dom, int device, nemo_fct_handle *out);
+int nemo_fct_destroy(nemo_fct_handle h);
+/* Time-invariant module arrays of dom_oce.F90 (host pointers, copied to the device):
+ * tmask,umask,vmask,wmask (jpi,jpj,jpk); e1e2t,r1_e1e2t (jpi,jpj); mikt,mbkt INTEGER (jpi,jpj); flags of
+ * dom_oce.F90 (ln_linssh) and of the ice-shelf-cavity option (ln_isfcav).                                         */
+int nemo_fct_set_domain_arrays(nemo_fct_handle h, const double *tmask, const double *umask, const double *vmask,
+                               const double *wmask, const double *e1e2t, const double *r1_e1e2t, const int *mikt,
+                               const int *mbkt, int ln_linssh, int ln_isfcav);
+/* Vertical scale factors e3t_b, e3t_n, e3t_a (jpi,jpj,jpk), time-varying when .NOT.ln_linssh.
+ * is_device != 0: the pointers are device pointers that the context borrows (no copy).                            */
+int nemo_fct_set_e3t(nemo_fct_handle h, const double *e3t_b, const double *e3t_n, const double *e3t_a, int is_device);
+/* Run all subsequent work of this context on the caller's CUDA stream (cudaStream_t passed as void*; NULL
+ * restores the context's own stream).                                                                             */
+int nemo_fct_set_stream(nemo_fct_handle h, void *cuda_stream);
+int nemo_fct_synchronize(nemo_fct_handle h);
+
+/* ---- communicator (jpnij > 1, one process per GPU) -------------------------------------------------------------- */
+/* Rank 0 obtains an id, the host broadcasts the 128 bytes (MPI_Bcast in NEMO, torch.distributed in bench.py),
+ * then every rank calls nemo_fct_comm_init.  The halo strips and the north fold then move with ncclSend/ncclRecv. */
+int nemo_fct_comm_unique_id(void *id128);
+int nemo_fct_comm_init(nemo_fct_handle h, const void *id128, int nranks, int rank);
+/* In-process communicator: all `n` subdomains live in this process on the SAME device (decomposition tests on
+ * one GPU); collective entry points are then the nemo_group_* calls below.                                        */
+int nemo_fct_comm_init_local(nemo_fct_handle *hs, int n);
+
+/* ---- the hot path --------------------------------------------------------------------------------------------------- */
+/* tra_adv_fct (traadv_fct.F90:54-80), same argument list.  pun,pvn,pwn (jpi,jpj,jpk) are TRANSPORTS; ptb,ptn,pta
+ * (jpi,jpj,jpk,kjpt).  Only pta(2:jpim1,2:jpjm1,1:jpkm1,:) is modified.  kn_fct_h, kn_fct_v in {2,4}.
+ * Host variant: synchronous, copies inputs to the device and pta back.                                            */
+int nemo_tra_adv_fct(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
+                     const double *pvn, const double *pwn, const double *ptb, const double *ptn, double *pta,
+                     int kjpt, int kn_fct_h, int kn_fct_v);
+/* Device-resident variant: all pointers are device pointers; asynchronous on the context's stream.               */
+int nemo_tra_adv_fct_dev(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
+                         const double *pvn, const double *pwn, const double *ptb, const double *ptn, double *pta,
+                         int kjpt, int kn_fct_h, int kn_fct_v);
+/* In-process group variant (nemo_fct_comm_init_local): argument tables indexed like hs[].                         */
+int nemo_group_tra_adv_fct_dev(nemo_fct_handle *hs, int n, int kt, int kit000, const char *cdtype, double p2dt,
+                               const double *const *pun, const double *const *pvn, const double *const *pwn,
+                               const double *const *ptb, const double *const *ptn, double *const *pta, int kjpt,
+                               int kn_fct_h, int kn_fct_v);
+
+/* interp_4th_cpt (traadv_fct.F90:517-527; also called by traadv_cen.F90:158): pt_in, pt_out (jpi,jpj,jpk);
+ * pt_out is defined on (2:jpim1, 2:jpjm1, 2:jpkm1) only.                                                          */
+int nemo_interp_4th_cpt(nemo_fct_handle h, const double *pt_in, double *pt_out);
+int nemo_interp_4th_cpt_dev(nemo_fct_handle h, const double *pt_in, double *pt_out);
+
+/* Effective transports of tra_adv / trc_adv (traadv.F90:100-124, trcadv.F90:93-108), Eulerian branch:
+ * zun = e2u*e3u_n*un, zvn = e1v*e3v_n*vn, zwn = e1e2t*wn, level jpk zeroed.  Device pointers.                      */
+int nemo_tra_adv_transports_dev(nemo_fct_handle h, const double *e2u, const double *e1v, const double *e3u_n,
+                                const double *e3v_n, const double *un, const double *vn, const double *wn,
+                                double *zun, double *zvn, double *zwn);
+
+/* lbc_lnk_multi (lbc_lnk_multi_generic.h90:16-29): nfld fields ptab[f] of (jpi,jpj,ipk) each (a 4-D field is a
+ * 3-D field with ipk*ipl levels), grid-point type cd_nat[f] in "TUVWF", fold sign psgn[f]; has_pval/pval = the
+ * optional land value.  cd_mpp is not supported (not used on this path).                                          */
+int nemo_lbc_lnk_multi(nemo_fct_handle h, const char *cdname, int nfld, double *const *ptab, const char *cd_nat,
+                       const double *psgn, int ipk, int has_pval, double pval);
+int nemo_lbc_lnk_multi_dev(nemo_fct_handle h, const char *cdname, int nfld, double *const *ptab,
+                           const char *cd_nat, const double *psgn, int ipk, int has_pval, double pval);
+int nemo_group_lbc_lnk_multi_dev(nemo_fct_handle *hs, int n, const char *cdname, int nfld,
+                                 double *const *const *ptab, const char *cd_nat, const double *psgn, int ipk,
+                                 int has_pval, double pval);
+
+/* ---- diagnostics ------------------------------------------------------------------------------------------------------ */
+const char *nemo_fct_last_error(void);
+int nemo_fct_abi_version(void);
+/* number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches)                */
+long long nemo_fct_launch_count(void);
+/* communication report in the spirit of mpp_report (lib_mpp.F90:1471-1587): exchanges and bytes sent so far       */
+int nemo_fct_comm_report(nemo_fct_handle h, long long *n_exchanges, long long *bytes_sent);
+/* Select the kernel schedule: 0 = reference pass structure (one kernel per pass group, exchanges X1..X4 as in
+ * traadv_fct.F90:209,280,400,426); higher = fused schedules.  Results are identical.              */
+int nemo_fct_set_schedule(nemo_fct_handle h, int schedule);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,347 @@
+"""nemo-fmi-devel_b200 -- host-side mirror of the NEMO interfaces on the FCT tracer-advection path.
+
+This package is a thin ctypes binding of ``libnemo_fct.so`` (C ABI in ``include/nemo_fct.h``), keeping the
+reference's routine names, argument order and meaning so that tests read like calls into NEMO:
+
+    mpp_init            src/OCE/LBC/mppini.F90:110           -> :func:`mpp_init`
+    tra_adv_fct         src/OCE/TRA/traadv_fct.F90:54        -> :meth:`FctContext.tra_adv_fct`
+    interp_4th_cpt      src/OCE/TRA/traadv_fct.F90:517       -> :meth:`FctContext.interp_4th_cpt`
+    lbc_lnk_multi       src/OCE/LBC/lbc_lnk_multi_generic.h90:16 -> :meth:`FctContext.lbc_lnk_multi`
+    tra_adv transports  src/OCE/TRA/traadv.F90:100-124       -> :meth:`FctContext.tra_adv_transports`
+
+Arrays are fp64 with the Fortran memory image ``a(jpi,jpj,jpk[,kjpt])``, i.e. C-order shape ``([kjpt,] jpk, jpj, jpi)``.
+numpy arrays are passed as HOST pointers (the library copies H2D/D2H, as a Fortran host would see it); CUDA
+``torch`` tensors are passed as DEVICE pointers (device-resident path).  There is no CPU implementation here:
+without the CUDA library the import of the binding fails loudly, and without a GPU every compute call raises.
+
+(The directory name carries a hyphen as the project layout prescribes; import it with
+``importlib.import_module("nemo-fmi-devel_b200")`` or through the ``nemo_fct_b200`` alias module at the repo root.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnemo_fct.so")
+JPMAXNGH = 3
+UNIQUE_ID_BYTES = 128
+
+
+class NemoFctError(RuntimeError):
+    """Raised for every non-zero return of the C ABI (the Fortran shim would CALL ctl_stop('STOP', msg))."""
+
+
+class Domain(C.Structure):
+    """struct nemo_fct_domain: the decomposition scalars of par_oce.F90 / dom_oce.F90 (mppini.F90:548-580)."""
+    _fields_ = [(n, C.c_int) for n in (
+        "jpiglo jpjglo jpk jperio jpni jpnj narea jpi jpj jpimax jpjmax nimpp njmpp nlci nlcj nldi nlei nldj nlej "
+        "nbondi nbondj noea nowe noso nono npolj l_Iperio l_Jperio nsndto").split()] + [
+        ("isendto", C.c_int * JPMAXNGH), ("key_mpp_mpi", C.c_int)]
+
+    @property
+    def shape3(self):
+        return (self.jpk, self.jpj, self.jpi)
+
+    @property
+    def nproc(self):
+        return self.narea - 1
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "isendto"}
+        d["isendto"] = list(self.isendto)[: self.nsndto]
+        return d
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libnemo_fct.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    import subprocess
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j4"], stdout=out)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a).  There is no CPU fallback for the FCT path.")
+    L = C.CDLL(LIB_PATH)
+    vp, ip, dp, i, d = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.c_double
+    L.nemo_fct_last_error.restype = C.c_char_p
+    L.nemo_fct_launch_count.restype = C.c_longlong
+    sig = {
+        "nemo_mpp_init": [i] * 8 + [C.POINTER(Domain)],
+        "nemo_mpp_basic_decomposition": [i] * 5 + [ip] * 6,
+        "nemo_lbc_plan_query": [C.POINTER(Domain), C.c_char, i, ip, ip, ip],
+        "nemo_fct_create": [C.POINTER(Domain), i, C.POINTER(vp)],
+        "nemo_fct_destroy": [vp],
+        "nemo_fct_set_domain_arrays": [vp] + [vp] * 8 + [i, i],
+        "nemo_fct_set_e3t": [vp, vp, vp, vp, i],
+        "nemo_fct_set_stream": [vp, vp],
+        "nemo_fct_synchronize": [vp],
+        "nemo_fct_comm_unique_id": [vp],
+        "nemo_fct_comm_init": [vp, vp, i, i],
+        "nemo_fct_comm_init_local": [C.POINTER(vp), i],
+        "nemo_tra_adv_fct": [vp, i, i, C.c_char_p, d] + [vp] * 6 + [i, i, i],
+        "nemo_tra_adv_fct_dev": [vp, i, i, C.c_char_p, d] + [vp] * 6 + [i, i, i],
+        "nemo_group_tra_adv_fct_dev": [C.POINTER(vp), i, i, i, C.c_char_p, d] + [C.POINTER(vp)] * 6 + [i, i, i],
+        "nemo_interp_4th_cpt": [vp, vp, vp],
+        "nemo_interp_4th_cpt_dev": [vp, vp, vp],
+        "nemo_tra_adv_transports_dev": [vp] * 11,
+        "nemo_lbc_lnk_multi": [vp, C.c_char_p, i, C.POINTER(vp), C.c_char_p, dp, i, i, d],
+        "nemo_lbc_lnk_multi_dev": [vp, C.c_char_p, i, C.POINTER(vp), C.c_char_p, dp, i, i, d],
+        "nemo_group_lbc_lnk_multi_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.c_char_p, dp, i, i, d],
+        "nemo_fct_comm_report": [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
+        "nemo_fct_set_schedule": [vp, i],
+        "nemo_fct_abi_version": [],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(L, name)          # AttributeError here == a declared symbol is not exported
+        fn.argtypes = argtypes
+        if name not in ("nemo_fct_last_error", "nemo_fct_launch_count"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+#: every symbol include/nemo_fct.h declares (checked by the CPU test-suite against the built library)
+ABI_SYMBOLS = (
+    "nemo_mpp_init nemo_mpp_basic_decomposition nemo_lbc_plan_query nemo_fct_create nemo_fct_destroy "
+    "nemo_fct_set_domain_arrays nemo_fct_set_e3t nemo_fct_set_stream nemo_fct_synchronize nemo_fct_comm_unique_id "
+    "nemo_fct_comm_init nemo_fct_comm_init_local nemo_tra_adv_fct nemo_tra_adv_fct_dev nemo_group_tra_adv_fct_dev "
+    "nemo_interp_4th_cpt nemo_interp_4th_cpt_dev nemo_tra_adv_transports_dev nemo_lbc_lnk_multi "
+    "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
+    "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule").split()
+
+
+def _check(rc):
+    if rc != 0:
+        raise NemoFctError(lib().nemo_fct_last_error().decode())
+
+
+def _is_dev(a):
+    return hasattr(a, "is_cuda") and a.is_cuda
+
+
+def _ptr(a):
+    """raw address of a numpy array (host) or torch tensor (host or device); must be contiguous fp64/int32"""
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous(), "arrays must be contiguous"
+        return C.c_void_p(a.data_ptr())
+    assert a.flags["C_CONTIGUOUS"], "arrays must be contiguous"
+    return C.c_void_p(a.ctypes.data)
+
+
+def _f64(a, what):
+    dt = str(a.dtype)
+    if "float64" not in dt:
+        raise TypeError(f"{what}: REAL(wp) arrays are float64, got {dt}")
+    return a
+
+
+def launch_count():
+    """CUDA kernels launched by the library in this process so far."""
+    return int(lib().nemo_fct_launch_count())
+
+
+def mpp_init(jpiglo, jpjglo, jpk, jperio, jpni=1, jpnj=1, narea=1, key_mpp_mpi=True):
+    """mpp_init (mppini.F90:110-692) for rank ``narea`` (1-based): returns the filled :class:`Domain`."""
+    dom = Domain()
+    _check(lib().nemo_mpp_init(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, narea, int(key_mpp_mpi), C.byref(dom)))
+    return dom
+
+
+def mpp_basic_decomposition(jpiglo, jpjglo, jperio, jpni, jpnj):
+    """mpp_basic_decomposition (mppini.F90:695-798): (jpimax, jpjmax, nimppt, njmppt, nlcit, nlcjt), tables (jpnj, jpni)."""
+    n = jpni * jpnj
+    tabs = [np.zeros(n, np.int32) for _ in range(4)]
+    jpimax, jpjmax = C.c_int(), C.c_int()
+    ip = C.POINTER(C.c_int)
+    _check(lib().nemo_mpp_basic_decomposition(jpiglo, jpjglo, jperio, jpni, jpnj, C.byref(jpimax), C.byref(jpjmax),
+                                              *[t.ctypes.data_as(ip) for t in tabs]))
+    return (jpimax.value, jpjmax.value) + tuple(t.reshape(jpnj, jpni) for t in tabs)
+
+
+def lbc_plan(dom, cd_nat, peer):
+    """Compiled lbc_lnk gather plan of rank ``dom.narea`` for type ``cd_nat``: cells received from rank ``peer``
+    (0-based; -1 = land-value fills) as arrays (dst_index, src_index, sgn_power) of local indices (i-1)+(j-1)*jpi."""
+    L = lib()
+    n = L.nemo_lbc_plan_query(C.byref(dom), cd_nat.encode(), peer, None, None, None)
+    if n < 0:
+        _check(1)
+    dst, src, sp = (np.zeros(n, np.int32) for _ in range(3))
+    ip = C.POINTER(C.c_int)
+    if n:
+        L.nemo_lbc_plan_query(C.byref(dom), cd_nat.encode(), peer, dst.ctypes.data_as(ip), src.ctypes.data_as(ip),
+                              sp.ctypes.data_as(ip))
+    return dst, src, sp
+
+
+def comm_unique_id():
+    """ncclUniqueId (128 bytes) to broadcast from rank 0 (mynode/MPI_Init analogue, lib_mpp.F90:197-331)."""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    _check(lib().nemo_fct_comm_unique_id(buf))
+    return buf.raw
+
+
+class FctContext:
+    """One subdomain on one GPU: the device-resident state behind ``tra_adv_fct`` (created once, like nemo_alloc)."""
+
+    def __init__(self, dom, device=-1):
+        self.dom = dom
+        self._h = C.c_void_p()
+        _check(lib().nemo_fct_create(C.byref(dom), device, C.byref(self._h)))
+        self._keep = {}
+
+    # -- life cycle -------------------------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            lib().nemo_fct_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_domain_arrays(self, tmask, umask, vmask, wmask, e1e2t, r1_e1e2t, mikt, mbkt, ln_linssh=False, ln_isfcav=False):
+        """dom_oce.F90 module arrays (host numpy): masks (jpk,jpj,jpi), metrics (jpj,jpi), mikt/mbkt int32 (jpj,jpi)."""
+        for a in (tmask, umask, vmask, wmask):
+            assert tuple(a.shape) == self.dom.shape3, (a.shape, self.dom.shape3)
+        mikt = np.ascontiguousarray(mikt, np.int32)
+        mbkt = np.ascontiguousarray(mbkt, np.int32)
+        arrs = [np.ascontiguousarray(_f64(a, "set_domain_arrays")) for a in (tmask, umask, vmask, wmask, e1e2t, r1_e1e2t)]
+        _check(lib().nemo_fct_set_domain_arrays(self._h, *[_ptr(a) for a in arrs], _ptr(mikt), _ptr(mbkt),
+                                                int(ln_linssh), int(ln_isfcav)))
+
+    def set_e3t(self, e3t_b, e3t_n, e3t_a):
+        """e3t_b/n/a (jpk,jpj,jpi): numpy -> copied to the device; CUDA tensors -> borrowed in place."""
+        dev = _is_dev(e3t_n)
+        for a in (e3t_b, e3t_n, e3t_a):
+            assert tuple(a.shape) == self.dom.shape3 and _is_dev(a) == dev
+            _f64(a, "set_e3t")
+        if dev:
+            self._keep["e3t"] = (e3t_b, e3t_n, e3t_a)
+        _check(lib().nemo_fct_set_e3t(self._h, _ptr(e3t_b), _ptr(e3t_n), _ptr(e3t_a), int(dev)))
+
+    def set_stream(self, stream_ptr):
+        """run on the caller's CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``); None = own stream"""
+        _check(lib().nemo_fct_set_stream(self._h, C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def synchronize(self):
+        _check(lib().nemo_fct_synchronize(self._h))
+
+    def set_schedule(self, schedule):
+        _check(lib().nemo_fct_set_schedule(self._h, schedule))
+
+    def comm_init(self, unique_id, nranks, rank):
+        _check(lib().nemo_fct_comm_init(self._h, unique_id, nranks, rank))
+
+    def comm_report(self):
+        n, b = C.c_longlong(), C.c_longlong()
+        _check(lib().nemo_fct_comm_report(self._h, C.byref(n), C.byref(b)))
+        return n.value, b.value
+
+    # -- the hot path -----------------------------------------------------------------------------------------
+    def tra_adv_fct(self, kt, kit000, cdtype, p2dt, pun, pvn, pwn, ptb, ptn, pta, kjpt, kn_fct_h, kn_fct_v):
+        """tra_adv_fct( kt, kit000, cdtype, p2dt, pun, pvn, pwn, ptb, ptn, pta, kjpt, kn_fct_h, kn_fct_v )
+        (traadv_fct.F90:54-55).  pta is updated in place on (2:jpim1, 2:jpjm1, 1:jpkm1, :)."""
+        s3, s4 = self.dom.shape3, (kjpt,) + self.dom.shape3
+        dev = _is_dev(pta)
+        for a, shp in ((pun, s3), (pvn, s3), (pwn, s3), (ptb, s4), (ptn, s4), (pta, s4)):
+            if tuple(a.shape) != shp:
+                raise ValueError(f"tra_adv_fct: array of shape {tuple(a.shape)}, expected {shp}")
+            if _is_dev(a) != dev:
+                raise ValueError("tra_adv_fct: all arrays must live on the same side (all host or all device)")
+            _f64(a, "tra_adv_fct")
+        fn = lib().nemo_tra_adv_fct_dev if dev else lib().nemo_tra_adv_fct
+        _check(fn(self._h, kt, kit000, cdtype.encode(), float(p2dt), _ptr(pun), _ptr(pvn), _ptr(pwn), _ptr(ptb),
+                  _ptr(ptn), _ptr(pta), kjpt, kn_fct_h, kn_fct_v))
+
+    def interp_4th_cpt(self, pt_in, pt_out):
+        """interp_4th_cpt( pt_in, pt_out ) (traadv_fct.F90:517): pt_out defined on (2:jpim1,2:jpjm1,2:jpkm1)."""
+        dev = _is_dev(pt_in)
+        assert tuple(pt_in.shape) == self.dom.shape3 and tuple(pt_out.shape) == self.dom.shape3
+        fn = lib().nemo_interp_4th_cpt_dev if dev else lib().nemo_interp_4th_cpt
+        _check(fn(self._h, _ptr(_f64(pt_in, "interp_4th_cpt")), _ptr(_f64(pt_out, "interp_4th_cpt"))))
+
+    def tra_adv_transports(self, e2u, e1v, e3u_n, e3v_n, un, vn, wn, zun, zvn, zwn):
+        """zun = e2u*e3u_n*un, zvn = e1v*e3v_n*vn, zwn = e1e2t*wn (traadv.F90:100-124); device tensors only."""
+        arrs = (e2u, e1v, e3u_n, e3v_n, un, vn, wn, zun, zvn, zwn)
+        if not all(_is_dev(a) for a in arrs):
+            raise ValueError("tra_adv_transports: device tensors only")
+        _check(lib().nemo_tra_adv_transports_dev(self._h, *[_ptr(a) for a in arrs]))
+
+    def lbc_lnk_multi(self, cdname, *triplets, pval=None):
+        """lbc_lnk_multi( cdname, pt1, cdna1, psgn1 [, pt2, cdna2, psgn2, ...] [, pval] )
+        (lbc_lnk_multi_generic.h90:16-29).  Fields (ipk,jpj,jpi) or (jpj,jpi), all with the same ipk."""
+        assert len(triplets) % 3 == 0 and triplets
+        fields, nats, sgns = triplets[0::3], triplets[1::3], triplets[2::3]
+        nfld = len(fields)
+        jpj, jpi = self.dom.jpj, self.dom.jpi
+        ipk = None
+        for a in fields:
+            if tuple(a.shape[-2:]) != (jpj, jpi):
+                raise ValueError(f"lbc_lnk: field of shape {tuple(a.shape)}")
+            k = int(np.prod(a.shape[:-2])) if len(a.shape) > 2 else 1
+            if ipk is not None and k != ipk:
+                raise ValueError("lbc_lnk_multi: all fields must have the same number of levels")
+            ipk = k
+            _f64(a, "lbc_lnk")
+        dev = _is_dev(fields[0])
+        tab = (C.c_void_p * nfld)(*[_ptr(a) for a in fields])
+        sg = (C.c_double * nfld)(*[float(s) for s in sgns])
+        fn = lib().nemo_lbc_lnk_multi_dev if dev else lib().nemo_lbc_lnk_multi
+        _check(fn(self._h, cdname.encode(), nfld, tab, "".join(nats).encode(), sg, ipk, int(pval is not None),
+                  float(pval or 0.0)))
+
+    def lbc_lnk(self, cdname, pt, cd_nat, psgn, pval=None):
+        """lbc_lnk( cdname, ptab, cd_nat, psgn [, pval] ) (lbclnk.F90:21-29)"""
+        self.lbc_lnk_multi(cdname, pt, cd_nat, psgn, pval=pval)
+
+
+class LocalGroup:
+    """All jpni*jpnj subdomains of a layout inside ONE process on ONE GPU (decomposition tests on a single
+    device).  Collective calls take per-rank lists of device tensors."""
+
+    def __init__(self, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, device=0):
+        self.n = jpni * jpnj
+        self.doms = [mpp_init(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, r + 1) for r in range(self.n)]
+        self.ctx = [FctContext(d, device) for d in self.doms]
+        self._hs = (C.c_void_p * self.n)(*[c._h for c in self.ctx])
+        _check(lib().nemo_fct_comm_init_local(self._hs, self.n))
+
+    def close(self):
+        for c in self.ctx:
+            c.close()
+
+    def _tab(self, arrs):
+        return (C.c_void_p * self.n)(*[_ptr(a) for a in arrs])
+
+    def tra_adv_fct(self, kt, kit000, cdtype, p2dt, pun, pvn, pwn, ptb, ptn, pta, kjpt, kn_fct_h, kn_fct_v):
+        for lst in (pun, pvn, pwn, ptb, ptn, pta):
+            assert len(lst) == self.n and all(_is_dev(a) for a in lst)
+        _check(lib().nemo_group_tra_adv_fct_dev(self._hs, self.n, kt, kit000, cdtype.encode(), float(p2dt),
+                                                self._tab(pun), self._tab(pvn), self._tab(pwn), self._tab(ptb),
+                                                self._tab(ptn), self._tab(pta), kjpt, kn_fct_h, kn_fct_v))
+
+    def lbc_lnk_multi(self, cdname, fields, nats, sgns, pval=None):
+        """fields[f][rank]: device tensors (ipk,jpj,jpi)"""
+        nfld = len(fields)
+        ipk = int(np.prod(fields[0][0].shape[:-2])) if len(fields[0][0].shape) > 2 else 1
+        per_rank = [(C.c_void_p * nfld)(*[_ptr(fields[f][r]) for f in range(nfld)]) for r in range(self.n)]
+        tabs = (C.POINTER(C.c_void_p) * self.n)(*[C.cast(t, C.POINTER(C.c_void_p)) for t in per_rank])
+        sg = (C.c_double * nfld)(*[float(s) for s in sgns])
+        _check(lib().nemo_group_lbc_lnk_multi_dev(self._hs, self.n, cdname.encode(), nfld, tabs, "".join(nats).encode(),
+                                                  sg, ipk, int(pval is not None), float(pval or 0.0)))
+
+    def synchronize(self):
+        self.ctx[0].synchronize()

@@ -1,0 +1,63 @@
+// kernels.cuh -- launch interfaces of the sm_100a kernels of the FCT path (definitions in fct_kernels.cu and
+// lbc_kernels.cu).  All arrays are Fortran column-major fp64 (ji fastest); indices in comments are 1-based as in
+// the reference (src/OCE/TRA/traadv_fct.F90).  Everything is compiled with -fmad=false: the reference builds are
+// IEEE-strict without FMA contraction (arch/arch-linux_gfortran.fcm), and with the reference's operation order
+// kept inside each expression the results are bit-identical to the op-by-op CPU restatement (oracle/).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace nemo {
+
+struct FctArgs {
+    int jpi, jpj, jpk;
+    size_t jpij, n3;                       // jpi*jpj, jpi*jpj*jpk
+    // dom_oce module arrays
+    const double *tmask, *umask, *vmask, *wmask, *e3t_b, *e3t_n, *e3t_a, *e1e2t, *r1_e1e2t;
+    const int *mikt, *mbkt;
+    const double *cpt_zwt;                 // time-invariant Thomas pivots of interp_4th_cpt (traadv_fct.F90:577-588)
+    // tra_adv_fct arguments
+    const double *pun, *pvn, *pwn, *ptb, *ptn;
+    double *pta;
+    // work arrays (jpi,jpj,jpk,kjpt) -- the automatic arrays of traadv_fct.F90:86 and :351, batched over tracers
+    double *zwi, *zwx, *zwy, *zwz, *zltu, *zltv, *ztw, *zbetup, *zbetdo;
+    double p2dt;
+    int kjpt, kn_fct_h, kn_fct_v, ln_linssh, ln_isfcav;
+    int nkchunk;                           // the jk loop is split in nkchunk chunks across blockIdx.y
+};
+
+// P4 (order 4): zltu, zltv on (2:jpim1,2:jpjm1,1:jpkm1)                     traadv_fct.F90:195-208
+void launch_fct_laplacian(const FctArgs &a, cudaStream_t s);
+// P1-P5: upstream fluxes, low-order update (pta, zwi), anti-diffusive fluxes  traadv_fct.F90:123-278
+void launch_fct_low_antidiff(const FctArgs &a, cudaStream_t s);
+// nonosc P6: zbetup, zbetdo                                                 traadv_fct.F90:356-399
+void launch_fct_betas(const FctArgs &a, cudaStream_t s);
+// nonosc P7: limit zwx, zwy, zwz in place                                   traadv_fct.F90:404-425
+void launch_fct_limit(const FctArgs &a, cudaStream_t s);
+// P8: final trend                                                           traadv_fct.F90:288-297
+void launch_fct_final(const FctArgs &a, cudaStream_t s);
+// fused P7+P8 (schedule >= 1): no X4 exchange, limited fluxes recomputed at the 6 faces
+void launch_fct_limit_final(const FctArgs &a, cudaStream_t s);
+
+// interp_4th_cpt                                                            traadv_fct.F90:517-616
+void launch_cpt_pivots(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt,
+                       int ln_isfcav, double *zwt, cudaStream_t s);
+void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
+                           int ln_isfcav, const double *zwt, const double *pt_in, double *pt_out, cudaStream_t s);
+// tra_adv transports                                                        traadv.F90:100-124
+void launch_transports(int jpi, int jpj, int jpk, const double *e2u, const double *e1v, const double *e1e2t,
+                       const double *e3u_n, const double *e3v_n, const double *un, const double *vn,
+                       const double *wn, double *zun, double *zvn, double *zwn, cudaStream_t s);
+
+// ---- lbc_lnk on the device: gather plan execution -------------------------------------------------------------
+// One job = one (peer, field) pair: `ncell` cells x `nlev` levels.
+struct PackJob   { const double *field; const int *src; double *buf; int ncell; };                       // buf[k*ncell+c] = field[src[c] + k*jpij]
+struct UnpackJob { double *field; const int *dst; const int *spow; const double *buf; int ncell; double sgn; }; // field[dst[c]+k*jpij] = sgn^spow[c] * buf[k*ncell+c]
+struct FillJob   { double *field; const int *dst; const int *spow; int ncell; double sgn; double zland; };
+void launch_lbc_pack(const PackJob *jobs_dev, int njobs, int maxcell, int nlev, size_t jpij, cudaStream_t s);
+void launch_lbc_unpack(const UnpackJob *jobs_dev, int njobs, int maxcell, int nlev, size_t jpij, cudaStream_t s);
+void launch_lbc_fill(const FillJob *jobs_dev, int njobs, int maxcell, int nlev, size_t jpij, cudaStream_t s);
+
+long long kernel_launch_count();
+
+}  // namespace nemo

@@ -1,0 +1,794 @@
+// nemo_fct.cu -- device context, exchange engine and the extern "C" ABI of libnemo_fct.so (include/nemo_fct.h).
+//
+// One context = one subdomain on one GPU, created once (as nemo_alloc does for the Fortran module arrays,
+// src/OCE/nemogcm.F90:640-673).  Work arrays, exchange buffers and job tables are persistent; a step is a fixed
+// sequence of kernel launches on one CUDA stream, so the host side is launch-only (graph-capturable).
+// Multi-GPU: one process per GPU, halo strips and the north fold move with ncclSend/ncclRecv (NCCL is loaded
+// with dlopen so that the library also loads on a machine without NCCL / without a GPU for the ABI tests).
+// There is no CPU fallback anywhere: without a usable CUDA device every compute entry point fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nemo_fct.h"
+#include "kernels.cuh"
+#include "layout.hpp"
+
+using namespace nemo;
+
+// ------------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CUTHROW(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// NCCL through dlopen (only the p2p subset is used)
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct NcclUid { char b[NEMO_FCT_UNIQUE_ID_BYTES]; };                  // ncclUniqueId, passed by value
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int kNcclFloat64 = 8;   // ncclDouble, nccl.h
+
+int load_nccl()
+{
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+    if (!g_nccl.lib) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(f) *(void **)(&g_nccl.f) = dlsym(g_nccl.lib, "nccl" #f); if (!g_nccl.f) return fail("libnccl: missing symbol nccl" #f)
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+#undef SYM
+    return 0;
+}
+#define NC(call) do { int r_ = (call); if (r_ != 0) return fail("%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); } while (0)
+
+inline int nat_slot(char c)
+{
+    switch (c) { case 'T': case 'W': return 0; case 'U': return 1; case 'V': return 2; case 'F': return 3; default: return -1; }
+}
+const char kSlotNat[4] = {'T', 'U', 'V', 'F'};
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    void alloc(size_t count) { release(); if (count) { CUTHROW(cudaMalloc(&p, count * sizeof(T))); } n = count; }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void upload(const std::vector<T> &h) { alloc(h.size()); if (!h.empty()) CUTHROW(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    ~DevBuf() { release(); }
+    DevBuf() = default; DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct DevPeer { int peer = -1; int ncell = 0; DevBuf<int> a, b; };   // send: a = src ; recv: a = dst, b = spow
+struct DevPlan {
+    bool built = false;
+    std::vector<std::unique_ptr<DevPeer>> send, recv;
+    DevPeer fill;                                                      // a = dst, b = spow
+    const DevPeer *find(const std::vector<std::unique_ptr<DevPeer>> &v, int peer) const {
+        for (auto &p : v) if (p->peer == peer) return p.get();
+        return nullptr;
+    }
+};
+
+struct JobTables {                                                     // one cached exchange
+    DevBuf<PackJob> pack; DevBuf<UnpackJob> unpack; DevBuf<FillJob> fill;
+    int npack = 0, nunpack = 0, nfill = 0, maxpack = 0, maxunpack = 0, maxfill = 0, nlev = 0;
+    std::vector<size_t> send_off, send_cnt, recv_off, recv_cnt;        // per peer rank, in doubles
+};
+}  // namespace
+
+struct nemo_fct_ctx {
+    nemo_fct_domain dom{};
+    Layout L;
+    int device = 0, rank = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    size_t jpij = 0, n3 = 0;
+    // dom_oce arrays
+    DevBuf<double> tmask, umask, vmask, wmask, e1e2t, r1_e1e2t, e3t_own[3], cpt_zwt;
+    DevBuf<int> mikt, mbkt;
+    const double *e3t[3] = {nullptr, nullptr, nullptr};
+    bool have_dom = false;
+    int ln_linssh = 0, ln_isfcav = 0;
+    // work arrays (batched over tracers)
+    int kjpt_cap = 0; bool have_h4 = false, have_v4 = false;
+    DevBuf<double> zwi, zwx, zwy, zwz, zltu, zltv, ztw, zbetup, zbetdo;
+    // host-variant staging
+    int stage_kjpt = 0;
+    DevBuf<double> s_pun, s_pvn, s_pwn, s_ptb, s_ptn, s_pta, s_e3t[3], s_cpt_in, s_cpt_out;
+    std::vector<std::unique_ptr<DevBuf<double>>> s_lbc;
+    // exchange engine
+    DevPlan plan[4];
+    DevBuf<double> sendbuf, recvbuf;
+    std::map<std::string, std::unique_ptr<JobTables>> jobcache;
+    std::vector<nemo_fct_ctx *> group;                                 // in-process communicator (incl. self)
+    void *nccl_comm = nullptr; int nccl_nranks = 0;
+    long long n_exchanges = 0, bytes_sent = 0;
+    int schedule = 0;
+};
+typedef nemo_fct_ctx Ctx;
+
+// ------------------------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------------------------
+static void build_plan(Ctx *c, int slot)
+{
+    if (c->plan[slot].built) return;
+    std::vector<RankPlan> all = compile_lbc_plan(c->L, kSlotNat[slot]);
+    const RankPlan &rp = all[c->rank];
+    DevPlan &dp = c->plan[slot];
+    for (const PeerList &pl : rp.send) {
+        auto d = std::make_unique<DevPeer>(); d->peer = pl.peer; d->ncell = (int)pl.cells.size();
+        std::vector<int> src(pl.cells.size());
+        for (size_t i = 0; i < pl.cells.size(); ++i) src[i] = pl.cells[i].src;
+        d->a.upload(src); dp.send.push_back(std::move(d));
+    }
+    for (const PeerList &pl : rp.recv) {
+        auto d = std::make_unique<DevPeer>(); d->peer = pl.peer; d->ncell = (int)pl.cells.size();
+        std::vector<int> dst(pl.cells.size()), sp(pl.cells.size());
+        for (size_t i = 0; i < pl.cells.size(); ++i) { dst[i] = pl.cells[i].dst; sp[i] = pl.cells[i].spow; }
+        d->a.upload(dst); d->b.upload(sp); dp.recv.push_back(std::move(d));
+    }
+    {
+        std::vector<int> dst(rp.fill.size()), sp(rp.fill.size());
+        for (size_t i = 0; i < rp.fill.size(); ++i) { dst[i] = rp.fill[i].dst; sp[i] = rp.fill[i].spow; }
+        dp.fill.ncell = (int)rp.fill.size(); dp.fill.a.upload(dst); dp.fill.b.upload(sp);
+    }
+    dp.built = true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// exchange engine: lbc_lnk_multi on device arrays for a set of in-process subdomains (size 1 with NCCL)
+// ------------------------------------------------------------------------------------------------------------
+struct LnkCall { int nfld; std::vector<std::vector<double *>> ptab; std::string nat; std::vector<double> sgn; int nlev; int has_pval; double pval; };
+
+static int peer_ncell(const DevPlan &p, bool send, int peer)
+{
+    const DevPeer *d = p.find(send ? p.send : p.recv, peer);
+    return d ? d->ncell : 0;
+}
+
+static int lbc_exchange(std::vector<Ctx *> &g, const LnkCall &call)
+{
+    const int ng = (int)g.size();
+    if (call.nfld < 1 || call.nfld > 64) return fail("lbc_lnk_multi: nfld = %d out of range", call.nfld);
+    std::vector<int> slots(call.nfld);
+    for (int f = 0; f < call.nfld; ++f) {
+        slots[f] = nat_slot(call.nat[f]);
+        if (slots[f] < 0) return fail("lbc_lnk_multi: cd_nat '%c' is not one of T,U,V,W,F", call.nat[f]);
+    }
+    std::vector<JobTables *> jt(ng, nullptr);
+    std::vector<bool> fresh(ng, false);
+    try {
+        // pass 1a: plans, message sizes, persistent buffers (growing a buffer invalidates every cached job table
+        // of the in-process group, because peers' tables point into it)
+        std::vector<std::vector<size_t>> scnt(ng), rcnt(ng);
+        bool grown = false;
+        for (int m = 0; m < ng; ++m) {
+            Ctx *c = g[m];
+            CUTHROW(cudaSetDevice(c->device));
+            for (int s : slots) build_plan(c, s);
+            const int nr = c->L.jpnij;
+            scnt[m].assign(nr, 0); rcnt[m].assign(nr, 0);
+            size_t so = 0, ro = 0;
+            for (int p = 0; p < nr; ++p) {
+                for (int f = 0; f < call.nfld; ++f) {
+                    scnt[m][p] += (size_t)call.nlev * peer_ncell(c->plan[slots[f]], true, p);
+                    rcnt[m][p] += (size_t)call.nlev * peer_ncell(c->plan[slots[f]], false, p);
+                }
+                so += scnt[m][p]; ro += rcnt[m][p];
+            }
+            if (so > c->sendbuf.n || ro > c->recvbuf.n) {
+                CUTHROW(cudaStreamSynchronize(c->stream));
+                if (so > c->sendbuf.n) c->sendbuf.alloc(so + so / 4);
+                if (ro > c->recvbuf.n) c->recvbuf.alloc(ro + ro / 4);
+                grown = true;
+            }
+        }
+        if (grown) for (Ctx *c : g) { CUTHROW(cudaStreamSynchronize(c->stream)); c->jobcache.clear(); }
+        // pass 1b: cached job tables
+        for (int m = 0; m < ng; ++m) {
+            Ctx *c = g[m];
+            std::string key((const char *)call.ptab[m].data(), call.ptab[m].size() * sizeof(double *));
+            key += call.nat; key.append((const char *)call.sgn.data(), call.sgn.size() * sizeof(double));
+            key.append((const char *)&call.nlev, sizeof(int)); key.append((const char *)&call.has_pval, sizeof(int));
+            key.append((const char *)&call.pval, sizeof(double));
+            for (Ctx *o : g) key.append((const char *)&o, sizeof(Ctx *));
+            auto it = c->jobcache.find(key);
+            if (it == c->jobcache.end()) {
+                if (c->jobcache.size() > 64) {                          // unbounded distinct calls: start over
+                    for (Ctx *o : g) { CUTHROW(cudaStreamSynchronize(o->stream)); o->jobcache.clear(); }
+                    for (int q = 0; q < m; ++q) fresh[q] = true;
+                }
+                it = c->jobcache.emplace(key, std::make_unique<JobTables>()).first;
+                fresh[m] = true;
+                JobTables &t = *it->second;
+                const int nr = c->L.jpnij;
+                t.send_cnt = scnt[m]; t.recv_cnt = rcnt[m];
+                t.send_off.assign(nr, 0); t.recv_off.assign(nr, 0);
+                size_t so = 0, ro = 0;
+                for (int p = 0; p < nr; ++p) { t.send_off[p] = so; so += t.send_cnt[p]; t.recv_off[p] = ro; ro += t.recv_cnt[p]; }
+            }
+            jt[m] = it->second.get();
+        }
+        // a fresh table anywhere in an in-process group: peers' unpack jobs read its send offsets, rebuild all
+        bool any_fresh = false; for (int m = 0; m < ng; ++m) any_fresh = any_fresh || fresh[m];
+        if (any_fresh && ng > 1) for (int m = 0; m < ng; ++m) fresh[m] = true;
+        // pass 2: job tables
+        for (int m = 0; m < ng; ++m) {
+            if (!fresh[m]) continue;
+            Ctx *c = g[m]; JobTables &t = *jt[m];
+            CUTHROW(cudaSetDevice(c->device));
+            std::vector<PackJob> pj; std::vector<UnpackJob> uj; std::vector<FillJob> fj;
+            t.maxpack = t.maxunpack = t.maxfill = 0; t.nlev = call.nlev;
+            const int nr = c->L.jpnij;
+            for (int p = 0; p < nr; ++p) {
+                size_t off = t.send_off[p];
+                for (int f = 0; f < call.nfld; ++f) {
+                    const DevPeer *d = c->plan[slots[f]].find(c->plan[slots[f]].send, p);
+                    if (!d || d->ncell == 0) continue;
+                    pj.push_back(PackJob{call.ptab[m][f], d->a.p, c->sendbuf.p + off, d->ncell});
+                    t.maxpack = std::max(t.maxpack, d->ncell);
+                    off += (size_t)call.nlev * d->ncell;
+                }
+            }
+            for (int p = 0; p < nr; ++p) {
+                // where do the data from rank p arrive?  own rank / in-process peer: read the sender's send buffer
+                const double *base = nullptr;
+                if (p == c->rank) base = c->sendbuf.p + t.send_off[p];
+                else {
+                    Ctx *peer = nullptr; int pm = -1;
+                    for (int q = 0; q < ng; ++q) if (g[q]->rank == p) { peer = g[q]; pm = q; }
+                    if (peer) base = peer->sendbuf.p + jt[pm]->send_off[c->rank];
+                    else base = c->recvbuf.p + t.recv_off[p];
+                }
+                size_t off = 0;
+                for (int f = 0; f < call.nfld; ++f) {
+                    const DevPeer *d = c->plan[slots[f]].find(c->plan[slots[f]].recv, p);
+                    if (!d || d->ncell == 0) continue;
+                    uj.push_back(UnpackJob{call.ptab[m][f], d->a.p, d->b.p, base + off, d->ncell, call.sgn[f]});
+                    t.maxunpack = std::max(t.maxunpack, d->ncell);
+                    off += (size_t)call.nlev * d->ncell;
+                }
+            }
+            for (int f = 0; f < call.nfld; ++f) {
+                const DevPeer &d = c->plan[slots[f]].fill;
+                if (d.ncell == 0) continue;
+                fj.push_back(FillJob{call.ptab[m][f], d.a.p, d.b.p, d.ncell, call.sgn[f], call.has_pval ? call.pval : 0.0});
+                t.maxfill = std::max(t.maxfill, d.ncell);
+            }
+            t.npack = (int)pj.size(); t.nunpack = (int)uj.size(); t.nfill = (int)fj.size();
+            t.pack.upload(pj); t.unpack.upload(uj); t.fill.upload(fj);
+        }
+    } catch (const std::exception &e) { return fail("lbc_lnk_multi: %s", e.what()); }
+
+    // ---- run: pack everywhere, move, then fill + unpack everywhere (all sources are pre-exchange values)
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m]; JobTables &t = *jt[m];
+        CU(cudaSetDevice(c->device));
+        launch_lbc_pack(t.pack.p, t.npack, t.maxpack, t.nlev, c->jpij, c->stream);
+    }
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m]; JobTables &t = *jt[m];
+        const int nr = c->L.jpnij;
+        bool remote = false;
+        for (int p = 0; p < nr; ++p) {
+            bool local = false; for (Ctx *o : g) local = local || (o->rank == p);
+            if (!local && (t.send_cnt[p] || t.recv_cnt[p])) remote = true;
+        }
+        c->n_exchanges++;
+        if (!remote) continue;
+        if (!c->nccl_comm) return fail("lbc_lnk_multi: rank %d needs remote neighbours but nemo_fct_comm_init was not called", c->rank);
+        CU(cudaSetDevice(c->device));
+        NC(g_nccl.GroupStart());
+        for (int p = 0; p < nr; ++p) {
+            bool local = false; for (Ctx *o : g) local = local || (o->rank == p);
+            if (local) continue;
+            if (t.send_cnt[p]) { NC(g_nccl.Send(c->sendbuf.p + t.send_off[p], t.send_cnt[p], kNcclFloat64, p, c->nccl_comm, c->stream)); c->bytes_sent += (long long)t.send_cnt[p] * 8; }
+            if (t.recv_cnt[p]) NC(g_nccl.Recv(c->recvbuf.p + t.recv_off[p], t.recv_cnt[p], kNcclFloat64, p, c->nccl_comm, c->stream));
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m]; JobTables &t = *jt[m];
+        CU(cudaSetDevice(c->device));
+        launch_lbc_fill(t.fill.p, t.nfill, t.maxfill, t.nlev, c->jpij, c->stream);
+        launch_lbc_unpack(t.unpack.p, t.nunpack, t.maxunpack, t.nlev, c->jpij, c->stream);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FCT step over a set of in-process subdomains
+// ------------------------------------------------------------------------------------------------------------
+struct FctCall { const double *pun, *pvn, *pwn, *ptb, *ptn; double *pta; };
+
+static int ensure_work(Ctx *c, int kjpt, int h, int v)
+{
+    try {
+        CUTHROW(cudaSetDevice(c->device));
+        const size_t n = c->n3 * (size_t)kjpt;
+        if (kjpt > c->kjpt_cap) {
+            CUTHROW(cudaStreamSynchronize(c->stream));
+            c->jobcache.clear();
+            DevBuf<double> *arrs[] = {&c->zwi, &c->zwx, &c->zwy, &c->zwz, &c->zbetup, &c->zbetdo};
+            for (auto *a : arrs) { a->alloc(n); CUTHROW(cudaMemset(a->p, 0, n * sizeof(double))); }
+            c->kjpt_cap = kjpt; c->have_h4 = c->have_v4 = false; c->zltu.release(); c->zltv.release(); c->ztw.release();
+        }
+        const size_t ncap = c->n3 * (size_t)c->kjpt_cap;
+        if (h == 4 && !c->have_h4) {
+            c->zltu.alloc(ncap); c->zltv.alloc(ncap);
+            CUTHROW(cudaMemset(c->zltu.p, 0, ncap * sizeof(double))); CUTHROW(cudaMemset(c->zltv.p, 0, ncap * sizeof(double)));
+            c->have_h4 = true;
+        }
+        if (v == 4 && !c->have_v4) {
+            c->ztw.alloc(ncap); CUTHROW(cudaMemset(c->ztw.p, 0, ncap * sizeof(double)));
+            c->have_v4 = true;
+        }
+    } catch (const std::exception &e) { return fail("tra_adv_fct: allocating work arrays: %s", e.what()); }
+    return 0;
+}
+
+static int pick_nkchunk(const Ctx *c, int kjpt)
+{
+    const long long ncol = (long long)(c->dom.jpi - 2) * (c->dom.jpj - 2) * kjpt;
+    const long long want = 148LL * 2048 * 3;                           // ~3 waves of resident threads on 148 SMs
+    long long n = (want + ncol - 1) / ncol;
+    const int kmax = std::max(1, (c->dom.jpk - 1) / 8);                // keep >= 8 levels per chunk
+    if (n < 1) n = 1;
+    if (n > kmax) n = kmax;
+    return (int)n;
+}
+
+static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, double p2dt, int kjpt, int h, int v)
+{
+    const int ng = (int)g.size();
+    if (kjpt < 1) return fail("tra_adv_fct: kjpt = %d", kjpt);
+    if ((h != 2 && h != 4) || (v != 2 && v != 4))
+        return fail("tra_adv_fct: kn_fct_h = %d, kn_fct_v = %d: only 2 and 4 are supported (41 is untested in the reference)", h, v);
+    std::vector<FctArgs> fa(ng);
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m];
+        if (!c->have_dom) return fail("tra_adv_fct: nemo_fct_set_domain_arrays has not been called");
+        if (!c->e3t[0] || !c->e3t[1] || !c->e3t[2]) return fail("tra_adv_fct: nemo_fct_set_e3t has not been called");
+        if (c->dom.jpk < 3) return fail("tra_adv_fct: jpk must be >= 3");
+        if (ensure_work(c, kjpt, h, v)) return 1;
+        FctArgs &a = fa[m];
+        a.jpi = c->dom.jpi; a.jpj = c->dom.jpj; a.jpk = c->dom.jpk; a.jpij = c->jpij; a.n3 = c->n3;
+        a.tmask = c->tmask.p; a.umask = c->umask.p; a.vmask = c->vmask.p; a.wmask = c->wmask.p;
+        a.e3t_b = c->e3t[0]; a.e3t_n = c->e3t[1]; a.e3t_a = c->e3t[2]; a.e1e2t = c->e1e2t.p; a.r1_e1e2t = c->r1_e1e2t.p;
+        a.mikt = c->mikt.p; a.mbkt = c->mbkt.p; a.cpt_zwt = c->cpt_zwt.p;
+        a.pun = args[m].pun; a.pvn = args[m].pvn; a.pwn = args[m].pwn; a.ptb = args[m].ptb; a.ptn = args[m].ptn; a.pta = args[m].pta;
+        a.zwi = c->zwi.p; a.zwx = c->zwx.p; a.zwy = c->zwy.p; a.zwz = c->zwz.p; a.zltu = c->zltu.p; a.zltv = c->zltv.p;
+        a.ztw = c->ztw.p; a.zbetup = c->zbetup.p; a.zbetdo = c->zbetdo.p;
+        a.p2dt = p2dt; a.kjpt = kjpt; a.kn_fct_h = h; a.kn_fct_v = v; a.ln_linssh = c->ln_linssh; a.ln_isfcav = c->ln_isfcav;
+        a.nkchunk = pick_nkchunk(c, kjpt);
+    }
+    auto exch = [&](const std::vector<DevBuf<double> Ctx::*> &fields, const char *nat, const std::vector<double> &sgn) {
+        LnkCall call; call.nfld = (int)fields.size(); call.nat = nat; call.sgn = sgn; call.has_pval = 0; call.pval = 0.0;
+        call.nlev = g[0]->dom.jpk * kjpt;
+        call.ptab.resize(ng);
+        for (int m = 0; m < ng; ++m) for (auto f : fields) call.ptab[m].push_back((g[m]->*f).p);
+        return lbc_exchange(g, call);
+    };
+#define EACH(stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); stmt; }
+    if (h == 4) {
+        EACH(launch_fct_laplacian(fa[m], c->stream));
+        if (exch({&Ctx::zltu, &Ctx::zltv}, "TT", {1.0, 1.0})) return 1;                            // X1 (:209)
+    }
+    if (v == 4) {
+        EACH(launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p,
+                                   c->ln_isfcav, c->cpt_zwt.p, fa[m].ptn, c->ztw.p, c->stream));
+    }
+    EACH(launch_fct_low_antidiff(fa[m], c->stream));
+    if (exch({&Ctx::zwi, &Ctx::zwx, &Ctx::zwy, &Ctx::zwz}, "TUVW", {1.0, -1.0, -1.0, 1.0})) return 1;   // X2 (:280)
+    EACH(launch_fct_betas(fa[m], c->stream));
+    if (exch({&Ctx::zbetup, &Ctx::zbetdo}, "TT", {1.0, 1.0})) return 1;                            // X3 (:400)
+    EACH(launch_fct_limit(fa[m], c->stream));
+    if (exch({&Ctx::zwx, &Ctx::zwy}, "UV", {-1.0, -1.0})) return 1;                                // X4 (:426)
+    EACH(launch_fct_final(fa[m], c->stream));
+#undef EACH
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *nemo_fct_last_error(void) { return g_err.c_str(); }
+int nemo_fct_abi_version(void) { return NEMO_FCT_ABI_VERSION; }
+long long nemo_fct_launch_count(void) { return kernel_launch_count(); }
+
+int nemo_mpp_init(int jpiglo, int jpjglo, int jpk, int jperio, int jpni, int jpnj, int narea, int key_mpp_mpi,
+                  nemo_fct_domain *out)
+{
+    if (!out) return fail("nemo_mpp_init: out is NULL");
+    try { *out = rank_domain(make_layout(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, key_mpp_mpi != 0), narea); }
+    catch (const std::exception &e) { return fail("%s", e.what()); }
+    return 0;
+}
+
+int nemo_mpp_basic_decomposition(int jpiglo, int jpjglo, int jperio, int jpni, int jpnj, int *jpimax, int *jpjmax,
+                                 int *nimppt, int *njmppt, int *nlcit, int *nlcjt)
+{
+    try {
+        Layout L = make_layout(jpiglo, jpjglo, 3, jperio, jpni, jpnj, true);
+        if (jpimax) *jpimax = L.jpimax;
+        if (jpjmax) *jpjmax = L.jpjmax;
+        for (int r = 0; r < L.jpnij; ++r) {
+            if (nimppt) nimppt[r] = L.nimppt[r];
+            if (njmppt) njmppt[r] = L.njmppt[r];
+            if (nlcit) nlcit[r] = L.nlcit[r];
+            if (nlcjt) nlcjt[r] = L.nlcjt[r];
+        }
+    } catch (const std::exception &e) { return fail("%s", e.what()); }
+    return 0;
+}
+
+int nemo_lbc_plan_query(const nemo_fct_domain *dom, char cd_nat, int peer, int *dst_index, int *src_index, int *sgn_power)
+{
+    // returns the cell count (>= 0) or -1 on error
+    if (!dom) { fail("nemo_lbc_plan_query: dom is NULL"); return -1; }
+    try {
+        Layout L = make_layout(dom->jpiglo, dom->jpjglo, dom->jpk, dom->jperio, dom->jpni, dom->jpnj, dom->key_mpp_mpi != 0);
+        std::vector<RankPlan> all = compile_lbc_plan(L, cd_nat);
+        const RankPlan &rp = all.at(dom->narea - 1);
+        const std::vector<PlanCell> *cells = nullptr;
+        if (peer == -1) cells = &rp.fill;
+        else for (const PeerList &pl : rp.recv) if (pl.peer == peer) cells = &pl.cells;
+        if (!cells) return 0;
+        for (size_t i = 0; i < cells->size(); ++i) {
+            if (dst_index) dst_index[i] = (*cells)[i].dst;
+            if (src_index) src_index[i] = (*cells)[i].src;
+            if (sgn_power) sgn_power[i] = (*cells)[i].spow;
+        }
+        return (int)cells->size();
+    } catch (const std::exception &e) { fail("%s", e.what()); return -1; }
+}
+
+int nemo_fct_create(const nemo_fct_domain *dom, int device, nemo_fct_handle *out)
+{
+    if (!dom || !out) return fail("nemo_fct_create: NULL argument");
+    *out = nullptr;
+    Layout L;
+    try { L = make_layout(dom->jpiglo, dom->jpjglo, dom->jpk, dom->jperio, dom->jpni, dom->jpnj, dom->key_mpp_mpi != 0); }
+    catch (const std::exception &e) { return fail("%s", e.what()); }
+    std::string bad = check_domain(L, *dom);
+    if (!bad.empty()) return fail("nemo_fct_create: %s", bad.c_str());
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return fail("nemo_fct_create: no usable CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0) { const char *lr = getenv("LOCAL_RANK"); device = lr ? atoi(lr) % ndev : 0; }
+    if (device >= ndev) return fail("nemo_fct_create: device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("nemo_fct_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    Ctx *c = new Ctx();
+    c->dom = *dom; c->L = L; c->device = device; c->rank = dom->narea - 1;
+    c->jpij = (size_t)dom->jpi * dom->jpj; c->n3 = c->jpij * dom->jpk;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
+    c->stream = c->own_stream;
+    c->group = {c};
+    *out = c;
+    return 0;
+}
+
+int nemo_fct_destroy(nemo_fct_handle h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+    for (Ctx *o : h->group) if (o != h) {                              // leave the in-process communicator
+        std::vector<Ctx *> ng; for (Ctx *q : o->group) if (q != h) ng.push_back(q);
+        o->group = ng; o->jobcache.clear();
+    }
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+int nemo_fct_set_stream(nemo_fct_handle h, void *cuda_stream)
+{
+    if (!h) return fail("NULL handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    for (Ctx *o : h->group) o->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->group[0]->own_stream;
+    return 0;
+}
+
+int nemo_fct_synchronize(nemo_fct_handle h)
+{
+    if (!h) return fail("NULL handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int nemo_fct_set_schedule(nemo_fct_handle h, int schedule)
+{
+    if (!h) return fail("NULL handle");
+    if (schedule < 0 || schedule > 0) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
+    h->schedule = schedule;
+    return 0;
+}
+
+int nemo_fct_set_domain_arrays(nemo_fct_handle h, const double *tmask, const double *umask, const double *vmask,
+                               const double *wmask, const double *e1e2t, const double *r1_e1e2t, const int *mikt,
+                               const int *mbkt, int ln_linssh, int ln_isfcav)
+{
+    if (!h) return fail("NULL handle");
+    if (!tmask || !umask || !vmask || !wmask || !e1e2t || !r1_e1e2t || !mikt || !mbkt) return fail("nemo_fct_set_domain_arrays: NULL array");
+    // mikt/mbkt feed level indices on the device: validate them here (1 <= mikt, mbkt <= jpk-1 as domzgr.F90:292-294 builds them)
+    for (size_t i = 0; i < h->jpij; ++i)
+        if (mikt[i] < 1 || mikt[i] > h->dom.jpk - 1 || mbkt[i] < 1 || mbkt[i] > h->dom.jpk - 1)
+            return fail("nemo_fct_set_domain_arrays: mikt/mbkt out of 1..jpk-1 at horizontal index %zu", i);
+    CU(cudaSetDevice(h->device));
+    try {
+        CUTHROW(cudaStreamSynchronize(h->stream));
+        struct { DevBuf<double> *d; const double *s; size_t n; } v[] = {
+            {&h->tmask, tmask, h->n3}, {&h->umask, umask, h->n3}, {&h->vmask, vmask, h->n3}, {&h->wmask, wmask, h->n3},
+            {&h->e1e2t, e1e2t, h->jpij}, {&h->r1_e1e2t, r1_e1e2t, h->jpij}};
+        for (auto &x : v) { x.d->alloc(x.n); CUTHROW(cudaMemcpy(x.d->p, x.s, x.n * sizeof(double), cudaMemcpyHostToDevice)); }
+        h->mikt.alloc(h->jpij); h->mbkt.alloc(h->jpij);
+        CUTHROW(cudaMemcpy(h->mikt.p, mikt, h->jpij * sizeof(int), cudaMemcpyHostToDevice));
+        CUTHROW(cudaMemcpy(h->mbkt.p, mbkt, h->jpij * sizeof(int), cudaMemcpyHostToDevice));
+        h->ln_linssh = ln_linssh; h->ln_isfcav = ln_isfcav;
+        h->cpt_zwt.alloc(h->n3);
+        CUTHROW(cudaMemset(h->cpt_zwt.p, 0, h->n3 * sizeof(double)));
+        launch_cpt_pivots(h->dom.jpi, h->dom.jpj, h->dom.jpk, h->wmask.p, h->mikt.p, h->mbkt.p, ln_isfcav, h->cpt_zwt.p, h->stream);
+        CUTHROW(cudaStreamSynchronize(h->stream));
+        CUTHROW(cudaGetLastError());
+    } catch (const std::exception &e) { return fail("nemo_fct_set_domain_arrays: %s", e.what()); }
+    h->have_dom = true;
+    return 0;
+}
+
+int nemo_fct_set_e3t(nemo_fct_handle h, const double *e3t_b, const double *e3t_n, const double *e3t_a, int is_device)
+{
+    if (!h) return fail("NULL handle");
+    if (!e3t_b || !e3t_n || !e3t_a) return fail("nemo_fct_set_e3t: NULL array");
+    CU(cudaSetDevice(h->device));
+    const double *src[3] = {e3t_b, e3t_n, e3t_a};
+    if (is_device) { for (int i = 0; i < 3; ++i) h->e3t[i] = src[i]; return 0; }
+    try {
+        for (int i = 0; i < 3; ++i) {
+            if (h->e3t_own[i].n != h->n3) h->e3t_own[i].alloc(h->n3);
+            CUTHROW(cudaMemcpyAsync(h->e3t_own[i].p, src[i], h->n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            h->e3t[i] = h->e3t_own[i].p;
+        }
+        CUTHROW(cudaStreamSynchronize(h->stream));
+    } catch (const std::exception &e) { return fail("nemo_fct_set_e3t: %s", e.what()); }
+    return 0;
+}
+
+int nemo_fct_comm_unique_id(void *id128)
+{
+    if (!id128) return fail("NULL id");
+    if (load_nccl()) return 1;
+    NC(g_nccl.GetUniqueId(id128));
+    return 0;
+}
+
+int nemo_fct_comm_init(nemo_fct_handle h, const void *id128, int nranks, int rank)
+{
+    if (!h || !id128) return fail("NULL argument");
+    if (nranks != h->L.jpnij) return fail("nemo_fct_comm_init: nranks = %d but jpni*jpnj = %d", nranks, h->L.jpnij);
+    if (rank != h->rank) return fail("nemo_fct_comm_init: rank = %d but narea-1 = %d", rank, h->rank);
+    if (load_nccl()) return 1;
+    CU(cudaSetDevice(h->device));
+    NcclUid uid; memcpy(uid.b, id128, sizeof uid.b);
+    NC(g_nccl.CommInitRank(&h->nccl_comm, nranks, uid, rank));
+    h->nccl_nranks = nranks;
+    return 0;
+}
+
+int nemo_fct_comm_init_local(nemo_fct_handle *hs, int n)
+{
+    if (!hs || n < 1) return fail("nemo_fct_comm_init_local: bad arguments");
+    if (n != hs[0]->L.jpnij) return fail("nemo_fct_comm_init_local: %d subdomains given but jpni*jpnj = %d", n, hs[0]->L.jpnij);
+    std::vector<Ctx *> g(hs, hs + n);
+    for (int m = 0; m < n; ++m) {
+        if (!hs[m]) return fail("NULL handle");
+        if (hs[m]->rank != m) return fail("nemo_fct_comm_init_local: hs[%d] has narea-1 = %d (handles must be in rank order)", m, hs[m]->rank);
+        if (hs[m]->device != hs[0]->device) return fail("nemo_fct_comm_init_local: all subdomains must be on one device");
+    }
+    for (int m = 0; m < n; ++m) { g[m]->group = g; g[m]->jobcache.clear(); g[m]->stream = g[0]->stream; }
+    return 0;
+}
+
+int nemo_fct_comm_report(nemo_fct_handle h, long long *n_exchanges, long long *bytes_sent)
+{
+    if (!h) return fail("NULL handle");
+    if (n_exchanges) *n_exchanges = h->n_exchanges;
+    if (bytes_sent) *bytes_sent = h->bytes_sent;
+    return 0;
+}
+
+static int need_single(Ctx *h, const char *what)
+{
+    if (!h) return fail("NULL handle");
+    if (h->group.size() != 1) return fail("%s: this subdomain belongs to an in-process communicator, use the nemo_group_* entry point", what);
+    return 0;
+}
+
+int nemo_tra_adv_fct_dev(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
+                         const double *pvn, const double *pwn, const double *ptb, const double *ptn, double *pta,
+                         int kjpt, int kn_fct_h, int kn_fct_v)
+{
+    (void)kt; (void)kit000; (void)cdtype;
+    if (need_single(h, "nemo_tra_adv_fct_dev")) return 1;
+    if (!pun || !pvn || !pwn || !ptb || !ptn || !pta) return fail("tra_adv_fct: NULL array");
+    std::vector<Ctx *> g = {h};
+    return run_fct(g, {FctCall{pun, pvn, pwn, ptb, ptn, pta}}, p2dt, kjpt, kn_fct_h, kn_fct_v);
+}
+
+int nemo_group_tra_adv_fct_dev(nemo_fct_handle *hs, int n, int kt, int kit000, const char *cdtype, double p2dt,
+                               const double *const *pun, const double *const *pvn, const double *const *pwn,
+                               const double *const *ptb, const double *const *ptn, double *const *pta, int kjpt,
+                               int kn_fct_h, int kn_fct_v)
+{
+    (void)kt; (void)kit000; (void)cdtype;
+    if (!hs || n < 1) return fail("bad arguments");
+    std::vector<Ctx *> g(hs, hs + n);
+    if ((int)g[0]->group.size() != n) return fail("nemo_group_tra_adv_fct_dev: call nemo_fct_comm_init_local first");
+    std::vector<FctCall> a(n);
+    for (int m = 0; m < n; ++m) a[m] = FctCall{pun[m], pvn[m], pwn[m], ptb[m], ptn[m], pta[m]};
+    return run_fct(g, a, p2dt, kjpt, kn_fct_h, kn_fct_v);
+}
+
+int nemo_tra_adv_fct(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
+                     const double *pvn, const double *pwn, const double *ptb, const double *ptn, double *pta,
+                     int kjpt, int kn_fct_h, int kn_fct_v)
+{
+    if (need_single(h, "nemo_tra_adv_fct")) return 1;
+    if (!pun || !pvn || !pwn || !ptb || !ptn || !pta) return fail("tra_adv_fct: NULL array");
+    if (kjpt < 1) return fail("tra_adv_fct: kjpt = %d", kjpt);
+    CU(cudaSetDevice(h->device));
+    const size_t n3 = h->n3, n4 = n3 * (size_t)kjpt;
+    try {
+        if (h->s_pun.n != n3) { h->s_pun.alloc(n3); h->s_pvn.alloc(n3); h->s_pwn.alloc(n3); }
+        if (h->stage_kjpt < kjpt) { h->s_ptb.alloc(n4); h->s_ptn.alloc(n4); h->s_pta.alloc(n4); h->stage_kjpt = kjpt; }
+    } catch (const std::exception &e) { return fail("tra_adv_fct: staging buffers: %s", e.what()); }
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->s_pun.p, pun, n3 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_pvn.p, pvn, n3 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_pwn.p, pwn, n3 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_ptb.p, ptb, n4 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_ptn.p, ptn, n4 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_pta.p, pta, n4 * 8, cudaMemcpyHostToDevice, s));
+    if (nemo_tra_adv_fct_dev(h, kt, kit000, cdtype, p2dt, h->s_pun.p, h->s_pvn.p, h->s_pwn.p, h->s_ptb.p, h->s_ptn.p,
+                             h->s_pta.p, kjpt, kn_fct_h, kn_fct_v)) return 1;
+    CU(cudaMemcpyAsync(pta, h->s_pta.p, n4 * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int nemo_interp_4th_cpt_dev(nemo_fct_handle h, const double *pt_in, double *pt_out)
+{
+    if (!h) return fail("NULL handle");
+    if (!h->have_dom) return fail("interp_4th_cpt: nemo_fct_set_domain_arrays has not been called");
+    if (h->dom.jpk < 3) return fail("interp_4th_cpt: jpk must be >= 3");
+    CU(cudaSetDevice(h->device));
+    launch_interp_4th_cpt(h->dom.jpi, h->dom.jpj, h->dom.jpk, 1, h->wmask.p, h->mikt.p, h->mbkt.p, h->ln_isfcav,
+                          h->cpt_zwt.p, pt_in, pt_out, h->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int nemo_interp_4th_cpt(nemo_fct_handle h, const double *pt_in, double *pt_out)
+{
+    if (!h) return fail("NULL handle");
+    if (!pt_in || !pt_out) return fail("interp_4th_cpt: NULL array");
+    CU(cudaSetDevice(h->device));
+    try { if (h->s_cpt_in.n != h->n3) { h->s_cpt_in.alloc(h->n3); h->s_cpt_out.alloc(h->n3); } }
+    catch (const std::exception &e) { return fail("interp_4th_cpt: %s", e.what()); }
+    CU(cudaMemcpyAsync(h->s_cpt_in.p, pt_in, h->n3 * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->s_cpt_out.p, pt_out, h->n3 * 8, cudaMemcpyHostToDevice, h->stream));   // keep undefined cells as given
+    if (nemo_interp_4th_cpt_dev(h, h->s_cpt_in.p, h->s_cpt_out.p)) return 1;
+    CU(cudaMemcpyAsync(pt_out, h->s_cpt_out.p, h->n3 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int nemo_tra_adv_transports_dev(nemo_fct_handle h, const double *e2u, const double *e1v, const double *e3u_n,
+                                const double *e3v_n, const double *un, const double *vn, const double *wn,
+                                double *zun, double *zvn, double *zwn)
+{
+    if (!h) return fail("NULL handle");
+    if (!h->have_dom) return fail("tra_adv: nemo_fct_set_domain_arrays has not been called");
+    CU(cudaSetDevice(h->device));
+    launch_transports(h->dom.jpi, h->dom.jpj, h->dom.jpk, e2u, e1v, h->e1e2t.p, e3u_n, e3v_n, un, vn, wn, zun, zvn, zwn, h->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int lnk_common(std::vector<Ctx *> &g, int nfld, double *const *const *ptab, const char *cd_nat, const double *psgn,
+                      int ipk, int has_pval, double pval)
+{
+    if (nfld < 1 || !ptab || !cd_nat || !psgn || ipk < 1) return fail("lbc_lnk_multi: bad arguments");
+    if ((int)strlen(cd_nat) < nfld) return fail("lbc_lnk_multi: cd_nat shorter than nfld");
+    LnkCall call; call.nfld = nfld; call.nat.assign(cd_nat, nfld); call.sgn.assign(psgn, psgn + nfld);
+    call.nlev = ipk; call.has_pval = has_pval; call.pval = pval;
+    call.ptab.resize(g.size());
+    for (size_t m = 0; m < g.size(); ++m) for (int f = 0; f < nfld; ++f) {
+        if (!ptab[m][f]) return fail("lbc_lnk_multi: NULL field");
+        call.ptab[m].push_back(ptab[m][f]);
+    }
+    return lbc_exchange(g, call);
+}
+
+int nemo_lbc_lnk_multi_dev(nemo_fct_handle h, const char *cdname, int nfld, double *const *ptab, const char *cd_nat,
+                           const double *psgn, int ipk, int has_pval, double pval)
+{
+    (void)cdname;
+    if (need_single(h, "nemo_lbc_lnk_multi_dev")) return 1;
+    std::vector<Ctx *> g = {h};
+    double *const *tabs[1] = {ptab};
+    return lnk_common(g, nfld, tabs, cd_nat, psgn, ipk, has_pval, pval);
+}
+
+int nemo_group_lbc_lnk_multi_dev(nemo_fct_handle *hs, int n, const char *cdname, int nfld, double *const *const *ptab,
+                                 const char *cd_nat, const double *psgn, int ipk, int has_pval, double pval)
+{
+    (void)cdname;
+    if (!hs || n < 1) return fail("bad arguments");
+    std::vector<Ctx *> g(hs, hs + n);
+    if ((int)g[0]->group.size() != n) return fail("nemo_group_lbc_lnk_multi_dev: call nemo_fct_comm_init_local first");
+    return lnk_common(g, nfld, ptab, cd_nat, psgn, ipk, has_pval, pval);
+}
+
+int nemo_lbc_lnk_multi(nemo_fct_handle h, const char *cdname, int nfld, double *const *ptab, const char *cd_nat,
+                       const double *psgn, int ipk, int has_pval, double pval)
+{
+    if (need_single(h, "nemo_lbc_lnk_multi")) return 1;
+    if (nfld < 1 || !ptab || ipk < 1) return fail("lbc_lnk_multi: bad arguments");
+    CU(cudaSetDevice(h->device));
+    const size_t n = h->jpij * (size_t)ipk;
+    try {
+        while ((int)h->s_lbc.size() < nfld) h->s_lbc.push_back(std::make_unique<DevBuf<double>>());
+        for (int f = 0; f < nfld; ++f) if (h->s_lbc[f]->n < n) { CUTHROW(cudaStreamSynchronize(h->stream)); h->s_lbc[f]->alloc(n); }
+    } catch (const std::exception &e) { return fail("lbc_lnk_multi: %s", e.what()); }
+    std::vector<double *> dev(nfld);
+    for (int f = 0; f < nfld; ++f) {
+        if (!ptab[f]) return fail("lbc_lnk_multi: NULL field");
+        dev[f] = h->s_lbc[f]->p;
+        CU(cudaMemcpyAsync(dev[f], ptab[f], n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (nemo_lbc_lnk_multi_dev(h, cdname, nfld, dev.data(), cd_nat, psgn, ipk, has_pval, pval)) return 1;
+    for (int f = 0; f < nfld; ++f) CU(cudaMemcpyAsync(ptab[f], dev[f], n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"
