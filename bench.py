@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- FCT tracer-advection step (tra_adv_fct + its lbc_lnk halo / north-fold exchanges) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+              bench.py --gpus N --steps K --warmup W
+
+One "step" = one tra_adv_fct call over all kjpt tracers of the workload, halo exchanges included.
+Metric (BASELINE.json / BASELINE.md par. 3):  Mpts/s = jpiglo*jpjglo*jpk / t_step / 1e6  (whole job, all GPUs).
+  value    : inputs resident in HBM, CUDA events on the launching stream, max over ranks, barrier + sync both sides
+  e2e      : the same call through the host-pointer C-ABI entry point (nemo_fct_set_e3t + nemo_tra_adv_fct) with
+             pinned HOST buffers: H2D of e3t_b/n/a, pun, pvn, pwn, ptb, ptn, pta and D2H of pta inside the timed region
+  roofline : HBM bound; whole-step algorithmic bytes B_alg = N*(32*kjpt+56) over the step time, plus the same
+             accounting per kernel from CUDA events recorded around every launch inside the timed region
+  cpu_baseline / --impl reference : the C oracle (line-faithful restatement of the reference's CPU tra_adv_fct;
+             the Fortran itself cannot be built here: no Fortran compiler) on the host cores, threads as MPI ranks.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FCT tracer-advection Mpts/s per step"
+UNIT = "Mpts/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    """HBM GB/s denominator: driver-measured MEASURED_PEAKS.json, else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores (cpu_baseline of our arm, and the whole of --impl reference)
+# ----------------------------------------------------------------------------------------------------------------
+CPU_PARTITION = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2), 16: (4, 4), 32: (8, 4), 64: (8, 8)}   # tests/BENCH/EXPREF/best_jpni_jpnj_eorca025 (16: 4x4)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(cfg, steps, warmup):
+    """Time the oracle's tra_adv_fct (threads standing in for MPI ranks, halo exchange through the restated
+    mpp_lnk) on a bounded j-slab of the workload.  Returns (Mpts/s, info dict)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    from oracle import oracle as O
+    G, GJ, K, jperio, kjpt, h, v, rdt = cfg
+    cores = max(c for c in CPU_PARTITION if c <= host_cores())
+    jpni, jpnj = CPU_PARTITION[cores]
+    # bounded sample: same jpiglo, jpk, jperio, tracers and scheme; jpjglo cut so that one step is O(1-5 s) of CPU
+    target_pts = 30.0e6
+    gj = GJ if G * GJ * K <= target_pts else max(8 * jpnj, int(target_pts / (G * K)))
+    gf = H.global_bench_fields(O, G, gj, K, jperio, kjpt, rn_rdt=rdt)
+    w = O.World(G, gj, K, jperio, jpni, jpnj, ln_nnogather=True)
+    loc = {k: w.scatter(gf[k]) for k in H.DOM_KEYS + ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
+    for r, d in enumerate(w.doms):
+        d.set_fields(*[loc[k][r] for k in H.DOM_KEYS])
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        w.tra_adv_fct(gf["p2dt"], loc["pun"], loc["pvn"], loc["pwn"], loc["ptb"], loc["ptn"], loc["pta"], kjpt, h, v)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    w.close()
+    npts = G * gj * K
+    ms = 1e3 * sum(times) / len(times)
+    info = {"cores": cores, "kind": "port",
+            "sample": "%dx%dx%d of %dx%dx%d (same jpiglo/jpk/jperio=%d, kjpt=%d, FCT h%d/v%d), %dx%d subdomains = %d threads as MPI ranks, "
+                      "C restatement of tra_adv_fct (gcc -O2 -ffp-contract=off), not the Fortran binary" %
+                      (G, gj, K, G, GJ, K, jperio, kjpt, h, v, jpni, jpnj, cores),
+            "ms_per_step": ms}
+    return npts / (ms * 1e-3) / 1e6, info
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    val, info = cpu_reference_run(cfg, steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, cfg, 1, (1, 1)),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, cfg, n_gpus, part):
+    G, GJ, K, jperio, kjpt, h, v, rdt = cfg
+    return {"workload": "%s: tests/BENCH-style %dx%dx%d, jperio=%d, kjpt=%d, FCT h%d/v%d, z-star (ln_linssh=F)" %
+                        (name, G, GJ, K, jperio, kjpt, h, v),
+            "jpni_x_jpnj": "%dx%d" % part, "n_gpus": n_gpus,
+            "cache": "inputs larger than L2 (working set >> 126 MB), no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="orca025")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--schedule", type=int, default=None)
+    args = ap.parse_args()
+
+    BF = importlib.import_module("nemo-fmi-devel_b200.bench_fields")
+    cfg = BF.CONFIGS[args.workload]
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import nemo_fct_b200 as N
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the FCT path has no CPU fallback (use --impl reference for the CPU arm)")
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    G, GJ, K, jperio, kjpt, h, v, rdt = cfg
+    part = BF.best_partition(world)
+    dom = N.mpp_init(G, GJ, K, jperio, part[0], part[1], rank + 1)
+    ctx = N.FctContext(dom, local_rank)
+    if args.schedule is not None:
+        ctx.set_schedule(args.schedule)
+    if world > 1:
+        idt = torch.zeros(N.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(N.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+    # a dedicated (non-default) torch stream: the library launches on it, torch events time it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- synthetic BENCH fields, generated on the device; halos through the product's own lbc_lnk --------------
+    def lbc(trip):
+        flat = []
+        for t, nat, sgn in trip:
+            flat += [t, nat, sgn]
+        ctx.lbc_lnk_multi("bench", *flat)
+
+    f = BF.bench_fields(dom, kjpt, lbc, rdt, device=dev)
+    torch.cuda.synchronize()
+    ctx.set_domain_arrays(*[f[k].cpu().numpy() for k in ("tmask", "umask", "vmask", "wmask", "e1e2t", "r1_e1e2t", "mikt", "mbkt")],
+                          ln_linssh=False, ln_isfcav=False)
+    for k in ("umask", "vmask", "wmask"):
+        f[k] = None
+    ctx.set_e3t(f["e3t_b"], f["e3t_n"], f["e3t_a"])          # device-resident, borrowed
+    pta0 = f["pta"].clone()
+    npts_global = G * GJ * K
+    npts_local = dom.jpi * dom.jpj * dom.jpk
+
+    def step():
+        ctx.tra_adv_fct(1, 1, "TRA", f["p2dt"], f["pun"], f["pvn"], f["pwn"], f["ptb"], f["ptn"], f["pta"], kjpt, h, v)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    f["pta"].copy_(pta0)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.set_profiling(True)
+    n0 = N.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    launches = N.launch_count() - n0
+    ms = e0.elapsed_time(e1) / args.steps
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = npts_global / (ms_max * 1e-3) / 1e6
+    checksum = float(f["pta"].double().abs().sum().item())
+    if not np.isfinite(checksum):
+        raise SystemExit("bench.py: non-finite result")
+
+    # ---- roofline ---------------------------------------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    b_alg = BF.algorithmic_bytes(npts_local, kjpt)            # this GPU's share
+    n3 = npts_local
+    # per-kernel algorithmic bytes: the arrays each kernel must read/write once (DESIGN.md par. "kernels")
+    kbytes = {
+        "fct_laplacian": n3 * 8 * (1 * kjpt + 2 * kjpt) + n3 * 8 * 2,                  # r ptn, umask, vmask; w zltu, zltv
+        "interp_4th_cpt": n3 * 8 * (2 * kjpt) + n3 * 8 * 2,                            # r ptn; w ztw; r wmask, zwt
+        "fct_low_antidiff": n3 * 8 * ((3 + 5) * kjpt) + n3 * 8 * 8,                    # r ptb ptn pta; w pta zwi zwx zwy zwz; r pun pvn pwn e3t_b/n/a tmask wmask
+        "fct_betas": n3 * 8 * ((5 + 2) * kjpt) + n3 * 8 * 2,                           # r ptb zwi zwx zwy zwz; w zbetup zbetdo; r tmask e3t_n
+        "fct_limit": n3 * 8 * ((5 + 3) * kjpt),                                        # r zbetup zbetdo zwx zwy zwz; w zwx zwy zwz
+        "fct_final": n3 * 8 * ((4 + 1) * kjpt) + n3 * 8 * 1,                           # r zwx zwy zwz pta; w pta; r e3t_n
+        "fct_limit_final": n3 * 8 * ((6 + 1) * kjpt) + n3 * 8 * 1,
+    }
+    if h == 4:
+        kbytes["fct_low_antidiff"] += n3 * 8 * 2 * kjpt
+    if v == 4:
+        kbytes["fct_low_antidiff"] += n3 * 8 * 1 * kjpt
+    kern = {}
+    for name, (tot, calls) in prof.items():
+        avg = tot / max(calls, 1)
+        ent = {"ms": round(avg, 5), "launches_per_step": calls / args.steps}
+        if name in kbytes:
+            ent["alg_bytes"] = kbytes[name]
+            ent["gbs"] = round(kbytes[name] / (avg * 1e-3) / 1e9, 1)
+            ent["frac"] = round(ent["gbs"] / peak, 4)
+        kern[name] = ent
+    dominant = max((k for k in kern if k in kbytes), key=lambda k: kern[k]["ms"] * kern[k]["launches_per_step"], default=None)
+    achieved = b_alg / (ms_max * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "scope": "whole step per GPU: B_alg = N_local*(32*kjpt+56) bytes over the step time (all kernels + exchanges)",
+                "alg_bytes_per_step": b_alg, "dominant_kernel": dominant, "kernels": kern}
+
+    # ---- e2e: host-pointer entry points, pinned host buffers ---------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        names3 = ["e3t_b", "e3t_n", "e3t_a", "pun", "pvn", "pwn"]
+        names4 = ["ptb", "ptn", "pta"]
+        host = {}
+        for k in names3 + names4:
+            host[k] = torch.empty(f[k].shape, dtype=torch.float64, pin_memory=True)
+            host[k].copy_(f[k] if k != "pta" else pta0)
+        hn = {k: host[k].numpy() for k in host}
+        h2d = sum(hn[k].nbytes for k in hn)
+        d2h = hn["pta"].nbytes
+        n_e2e = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            ctx.set_e3t(hn["e3t_b"], hn["e3t_n"], hn["e3t_a"])                 # e3t varies every step under vvl
+            ctx.tra_adv_fct(1, 1, "TRA", f["p2dt"], hn["pun"], hn["pvn"], hn["pwn"], hn["ptb"], hn["ptn"], hn["pta"], kjpt, h, v)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        ems = 1e3 * (time.perf_counter() - t0) / n_e2e
+        te = torch.tensor([ems], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ems = float(te.item())
+        e2e = {"value": round(npts_global / (ems * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": round(ems, 3), "steps": n_e2e,
+               "path": "nemo_fct_set_e3t + nemo_tra_adv_fct (host pointers, pinned), synchronous"}
+        ctx.set_e3t(f["e3t_b"], f["e3t_n"], f["e3t_a"])
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cval, info = cpu_reference_run(cfg, 1, 0)
+            cpu = {"value": round(cval, 3), "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+        except Exception as ex:                                                    # never lose the GPU numbers
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_max, 4), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, cfg, world, part),
+                "tracer_mpts_per_s": round(value * kjpt, 2), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks, "checksum_abs_pta": checksum}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,13 @@ int nemo_fct_abi_version(void);
 long long nemo_fct_launch_count(void);
 /* communication report in the spirit of mpp_report (lib_mpp.F90:1471-1587): exchanges and bytes sent so far       */
 int nemo_fct_comm_report(nemo_fct_handle h, long long *n_exchanges, long long *bytes_sent);
+/* Per-kernel device timing with CUDA events recorded on the launching stream around every launch of this context
+ * (bench.py's roofline figures).  nemo_fct_set_profiling(h, 1) clears the counters and starts recording;
+ * nemo_fct_profile_read synchronises and returns the number of kernels seen, their names (name_stride bytes
+ * each, NUL-terminated), accumulated milliseconds and launch counts.  Returns -1 on error.                         */
+int nemo_fct_set_profiling(nemo_fct_handle h, int on);
+int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int name_stride, double *total_ms,
+                          long long *calls);
 /* Select the kernel schedule: 0 = reference pass structure (one kernel per pass group, exchanges X1..X4 as in
  * traadv_fct.F90:209,280,400,426); higher = fused schedules.  Results are identical.              */
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule);

@@ -100,6 +100,8 @@ def lib():
         "nemo_group_lbc_lnk_multi_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.c_char_p, dp, i, i, d],
         "nemo_fct_comm_report": [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
         "nemo_fct_set_schedule": [vp, i],
+        "nemo_fct_set_profiling": [vp, i],
+        "nemo_fct_profile_read": [vp, i, C.c_char_p, i, dp, C.POINTER(C.c_longlong)],
         "nemo_fct_abi_version": [],
     }
     for name, argtypes in sig.items():
@@ -118,7 +120,8 @@ ABI_SYMBOLS = (
     "nemo_fct_comm_init nemo_fct_comm_init_local nemo_tra_adv_fct nemo_tra_adv_fct_dev nemo_group_tra_adv_fct_dev "
     "nemo_interp_4th_cpt nemo_interp_4th_cpt_dev nemo_tra_adv_transports_dev nemo_lbc_lnk_multi "
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
-    "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule").split()
+    "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
+    "nemo_fct_profile_read").split()
 
 
 def _check(rc):
@@ -238,6 +241,21 @@ class FctContext:
 
     def synchronize(self):
         _check(lib().nemo_fct_synchronize(self._h))
+
+    def set_profiling(self, on):
+        """CUDA-event timing of every kernel launch of this context (read with :meth:`profile`)"""
+        _check(lib().nemo_fct_set_profiling(self._h, int(on)))
+
+    def profile(self):
+        """{kernel name: (total ms, launches)} since set_profiling(True)"""
+        stride, mx = 32, 16
+        names = C.create_string_buffer(stride * mx)
+        ms = (C.c_double * mx)()
+        calls = (C.c_longlong * mx)()
+        n = lib().nemo_fct_profile_read(self._h, mx, names, stride, ms, calls)
+        if n < 0:
+            _check(1)
+        return {names.raw[k * stride:(k + 1) * stride].split(b"\0")[0].decode(): (ms[k], int(calls[k])) for k in range(n)}
 
     def set_schedule(self, schedule):
         _check(lib().nemo_fct_set_schedule(self._h, schedule))

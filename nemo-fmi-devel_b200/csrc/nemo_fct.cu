@@ -131,8 +131,46 @@ struct nemo_fct_ctx {
     void *nccl_comm = nullptr; int nccl_nranks = 0;
     long long n_exchanges = 0, bytes_sent = 0;
     int schedule = 0;
+    // per-kernel CUDA-event timing (bench.py's roofline): off by default
+    bool profiling = false;
+    struct ProfRec { int id; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_open;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[16] = {0}; long long prof_calls[16] = {0};
 };
 typedef nemo_fct_ctx Ctx;
+
+// ------------------------------------------------------------------------------------------------------------
+// per-kernel timing with CUDA events on the launching stream
+// ------------------------------------------------------------------------------------------------------------
+enum ProfId { P_LAPLACIAN = 0, P_CPT, P_LOW_ANTIDIFF, P_BETAS, P_LIMIT, P_FINAL, P_LIMIT_FINAL, P_PACK, P_MOVE, P_UNPACK, P_COUNT };
+static const char *kProfName[P_COUNT] = {"fct_laplacian", "interp_4th_cpt", "fct_low_antidiff", "fct_betas", "fct_limit",
+                                         "fct_final", "fct_limit_final", "lbc_pack", "lbc_move_nccl", "lbc_fill_unpack"};
+struct ProfScope {
+    nemo_fct_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int id;
+    static cudaEvent_t get(nemo_fct_ctx *c) {
+        if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    ProfScope(nemo_fct_ctx *c_, int id_) : c(c_), id(id_) {
+        if (!c->profiling) return;
+        a = get(c); b = get(c); cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->prof_open.push_back({id, a, b});
+    }
+};
+static void prof_collect(nemo_fct_ctx *c)
+{
+    for (auto &r : c->prof_open) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.id] += ms; c->prof_calls[r.id]++; }
+        c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+    }
+    c->prof_open.clear();
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // plans
@@ -292,6 +330,7 @@ static int lbc_exchange(std::vector<Ctx *> &g, const LnkCall &call)
     for (int m = 0; m < ng; ++m) {
         Ctx *c = g[m]; JobTables &t = *jt[m];
         CU(cudaSetDevice(c->device));
+        ProfScope ps(c, P_PACK);
         launch_lbc_pack(t.pack.p, t.npack, t.maxpack, t.nlev, c->jpij, c->stream);
     }
     for (int m = 0; m < ng; ++m) {
@@ -306,6 +345,7 @@ static int lbc_exchange(std::vector<Ctx *> &g, const LnkCall &call)
         if (!remote) continue;
         if (!c->nccl_comm) return fail("lbc_lnk_multi: rank %d needs remote neighbours but nemo_fct_comm_init was not called", c->rank);
         CU(cudaSetDevice(c->device));
+        ProfScope ps(c, P_MOVE);
         NC(g_nccl.GroupStart());
         for (int p = 0; p < nr; ++p) {
             bool local = false; for (Ctx *o : g) local = local || (o->rank == p);
@@ -318,6 +358,7 @@ static int lbc_exchange(std::vector<Ctx *> &g, const LnkCall &call)
     for (int m = 0; m < ng; ++m) {
         Ctx *c = g[m]; JobTables &t = *jt[m];
         CU(cudaSetDevice(c->device));
+        ProfScope ps(c, P_UNPACK);
         launch_lbc_fill(t.fill.p, t.nfill, t.maxfill, t.nlev, c->jpij, c->stream);
         launch_lbc_unpack(t.unpack.p, t.nunpack, t.maxunpack, t.nlev, c->jpij, c->stream);
     }
@@ -398,22 +439,22 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         for (int m = 0; m < ng; ++m) for (auto f : fields) call.ptab[m].push_back((g[m]->*f).p);
         return lbc_exchange(g, call);
     };
-#define EACH(stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); stmt; }
+#define EACH(id, stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); ProfScope ps(c, id); stmt; }
     if (h == 4) {
-        EACH(launch_fct_laplacian(fa[m], c->stream));
+        EACH(P_LAPLACIAN, launch_fct_laplacian(fa[m], c->stream));
         if (exch({&Ctx::zltu, &Ctx::zltv}, "TT", {1.0, 1.0})) return 1;                            // X1 (:209)
     }
     if (v == 4) {
-        EACH(launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p,
+        EACH(P_CPT, launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p,
                                    c->ln_isfcav, c->cpt_zwt.p, fa[m].ptn, c->ztw.p, c->stream));
     }
-    EACH(launch_fct_low_antidiff(fa[m], c->stream));
+    EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff(fa[m], c->stream));
     if (exch({&Ctx::zwi, &Ctx::zwx, &Ctx::zwy, &Ctx::zwz}, "TUVW", {1.0, -1.0, -1.0, 1.0})) return 1;   // X2 (:280)
-    EACH(launch_fct_betas(fa[m], c->stream));
+    EACH(P_BETAS, launch_fct_betas(fa[m], c->stream));
     if (exch({&Ctx::zbetup, &Ctx::zbetdo}, "TT", {1.0, 1.0})) return 1;                            // X3 (:400)
-    EACH(launch_fct_limit(fa[m], c->stream));
+    EACH(P_LIMIT, launch_fct_limit(fa[m], c->stream));
     if (exch({&Ctx::zwx, &Ctx::zwy}, "UV", {-1.0, -1.0})) return 1;                                // X4 (:426)
-    EACH(launch_fct_final(fa[m], c->stream));
+    EACH(P_FINAL, launch_fct_final(fa[m], c->stream));
 #undef EACH
     CU(cudaGetLastError());
     return 0;
@@ -512,7 +553,10 @@ int nemo_fct_destroy(nemo_fct_handle h)
     for (Ctx *o : h->group) if (o != h) {                              // leave the in-process communicator
         std::vector<Ctx *> ng; for (Ctx *q : o->group) if (q != h) ng.push_back(q);
         o->group = ng; o->jobcache.clear();
+        if (o->stream == h->own_stream) o->stream = o->own_stream;     // the shared stream dies with its owner
     }
+    prof_collect(h);
+    for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -533,6 +577,33 @@ int nemo_fct_synchronize(nemo_fct_handle h)
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+int nemo_fct_set_profiling(nemo_fct_handle h, int on)
+{
+    if (!h) return fail("NULL handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    prof_collect(h);
+    h->profiling = on != 0;
+    for (int i = 0; i < P_COUNT; ++i) { h->prof_ms[i] = 0.0; h->prof_calls[i] = 0; }
+    return 0;
+}
+
+int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int name_stride, double *total_ms, long long *calls)
+{
+    if (!h) { fail("NULL handle"); return -1; }
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) { fail("profile_read: sync failed"); return -1; }
+    prof_collect(h);
+    int n = 0;
+    for (int i = 0; i < P_COUNT && n < max_entries; ++i) {
+        if (!h->prof_calls[i]) continue;
+        if (names && name_stride > 0) { strncpy(names + (size_t)n * name_stride, kProfName[i], name_stride - 1); names[(size_t)n * name_stride + name_stride - 1] = 0; }
+        if (total_ms) total_ms[n] = h->prof_ms[i];
+        if (calls) calls[n] = h->prof_calls[i];
+        ++n;
+    }
+    return n;
 }
 
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule)
