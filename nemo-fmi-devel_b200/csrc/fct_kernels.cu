@@ -38,6 +38,20 @@ __device__ __forceinline__ bool interior_column(int jpi, int jpj, int &ji, int &
     return true;
 }
 
+// column owned by this thread within a Region (up to 4 rectangles)
+__device__ __forceinline__ bool region_column(const Region &rg, int &ji, int &jj)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= rg.start[rg.n]) return false;
+    int q = 0;
+    while (q + 1 < rg.n && p >= rg.start[q + 1]) ++q;
+    const int loc = (int)p - rg.start[q];
+    const int ni = rg.r[q].i1 - rg.r[q].i0 + 1;
+    jj = rg.r[q].j0 + loc / ni;
+    ji = rg.r[q].i0 + loc % ni;
+    return true;
+}
+
 // this block's chunk of the jk loop: levels ka..kb (1-based, inclusive) out of 1..kmax
 __device__ __forceinline__ void k_chunk(int kmax, int nchunk, int &ka, int &kb)
 {
@@ -69,7 +83,7 @@ __device__ __forceinline__ double upstream_w(const FctArgs &a, const double *ptb
 __global__ void __launch_bounds__(kThreads) k_fct_laplacian(const FctArgs a)
 {
     int ji, jj, ka, kb;
-    if (!interior_column(a.jpi, a.jpj, ji, jj)) return;
+    if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *ptn = a.ptn + toff;
@@ -98,7 +112,7 @@ template <int H, int V>
 __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff(const FctArgs a)
 {
     int ji, jj, ka, kb;
-    if (!interior_column(a.jpi, a.jpj, ji, jj)) return;
+    if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *ptb = a.ptb + toff, *ptn = a.ptn + toff;
@@ -167,7 +181,7 @@ __device__ __forceinline__ void bup_bdo(double pbef, double paft, double tm, dou
 __global__ void __launch_bounds__(kThreads) k_fct_betas(const FctArgs a)
 {
     int ji, jj, ka, kb;
-    if (!interior_column(a.jpi, a.jpj, ji, jj)) return;
+    if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *pbef = a.ptb + toff, *paft = a.zwi + toff;
@@ -227,24 +241,27 @@ __device__ __forceinline__ double limit_coef(double flux, double bdo_here, doubl
 __global__ void __launch_bounds__(kThreads) k_fct_limit(const FctArgs a)
 {
     int ji, jj, ka, kb;
-    if (!interior_column(a.jpi, a.jpj, ji, jj)) return;
+    if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
     const size_t toff = (size_t)blockIdx.z * a.n3;
-    double *paa = a.zwx + toff, *pbb = a.zwy + toff, *pcc = a.zwz + toff;
+    const double *paa = a.zwx + toff, *pbb = a.zwy + toff, *pcc = a.zwz + toff;
+    // in place (reference structure) or into separate arrays (schedule 1: the inner kernels still read zwx/zwy/zwz)
+    double *oaa = (a.zlx ? a.zlx : a.zwx) + toff, *obb = (a.zly ? a.zly : a.zwy) + toff, *occ = (a.zlz ? a.zlz : a.zwz) + toff;
     const double *zbetup = a.zbetup + toff, *zbetdo = a.zbetdo + toff;
     const int jpi = a.jpi;
     const size_t jpij = a.jpij;
     const size_t c2 = (size_t)(jj - 1) * jpi + (ji - 1);
     double bup_c = zbetup[c2 + (size_t)(ka - 1) * jpij], bdo_c = zbetdo[c2 + (size_t)(ka - 1) * jpij];
+    if (ka == 1 && a.zlz) occ[c2] = pcc[c2];                            // pcc(:,:,1) is never limited
     for (int k = ka; k <= kb; ++k) {
         const size_t o = c2 + (size_t)(k - 1) * jpij;
         const double bup_e = zbetup[o + 1], bdo_e = zbetdo[o + 1], bup_n = zbetup[o + jpi], bdo_n = zbetdo[o + jpi];
         const double bup_p = zbetup[o + jpij], bdo_p = zbetdo[o + jpij];
         const double fa = paa[o], fb = pbb[o], fc = pcc[o + jpij];
-        paa[o] = fa * limit_coef(fa, bdo_c, bup_e, bup_c, bdo_e);
-        pbb[o] = fb * limit_coef(fb, bdo_c, bup_n, bup_c, bdo_n);
+        oaa[o] = fa * limit_coef(fa, bdo_c, bup_e, bup_c, bdo_e);
+        obb[o] = fb * limit_coef(fb, bdo_c, bup_n, bup_c, bdo_n);
         // k direction (:419-422): za = MIN(1, zbetdo(jk+1), zbetup(jk)), zb = MIN(1, zbetup(jk+1), zbetdo(jk))
-        pcc[o + jpij] = fc * limit_coef(fc, bdo_p, bup_c, bup_p, bdo_c);
+        occ[o + jpij] = fc * limit_coef(fc, bdo_p, bup_c, bup_p, bdo_c);
         bup_c = bup_p; bdo_c = bdo_p;
     }
 }
@@ -255,10 +272,10 @@ __global__ void __launch_bounds__(kThreads) k_fct_limit(const FctArgs a)
 __global__ void __launch_bounds__(kThreads) k_fct_final(const FctArgs a)
 {
     int ji, jj, ka, kb;
-    if (!interior_column(a.jpi, a.jpj, ji, jj)) return;
+    if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
     const size_t toff = (size_t)blockIdx.z * a.n3;
-    const double *zwx = a.zwx + toff, *zwy = a.zwy + toff, *zwz = a.zwz + toff;
+    const double *zwx = (a.zlx ? a.zlx : a.zwx) + toff, *zwy = (a.zly ? a.zly : a.zwy) + toff, *zwz = (a.zlz ? a.zlz : a.zwz) + toff;
     double *pta = a.pta + toff;
     const int jpi = a.jpi;
     const size_t jpij = a.jpij;
@@ -366,9 +383,203 @@ __global__ void __launch_bounds__(256) k_transports(int jpk, size_t jpij, const 
     }
 }
 
+// ============================================================================================================
+// Schedule 1 (fused inner region).  The inner region keeps a margin of >= 3 cells from every array edge, so none of
+// the values it reads is produced by an exchange: the same arithmetic as the reference pass
+// structure, without the intermediate sweeps.  The boundary frame is left to the reference-structured kernels.
+// ============================================================================================================
+
+// umask / vmask / wmask: read from the module arrays, or derived from tmask when the host arrays were verified to be
+// the plain products of dommsk.F90:176-177,193 (saves three array streams)
+template <bool FROM_T> struct Masks {
+    const FctArgs &a;
+    __device__ __forceinline__ double u(size_t o) const { return FROM_T ? a.tmask[o] * a.tmask[o + 1] : a.umask[o]; }
+    __device__ __forceinline__ double v(size_t o) const { return FROM_T ? a.tmask[o] * a.tmask[o + a.jpi] : a.vmask[o]; }
+    __device__ __forceinline__ double w(size_t o, int k) const {
+        return FROM_T ? (k == 1 ? a.tmask[o] : a.tmask[o] * a.tmask[o - a.jpij]) : a.wmask[o];
+    }
+};
+
+// P1-P5 on the inner region with the 4th-order Laplacian zltu/zltv evaluated in place (:195-208 folded into :211-221)
+template <int H, int V, bool FROM_T>
+__global__ void __launch_bounds__(kThreads) k_fct_low_antidiff_inner(const FctArgs a)
+{
+    int ji, jj, ka, kb;
+    if (!region_column(a.reg, ji, jj)) return;
+    k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    const size_t toff = (size_t)blockIdx.z * a.n3;
+    const double *ptb = a.ptb + toff, *ptn = a.ptn + toff;
+    double *pta = a.pta + toff, *zwi = a.zwi + toff, *zwx = a.zwx + toff, *zwy = a.zwy + toff, *zwz = a.zwz + toff;
+    const double *ztw = a.ztw + toff;
+    const Masks<FROM_T> msk{a};
+    const int jpi = a.jpi;
+    const size_t jpij = a.jpij;
+    const size_t c2 = (size_t)(jj - 1) * jpi + (ji - 1);
+    const double r1 = a.r1_e1e2t[c2];
+    const int mik = a.ln_isfcav ? a.mikt[c2] : 1;
+    const double p2dt = a.p2dt;
+    const double r1_6 = 1.0 / 6.0;
+
+    // upstream vertical flux through the top face of level k, wmask through msk (same arithmetic as upstream_w)
+    auto upw = [&](int k) -> double {
+        double v = 0.0;
+        if (k >= 2 && k <= a.jpk - 1) {
+            const size_t o = c2 + (size_t)(k - 1) * jpij;
+            const double w = a.pwn[o];
+            const double zfp_wk = w + fabs(w), zfm_wk = w - fabs(w);
+            v = 0.5 * (zfp_wk * ptb[o] + zfm_wk * ptb[o - jpij]) * msk.w(o, k);
+        }
+        if (a.ln_linssh) {
+            const int ktop = a.ln_isfcav ? mik : 1;
+            if (k == ktop) { const size_t o = c2 + (size_t)(k - 1) * jpij; v = a.pwn[o] * ptb[o]; }
+        }
+        return v;
+    };
+
+    double upz_k = upw(ka);
+    double tn_m = (ka >= 2) ? ptn[c2 + (size_t)(ka - 2) * jpij] : 0.0;
+    for (int k = ka; k <= kb; ++k) {
+        const size_t o = c2 + (size_t)(k - 1) * jpij;
+        const double tb_c = ptb[o], tb_w = ptb[o - 1], tb_e = ptb[o + 1], tb_s = ptb[o - jpi], tb_n = ptb[o + jpi];
+        const double u_c = a.pun[o], u_w = a.pun[o - 1], v_c = a.pvn[o], v_s = a.pvn[o - jpi];
+        double zfp, zfm;
+        zfp = u_c + fabs(u_c); zfm = u_c - fabs(u_c);
+        const double upx_c = 0.5 * (zfp * tb_c + zfm * tb_e);
+        zfp = u_w + fabs(u_w); zfm = u_w - fabs(u_w);
+        const double upx_w = 0.5 * (zfp * tb_w + zfm * tb_c);
+        zfp = v_c + fabs(v_c); zfm = v_c - fabs(v_c);
+        const double upy_c = 0.5 * (zfp * tb_c + zfm * tb_n);
+        zfp = v_s + fabs(v_s); zfm = v_s - fabs(v_s);
+        const double upy_s = 0.5 * (zfp * tb_s + zfm * tb_c);
+        const double upz_kp1 = upw(k + 1);
+        const double ztra = -(upx_c - upx_w + upy_c - upy_s + upz_k - upz_kp1) * r1;
+        const double tm = a.tmask[o];
+        pta[o] = pta[o] + ztra / a.e3t_n[o] * tm;
+        zwi[o] = (a.e3t_b[o] * tb_c + p2dt * ztra) / a.e3t_a[o] * tm;
+        const double tn_c = ptn[o], tn_e = ptn[o + 1], tn_n = ptn[o + jpi];
+        if (H == 2) {
+            zwx[o] = 0.5 * u_c * (tn_c + tn_e) - upx_c;
+            zwy[o] = 0.5 * v_c * (tn_c + tn_n) - upy_c;
+        } else {
+            // ztu(i) = (ptn(i+1)-ptn(i))*umask(i);  zltu(i) = (ztu(i) + ztu(i-1))*r1_6   (:198, :204)
+            const double tn_w = ptn[o - 1], tn_ee = ptn[o + 2], tn_s = ptn[o - jpi], tn_nn = ptn[o + 2 * (size_t)jpi];
+            const double ztu_w = (tn_c - tn_w) * msk.u(o - 1), ztu_c = (tn_e - tn_c) * msk.u(o), ztu_e = (tn_ee - tn_e) * msk.u(o + 1);
+            const double ztv_s = (tn_c - tn_s) * msk.v(o - jpi), ztv_c = (tn_n - tn_c) * msk.v(o), ztv_n = (tn_nn - tn_n) * msk.v(o + jpi);
+            const double zltu_c = (ztu_c + ztu_w) * r1_6, zltu_e = (ztu_e + ztu_c) * r1_6;
+            const double zltv_c = (ztv_c + ztv_s) * r1_6, zltv_n = (ztv_n + ztv_c) * r1_6;
+            const double zC2t_u = tn_c + tn_e, zC2t_v = tn_c + tn_n;
+            zwx[o] = 0.5 * u_c * (zC2t_u + zltu_c - zltu_e) - upx_c;
+            zwy[o] = 0.5 * v_c * (zC2t_v + zltv_c - zltv_n) - upy_c;
+        }
+        double fz = 0.0;
+        if (k >= 2) {
+            if (V == 2) fz = (a.pwn[o] * 0.5 * (tn_c + tn_m) - upz_k) * msk.w(o, k);
+            else        fz = (a.pwn[o] * ztw[o] - upz_k) * msk.w(o, k);
+        }
+        zwz[o] = fz;
+        upz_k = upz_kp1; tn_m = tn_c;
+    }
+}
+
+// nonosc + final trend in ONE kernel (P6 + P7 + P8, :356-425 and :288-297) on the rectangle a.out.
+// A block owns an extended tile of NX x NY columns (halo 2 around its NX-4 x NY-4 output columns); one thread per
+// column marches down jk.  Per level: every thread publishes zbup/zbdo and its east/north anti-diffusive fluxes in
+// shared memory, the threads of the inner ring (halo 1) compute the betas of the level and publish them, and the
+// output threads limit the 6 fluxes of the level above and apply the final divergence.  Neither betas nor limited
+// fluxes ever reach HBM; X3 / X4 are not needed because no cell of the tile is touched by an exchange.
+constexpr int NX = 32, NY = 16, NHALO = 2;
+
+__global__ void __launch_bounds__(NX * NY) k_fct_nonosc_final(const FctArgs a)
+{
+    extern __shared__ double fct_smem[];
+    double(*sA)[4][NY][NX] = reinterpret_cast<double(*)[4][NY][NX]>(fct_smem);                          // [level % 3][zbup, zbdo, paa, pbb]
+    double(*sB)[2][NY][NX] = reinterpret_cast<double(*)[2][NY][NX]>(fct_smem + 3 * 4 * NY * NX);        // [level % 2][zbetup, zbetdo]
+    const int tx = threadIdx.x % NX, ty = threadIdx.x / NX;
+    const int ox = NX - 2 * NHALO, oy = NY - 2 * NHALO;
+    const int gi = a.out.i0 + (int)blockIdx.x * ox + tx - NHALO;
+    const int gj = a.out.j0 + (int)blockIdx.y * oy + ty - NHALO;
+    // tiles overhang the rectangle at its east/north end: clamp the address, never the role
+    const int ji = min(gi, a.out.i1 + NHALO), jj = min(gj, a.out.j1 + NHALO);
+    const bool is_out = tx >= NHALO && tx < NX - NHALO && ty >= NHALO && ty < NY - NHALO && gi <= a.out.i1 && gj <= a.out.j1;
+    const bool is_beta = tx >= 1 && tx < NX - 1 && ty >= 1 && ty < NY - 1;
+    const size_t toff = (size_t)blockIdx.z * a.n3;
+    const double *pbef = a.ptb + toff, *paft = a.zwi + toff;
+    const double *paa = a.zwx + toff, *pbb = a.zwy + toff, *pcc = a.zwz + toff;
+    double *pta = a.pta + toff;
+    const int jpi = a.jpi, jpk = a.jpk;
+    const size_t jpij = a.jpij;
+    const size_t c2 = (size_t)(jj - 1) * jpi + (ji - 1);
+    const double zrtrn = 1.e-15;
+    const double e12 = a.e1e2t[c2], r1 = a.r1_e1e2t[c2];
+    const double p2dt = a.p2dt;
+
+    double up_m, do_m, up_c, do_c, up_p, do_p;          // zbup/zbdo of this column at jk-1, jk, jk+1
+    bup_bdo(pbef[c2], paft[c2], a.tmask[c2], up_c, do_c);
+    up_m = up_c; do_m = do_c;                           // ikm1 = MAX(jk-1,1)
+    double aft_c = paft[c2];
+    double pcc_k = pcc[c2];                             // anti-diffusive pcc(jk), pcc(jk+1) rolling
+    double bup_mm = 0.0, bdo_mm = 0.0, bup_m = 0.0, bdo_m = 0.0;   // betas of this column at jk-2, jk-1
+    double paa_m = 0.0, pbb_m = 0.0, pcc_m = 0.0;       // own fluxes of level jk-1 (pcc_m = pcc(jk-1))
+    double e3n_m = 1.0;
+
+    for (int k = 1; k <= jpk; ++k) {
+        const size_t o = c2 + (size_t)(k - 1) * jpij;
+        const bool lev = k <= jpk - 1;                  // betas are computed for jk = 1..jpkm1, zbetup/do(jpk) = 0
+        double paa_c = 0.0, pbb_c = 0.0, pcc_p = 0.0, aft_p = 0.0, e3n_c = 1.0;
+        if (lev) {
+            aft_p = paft[o + jpij];
+            bup_bdo(pbef[o + jpij], aft_p, a.tmask[o + jpij], up_p, do_p);
+            paa_c = paa[o]; pbb_c = pbb[o]; pcc_p = pcc[o + jpij];
+            e3n_c = a.e3t_n[o];
+            double *A = &sA[k % 3][0][0][0];
+            A[0 * NX * NY + ty * NX + tx] = up_c; A[1 * NX * NY + ty * NX + tx] = do_c;
+            A[2 * NX * NY + ty * NX + tx] = paa_c; A[3 * NX * NY + ty * NX + tx] = pbb_c;
+        }
+        __syncthreads();
+        double bup_c = 0.0, bdo_c = 0.0;
+        if (lev && is_beta) {
+            const double(*A)[NY][NX] = sA[k % 3];
+            const double zup = dmax(dmax(dmax(dmax(dmax(dmax(up_c, A[0][ty][tx - 1]), A[0][ty][tx + 1]), A[0][ty - 1][tx]), A[0][ty + 1][tx]), up_m), up_p);
+            const double zdo = dmin(dmin(dmin(dmin(dmin(dmin(do_c, A[1][ty][tx - 1]), A[1][ty][tx + 1]), A[1][ty - 1][tx]), A[1][ty + 1][tx]), do_m), do_p);
+            const double paa_w = A[2][ty][tx - 1], pbb_s = A[3][ty - 1][tx];
+            const double zpos = dmax(0., paa_w) - dmin(0., paa_c) + dmax(0., pbb_s) - dmin(0., pbb_c)
+                              + dmax(0., pcc_p) - dmin(0., pcc_k);
+            const double zneg = dmax(0., paa_c) - dmin(0., paa_w) + dmax(0., pbb_c) - dmin(0., pbb_s)
+                              + dmax(0., pcc_k) - dmin(0., pcc_p);
+            const double zbt = e12 * e3n_c / p2dt;
+            bup_c = (zup - aft_c) / (zpos + zrtrn) * zbt;
+            bdo_c = (aft_c - zdo) / (zneg + zrtrn) * zbt;
+        }
+        sB[k % 2][0][ty][tx] = bup_c; sB[k % 2][1][ty][tx] = bdo_c;
+        __syncthreads();
+        if (k >= 2 && is_out) {
+            // final trend of level kk = k-1: betas(kk) of the neighbours from sB, own betas at kk-1, kk, kk+1
+            const int kk = k - 1;
+            const double(*Bm)[NY][NX] = sB[kk % 2];
+            const double(*Am)[NY][NX] = sA[kk % 3];
+            const double bup_e = Bm[0][ty][tx + 1], bdo_e = Bm[1][ty][tx + 1], bup_w = Bm[0][ty][tx - 1], bdo_w = Bm[1][ty][tx - 1];
+            const double bup_n = Bm[0][ty + 1][tx], bdo_n = Bm[1][ty + 1][tx], bup_s = Bm[0][ty - 1][tx], bdo_s = Bm[1][ty - 1][tx];
+            const double paa_w = Am[2][ty][tx - 1], pbb_s = Am[3][ty - 1][tx];
+            const double lx_e = paa_m * limit_coef(paa_m, bdo_m, bup_e, bup_m, bdo_e);
+            const double lx_w = paa_w * limit_coef(paa_w, bdo_w, bup_m, bup_w, bdo_m);
+            const double ly_n = pbb_m * limit_coef(pbb_m, bdo_m, bup_n, bup_m, bdo_n);
+            const double ly_s = pbb_s * limit_coef(pbb_s, bdo_s, bup_m, bup_s, bdo_m);
+            // pcc(jk+1) is limited with betas(jk), betas(jk+1) (:419-422); pcc(:,:,1) is never limited
+            const double lz_t = (kk == 1) ? pcc_m : pcc_m * limit_coef(pcc_m, bdo_m, bup_mm, bup_m, bdo_mm);
+            const double lz_b = pcc_k * limit_coef(pcc_k, bdo_c, bup_m, bup_c, bdo_m);
+            const size_t om = o - jpij;
+            pta[om] = pta[om] - (lx_e - lx_w + ly_n - ly_s + lz_t - lz_b) * r1 / e3n_m;
+        }
+        // rotate the column registers
+        up_m = up_c; do_m = do_c; up_c = up_p; do_c = do_p; aft_c = aft_p;
+        bup_mm = bup_m; bdo_mm = bdo_m; bup_m = bup_c; bdo_m = bdo_c;
+        paa_m = paa_c; pbb_m = pbb_c; pcc_m = pcc_k; pcc_k = pcc_p; e3n_m = e3n_c;
+    }
+}
+
 inline dim3 column_grid(const FctArgs &a)
 {
-    const long long ncol = (long long)(a.jpi - 2) * (a.jpj - 2);
+    const long long ncol = a.reg.ncol();
     return dim3((unsigned)((ncol + kThreads - 1) / kThreads), (unsigned)a.nkchunk, (unsigned)a.kjpt);
 }
 
@@ -386,6 +597,32 @@ void launch_fct_low_antidiff(const FctArgs &a, cudaStream_t s)
     else if (a.kn_fct_h == 2)               k_fct_low_antidiff<2, 4><<<g, kThreads, 0, s>>>(a);
     else if (a.kn_fct_v == 2)               k_fct_low_antidiff<4, 2><<<g, kThreads, 0, s>>>(a);
     else                                    k_fct_low_antidiff<4, 4><<<g, kThreads, 0, s>>>(a);
+    note_launch();
+}
+
+void launch_fct_low_antidiff_inner(const FctArgs &a, cudaStream_t s)
+{
+    const dim3 g = column_grid(a);
+    const bool ft = a.masks_from_t != 0;
+#define LAI(H, V) (ft ? k_fct_low_antidiff_inner<H, V, true><<<g, kThreads, 0, s>>>(a) : k_fct_low_antidiff_inner<H, V, false><<<g, kThreads, 0, s>>>(a))
+    if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LAI(2, 2);
+    else if (a.kn_fct_h == 2)               LAI(2, 4);
+    else if (a.kn_fct_v == 2)               LAI(4, 2);
+    else                                    LAI(4, 4);
+#undef LAI
+    note_launch();
+}
+
+void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s)
+{
+    static bool attr_set = false;
+    const size_t smem = (size_t)(3 * 4 + 2 * 2) * NY * NX * sizeof(double);
+    if (!attr_set) { cudaFuncSetAttribute(k_fct_nonosc_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    const int ox = NX - 2 * NHALO, oy = NY - 2 * NHALO;
+    const int ni = a.out.i1 - a.out.i0 + 1, nj = a.out.j1 - a.out.j0 + 1;
+    if (ni <= 0 || nj <= 0) return;
+    const dim3 g((unsigned)((ni + ox - 1) / ox), (unsigned)((nj + oy - 1) / oy), (unsigned)a.kjpt);
+    k_fct_nonosc_final<<<g, NX * NY, smem, s>>>(a);
     note_launch();
 }
 

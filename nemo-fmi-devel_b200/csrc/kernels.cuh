@@ -9,7 +9,27 @@
 
 namespace nemo {
 
+// A set of up to 4 disjoint rectangles of (ji,jj) columns (1-based, inclusive) that one launch covers: the whole
+// interior (2:jpim1, 2:jpjm1), the fused inner region, or the boundary frame around it.
+struct Rect { int i0, i1, j0, j1; };
+struct Region {
+    int n = 0;
+    Rect r[4];
+    int start[5] = {0, 0, 0, 0, 0};      // prefix sums of the column counts
+    int ncol() const { return start[n]; }
+    void add(int i0, int i1, int j0, int j1) {
+        if (i1 < i0 || j1 < j0) return;
+        r[n] = Rect{i0, i1, j0, j1};
+        start[n + 1] = start[n] + (i1 - i0 + 1) * (j1 - j0 + 1);
+        ++n;
+    }
+};
+
 struct FctArgs {
+    Region reg;                            // columns this launch works on
+    Rect out;                              // fused nonosc+final kernel: output rectangle
+    int masks_from_t;                      // umask/vmask/wmask are products of tmask (dommsk.F90:176-177,193): derive them
+    double *zlx, *zly, *zlz;               // schedule 1: limited fluxes of the frame path (separate from zwx/zwy/zwz)
     int jpi, jpj, jpk;
     size_t jpij, n3;                       // jpi*jpj, jpi*jpj*jpk
     // dom_oce module arrays
@@ -36,8 +56,10 @@ void launch_fct_betas(const FctArgs &a, cudaStream_t s);
 void launch_fct_limit(const FctArgs &a, cudaStream_t s);
 // P8: final trend                                                           traadv_fct.F90:288-297
 void launch_fct_final(const FctArgs &a, cudaStream_t s);
-// fused P7+P8 (schedule >= 1): no X4 exchange, limited fluxes recomputed at the 6 faces
-void launch_fct_limit_final(const FctArgs &a, cudaStream_t s);
+// schedule 1, inner region: P1-P5 with the 4th-order Laplacian computed in place (no zltu/zltv arrays, no X1)
+void launch_fct_low_antidiff_inner(const FctArgs &a, cudaStream_t s);
+// schedule 1, inner region: nonosc (P6, P7) + final trend (P8) in one kernel, betas shared through shared memory
+void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s);
 
 // interp_4th_cpt                                                            traadv_fct.F90:517-616
 void launch_cpt_pivots(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt,

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -119,6 +120,11 @@ struct nemo_fct_ctx {
     // work arrays (batched over tracers)
     int kjpt_cap = 0; bool have_h4 = false, have_v4 = false;
     DevBuf<double> zwi, zwx, zwy, zwz, zltu, zltv, ztw, zbetup, zbetdo;
+    DevBuf<double> zlx, zly, zlz;                                      // schedule 1: limited fluxes of the frame path
+    bool have_zl = false;
+    int masks_from_t = 0;                                              // umask/vmask/wmask verified to be tmask products
+    cudaStream_t side_stream = nullptr;                                // schedule 1: frame kernels + exchanges
+    cudaEvent_t ev_a = nullptr, ev_k1 = nullptr, ev_t = nullptr;
     // host-variant staging
     int stage_kjpt = 0;
     DevBuf<double> s_pun, s_pvn, s_pwn, s_ptb, s_ptn, s_pta, s_e3t[3], s_cpt_in, s_cpt_out;
@@ -143,9 +149,9 @@ typedef nemo_fct_ctx Ctx;
 // ------------------------------------------------------------------------------------------------------------
 // per-kernel timing with CUDA events on the launching stream
 // ------------------------------------------------------------------------------------------------------------
-enum ProfId { P_LAPLACIAN = 0, P_CPT, P_LOW_ANTIDIFF, P_BETAS, P_LIMIT, P_FINAL, P_LIMIT_FINAL, P_PACK, P_MOVE, P_UNPACK, P_COUNT };
+enum ProfId { P_LAPLACIAN = 0, P_CPT, P_LOW_ANTIDIFF, P_BETAS, P_LIMIT, P_FINAL, P_LOW_INNER, P_NONOSC_FINAL, P_PACK, P_MOVE, P_UNPACK, P_COUNT };
 static const char *kProfName[P_COUNT] = {"fct_laplacian", "interp_4th_cpt", "fct_low_antidiff", "fct_betas", "fct_limit",
-                                         "fct_final", "fct_limit_final", "lbc_pack", "lbc_move_nccl", "lbc_fill_unpack"};
+                                         "fct_final", "fct_low_antidiff_inner", "fct_nonosc_final", "lbc_pack", "lbc_move_nccl", "lbc_fill_unpack"};
 struct ProfScope {
     nemo_fct_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int id;
     static cudaEvent_t get(nemo_fct_ctx *c) {
@@ -431,6 +437,11 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         a.ztw = c->ztw.p; a.zbetup = c->zbetup.p; a.zbetdo = c->zbetdo.p;
         a.p2dt = p2dt; a.kjpt = kjpt; a.kn_fct_h = h; a.kn_fct_v = v; a.ln_linssh = c->ln_linssh; a.ln_isfcav = c->ln_isfcav;
         a.nkchunk = pick_nkchunk(c, kjpt);
+        a.masks_from_t = c->masks_from_t;
+        a.zlx = a.zly = a.zlz = nullptr;
+        a.out = Rect{0, -1, 0, -1};
+        a.reg = Region();
+        a.reg.add(2, a.jpi - 1, 2, a.jpj - 1);                          // the whole interior
     }
     auto exch = [&](const std::vector<DevBuf<double> Ctx::*> &fields, const char *nat, const std::vector<double> &sgn) {
         LnkCall call; call.nfld = (int)fields.size(); call.nat = nat; call.sgn = sgn; call.has_pval = 0; call.pval = 0.0;
@@ -440,22 +451,107 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         return lbc_exchange(g, call);
     };
 #define EACH(id, stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); ProfScope ps(c, id); stmt; }
+#define CPT() EACH(P_CPT, launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p, \
+                                                 c->ln_isfcav, c->cpt_zwt.p, fa[m].ptn, c->ztw.p, c->stream))
+    // schedule 1 needs room for the fused inner region on every subdomain
+    bool fused = g[0]->schedule >= 1;
+    for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < 20 || g[m]->dom.jpj < 20) fused = false;
+
+    if (!fused) {
+        // ---- schedule 0: the reference pass structure, one kernel per pass group, exchanges X1..X4 -------------
+        if (h == 4) {
+            EACH(P_LAPLACIAN, launch_fct_laplacian(fa[m], c->stream));
+            if (exch({&Ctx::zltu, &Ctx::zltv}, "TT", {1.0, 1.0})) return 1;                        // X1 (:209)
+        }
+        if (v == 4) CPT();
+        EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff(fa[m], c->stream));
+        if (exch({&Ctx::zwi, &Ctx::zwx, &Ctx::zwy, &Ctx::zwz}, "TUVW", {1.0, -1.0, -1.0, 1.0})) return 1;   // X2 (:280)
+        EACH(P_BETAS, launch_fct_betas(fa[m], c->stream));
+        if (exch({&Ctx::zbetup, &Ctx::zbetdo}, "TT", {1.0, 1.0})) return 1;                        // X3 (:400)
+        EACH(P_LIMIT, launch_fct_limit(fa[m], c->stream));
+        if (exch({&Ctx::zwx, &Ctx::zwy}, "UV", {-1.0, -1.0})) return 1;                            // X4 (:426)
+        EACH(P_FINAL, launch_fct_final(fa[m], c->stream));
+        CU(cudaGetLastError());
+        return 0;
+    }
+
+    // ---- schedule 1: fused inner region on the main stream, boundary frame + exchanges on the side stream --------
+    // Inner rectangles (1-based): K1 = low_antidiff_inner on (2:jpi-2, 2:jpj-2-f), K2 = nonosc_final on
+    // (4:jpi-4, 4:jpj-4-f), f = 1 on north-fold subdomains (the fold rewrites part of row jpj-1).  Everything K2 reads
+    // lies in K1's rectangle, and nothing either reads is produced by an exchange.  The frame (what is left of the
+    // interior) goes through the reference-structured kernels restricted to bands, with the real X1..X4.
+    std::vector<FctArgs> lap(fa), lowf(fa), k1(fa), k2(fa), bet(fa), lim(fa), fin(fa);
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m];
+        const int jpi = c->dom.jpi, jpj = c->dom.jpj, f = c->dom.npolj != 0 ? 1 : 0;
+        try {
+            CUTHROW(cudaSetDevice(c->device));
+            if (!c->have_zl || c->zlx.n < c->n3 * (size_t)c->kjpt_cap) {
+                const size_t n = c->n3 * (size_t)c->kjpt_cap;
+                CUTHROW(cudaStreamSynchronize(c->stream));
+                for (Ctx *o : g) o->jobcache.clear();
+                DevBuf<double> *arrs[] = {&c->zlx, &c->zly, &c->zlz};
+                for (auto *a : arrs) { a->alloc(n); CUTHROW(cudaMemset(a->p, 0, n * sizeof(double))); }
+                c->have_zl = true;
+            }
+            if (!c->side_stream) {
+                CUTHROW(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+                CUTHROW(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+                CUTHROW(cudaEventCreateWithFlags(&c->ev_k1, cudaEventDisableTiming));
+                CUTHROW(cudaEventCreateWithFlags(&c->ev_t, cudaEventDisableTiming));
+            }
+        } catch (const std::exception &e) { return fail("tra_adv_fct: schedule 1 set-up: %s", e.what()); }
+        auto band = [&](int wW, int wE, int wS, int wN) {
+            Region r;
+            r.add(2, 1 + wW, 2, jpj - 1);
+            r.add(jpi - wE, jpi - 1, 2, jpj - 1);
+            r.add(2 + wW, jpi - wE - 1, 2, 1 + wS);
+            r.add(2 + wW, jpi - wE - 1, jpj - wN, jpj - 1);
+            return r;
+        };
+        k1[m].reg = Region(); k1[m].reg.add(2, jpi - 2, 2, jpj - 2 - f);
+        k2[m].out = Rect{4, jpi - 4, 4, jpj - 4 - f};
+        lowf[m].reg = Region(); lowf[m].reg.add(jpi - 1, jpi - 1, 2, jpj - 1); lowf[m].reg.add(2, jpi - 2, jpj - 1 - f, jpj - 1);
+        lap[m].reg = band(1, 1, 1, 2 + f);
+        fin[m].reg = band(2, 3, 2, 3 + f);
+        lim[m].reg = band(3, 4, 3, 4 + f);
+        bet[m].reg = band(4, 5, 4, 5 + f);
+        for (FctArgs *x : {&lim[m], &fin[m]}) { x->zlx = c->zlx.p; x->zly = c->zly.p; x->zlz = c->zlz.p; }
+        // small launches: one jk chunk is enough for the bands
+        for (FctArgs *x : {&lap[m], &lowf[m], &bet[m], &lim[m], &fin[m]}) x->nkchunk = std::max(1, std::min(8, (c->dom.jpk - 1) / 8));
+    }
+    cudaStream_t side = g[0]->side_stream;
+    std::vector<cudaStream_t> mainst(ng);
+    for (int m = 0; m < ng; ++m) mainst[m] = g[m]->stream;
+    auto to_side = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = side; };
+    auto to_main = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = mainst[m]; };
+    struct Restore { std::function<void()> f; ~Restore() { f(); } } restore{to_main};
+
+    if (v == 4) CPT();                                                                             // ztw, whole interior
+    CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
+    EACH(P_LOW_INNER, launch_fct_low_antidiff_inner(k1[m], c->stream));
+    CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
+    EACH(P_NONOSC_FINAL, launch_fct_nonosc_final(k2[m], c->stream));
+    // frame
+    to_side();
+    CU(cudaStreamWaitEvent(side, g[0]->ev_a, 0));
     if (h == 4) {
-        EACH(P_LAPLACIAN, launch_fct_laplacian(fa[m], c->stream));
-        if (exch({&Ctx::zltu, &Ctx::zltv}, "TT", {1.0, 1.0})) return 1;                            // X1 (:209)
+        EACH(P_LAPLACIAN, launch_fct_laplacian(lap[m], c->stream));
+        if (exch({&Ctx::zltu, &Ctx::zltv}, "TT", {1.0, 1.0})) return 1;                            // X1
     }
-    if (v == 4) {
-        EACH(P_CPT, launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p,
-                                   c->ln_isfcav, c->cpt_zwt.p, fa[m].ptn, c->ztw.p, c->stream));
-    }
-    EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff(fa[m], c->stream));
-    if (exch({&Ctx::zwi, &Ctx::zwx, &Ctx::zwy, &Ctx::zwz}, "TUVW", {1.0, -1.0, -1.0, 1.0})) return 1;   // X2 (:280)
-    EACH(P_BETAS, launch_fct_betas(fa[m], c->stream));
-    if (exch({&Ctx::zbetup, &Ctx::zbetdo}, "TT", {1.0, 1.0})) return 1;                            // X3 (:400)
-    EACH(P_LIMIT, launch_fct_limit(fa[m], c->stream));
-    if (exch({&Ctx::zwx, &Ctx::zwy}, "UV", {-1.0, -1.0})) return 1;                                // X4 (:426)
-    EACH(P_FINAL, launch_fct_final(fa[m], c->stream));
+    EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff(lowf[m], c->stream));
+    CU(cudaStreamWaitEvent(side, g[0]->ev_k1, 0));
+    if (exch({&Ctx::zwi, &Ctx::zwx, &Ctx::zwy, &Ctx::zwz}, "TUVW", {1.0, -1.0, -1.0, 1.0})) return 1;       // X2
+    EACH(P_BETAS, launch_fct_betas(bet[m], c->stream));
+    if (exch({&Ctx::zbetup, &Ctx::zbetdo}, "TT", {1.0, 1.0})) return 1;                            // X3
+    EACH(P_LIMIT, launch_fct_limit(lim[m], c->stream));
+    if (exch({&Ctx::zlx, &Ctx::zly}, "UV", {-1.0, -1.0})) return 1;                                // X4 on the limited copies
+    EACH(P_FINAL, launch_fct_final(fin[m], c->stream));
+    CU(cudaEventRecord(g[0]->ev_t, side));
+    to_main();
+    CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_t, 0));
 #undef EACH
+#undef CPT
     CU(cudaGetLastError());
     return 0;
 }
@@ -557,6 +653,8 @@ int nemo_fct_destroy(nemo_fct_handle h)
     }
     prof_collect(h);
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
+    if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
+    for (cudaEvent_t e : {h->ev_a, h->ev_k1, h->ev_t}) if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -609,8 +707,8 @@ int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int n
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule)
 {
     if (!h) return fail("NULL handle");
-    if (schedule < 0 || schedule > 0) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
-    h->schedule = schedule;
+    if (schedule < 0 || schedule > 1) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
+    for (Ctx *o : h->group) o->schedule = schedule;
     return 0;
 }
 
@@ -625,6 +723,20 @@ int nemo_fct_set_domain_arrays(nemo_fct_handle h, const double *tmask, const dou
         if (mikt[i] < 1 || mikt[i] > h->dom.jpk - 1 || mbkt[i] < 1 || mbkt[i] > h->dom.jpk - 1)
             return fail("nemo_fct_set_domain_arrays: mikt/mbkt out of 1..jpk-1 at horizontal index %zu", i);
     CU(cudaSetDevice(h->device));
+    {   // are umask / vmask / wmask the plain tmask products of dommsk.F90:176-177,193 wherever the inner kernels read them?
+        const int jpi = h->dom.jpi, jpj = h->dom.jpj, jpk = h->dom.jpk;
+        bool ok = true;
+        for (int k = 0; k < jpk && ok; ++k)
+            for (int j = 0; j < jpj - 1 && ok; ++j) {
+                const size_t o = (size_t)k * h->jpij + (size_t)j * jpi;
+                for (int i = 0; i < jpi - 1; ++i) {
+                    const double tm = tmask[o + i];
+                    if (umask[o + i] != tm * tmask[o + i + 1] || vmask[o + i] != tm * tmask[o + i + jpi] ||
+                        wmask[o + i] != (k == 0 ? tm : tm * tmask[o + i - h->jpij])) { ok = false; break; }
+                }
+            }
+        h->masks_from_t = ok ? 1 : 0;
+    }
     try {
         CUTHROW(cudaStreamSynchronize(h->stream));
         struct { DevBuf<double> *d; const double *s; size_t n; } v[] = {

@@ -103,7 +103,7 @@ def oracle_fct(O, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_li
 
 
 def device_fct(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_linssh=False, ln_isfcav=False,
-               host_path=False):
+               host_path=False, schedule=0, nsteps=1):
     """Run the product on cuda:0 through the C ABI: single subdomain (jpni = jpnj = 1) or an in-process group of
     jpni x jpnj subdomains on one GPU.  Returns (global pta, list of local pta)."""
     from oracle import oracle as O   # only for scatter/gather bookkeeping of the test itself
@@ -118,6 +118,7 @@ def device_fct(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_li
     else:
         grp = N.LocalGroup(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, 0)
         ctxs = grp.ctx
+    ctxs[0].set_schedule(schedule)
     for r, c in enumerate(ctxs):
         c.set_domain_arrays(loc["tmask"][r], loc["umask"][r], loc["vmask"][r], loc["wmask"][r], loc["e1e2t"][r],
                             loc["r1_e1e2t"][r], loc["mikt"][r], loc["mbkt"][r], ln_linssh, ln_isfcav)
@@ -130,14 +131,15 @@ def device_fct(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_li
         out = [pta]
     else:
         t = {k: [torch.from_numpy(a).to(dev) for a in loc[k]] for k in ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
-        if n == 1:
-            ctxs[0].tra_adv_fct(1, 1, "TRA", gf["p2dt"], t["pun"][0], t["pvn"][0], t["pwn"][0], t["ptb"][0],
-                                t["ptn"][0], t["pta"][0], kjpt, h, v)
-            ctxs[0].synchronize()
-        else:
-            grp.tra_adv_fct(1, 1, "TRA", gf["p2dt"], t["pun"], t["pvn"], t["pwn"], t["ptb"], t["ptn"], t["pta"],
-                            kjpt, h, v)
-            grp.synchronize()
+        for _ in range(nsteps):
+            if n == 1:
+                ctxs[0].tra_adv_fct(1, 1, "TRA", gf["p2dt"], t["pun"][0], t["pvn"][0], t["pwn"][0], t["ptb"][0],
+                                    t["ptn"][0], t["pta"][0], kjpt, h, v)
+                ctxs[0].synchronize()
+            else:
+                grp.tra_adv_fct(1, 1, "TRA", gf["p2dt"], t["pun"], t["pvn"], t["pwn"], t["ptb"], t["ptn"], t["pta"],
+                                kjpt, h, v)
+                grp.synchronize()
         out = [a.cpu().numpy() for a in t["pta"]]
     glob = w.gather(out, gf["pta"].copy())
     w.close()

@@ -71,3 +71,55 @@ def test_decomposition_invariance_in_process_group(N, O, layout, jperio):
     mono, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, 2, 4, 4)
     got, _ = H.device_fct(N, gf, G, GJ, K, jperio, jpni, jpnj, 2, 4, 4)
     assert np.array_equal(got, mono)
+
+
+# ---- schedule 1: fused inner region + boundary frame on a side stream ------------------------------------------
+@pytest.mark.parametrize("jperio", [0, 1, 4, 6, 7, 3])
+@pytest.mark.parametrize("hv", [(2, 2), (4, 2), (2, 4), (4, 4)])
+def test_schedule1_single_domain_bit_exact(N, O, jperio, hv):
+    h, v = hv
+    G, GJ, K = 75, 44, 11
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=100 + 10 * jperio + h + v)
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, 2, h, v)
+    got, _ = H.device_fct(N, gf, G, GJ, K, jperio, 1, 1, 2, h, v, schedule=1)
+    bad = np.argwhere(got != ref)
+    assert np.array_equal(got, ref), "first mismatches (jn,k,j,i): %s of %d" % (bad[:6].tolist(), len(bad))
+
+
+@pytest.mark.parametrize("flags", [(True, False), (True, True), (False, True)])
+def test_schedule1_linssh_isfcav(N, O, flags):
+    ln_linssh, ln_isfcav = flags
+    G, GJ, K = 48, 40, 9
+    gf = H.random_fields(O, G, GJ, K, 4, kjpt=2, seed=78, ln_linssh=ln_linssh, ln_isfcav=ln_isfcav)
+    for h, v in [(2, 2), (4, 2)]:
+        ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, 4, 1, 1, 2, h, v, ln_linssh=ln_linssh, ln_isfcav=ln_isfcav)
+        got, _ = H.device_fct(N, gf, G, GJ, K, 4, 1, 1, 2, h, v, ln_linssh=ln_linssh, ln_isfcav=ln_isfcav, schedule=1)
+        assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("layout", [(2, 1), (2, 2), (3, 2)])
+@pytest.mark.parametrize("jperio", [0, 4, 6])
+def test_schedule1_decomposition_invariance(N, O, layout, jperio):
+    jpni, jpnj = layout
+    G, GJ, K = 80, 58, 7
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=4)
+    mono, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, 2, 4, 4)
+    got, _ = H.device_fct(N, gf, G, GJ, K, jperio, jpni, jpnj, 2, 4, 4, schedule=1)
+    assert np.array_equal(got, mono)
+
+
+def test_schedule1_repeated_steps_and_non_product_masks(N, O):
+    """(a) three consecutive steps on the same context (persistent buffers, stream/event reuse) equal three oracle
+    steps; (b) masks that are NOT plain tmask products make the inner kernel read umask/vmask/wmask arrays."""
+    G, GJ, K = 60, 41, 8
+    gf = H.random_fields(O, G, GJ, K, 1, kjpt=2, seed=9)
+    ref = gf
+    for _ in range(3):
+        out, _, _ = H.oracle_fct(O, ref, G, GJ, K, 1, 1, 1, 2, 4, 4)
+        ref = dict(ref); ref["pta"] = out
+    got, _ = H.device_fct(N, gf, G, GJ, K, 1, 1, 1, 2, 4, 4, schedule=1, nsteps=3)
+    assert np.array_equal(got, ref["pta"])
+    gf2 = dict(gf); gf2["umask"] = gf["umask"].copy(); gf2["umask"][2, 10:14, 20:30] = 0.0   # e.g. a closed strait
+    ref2, _, _ = H.oracle_fct(O, gf2, G, GJ, K, 1, 1, 1, 2, 4, 4)
+    got2, _ = H.device_fct(N, gf2, G, GJ, K, 1, 1, 1, 2, 4, 4, schedule=1)
+    assert np.array_equal(got2, ref2) and not np.array_equal(ref2, ref["pta"])
