@@ -12,6 +12,9 @@
 // (a > b ? a : b), SIGN(0.5,x) follows the key_nosignedzero override (x >= 0 -> +0.5, lib_fortran.F90:339-351).
 #include "kernels.cuh"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <atomic>
 
 namespace nemo {
@@ -235,6 +238,14 @@ __device__ __forceinline__ double limit_coef(double flux, double bdo_here, doubl
     return zcu * zau + (1.0 - zcu) * zbu;
 }
 
+// Same coefficient with the arithmetic select folded: zcu is exactly 1 or 0, so zcu*zau + (1-zcu)*zbu is zau or zbu
+// (x*1 = x, y*0 = +-0, x + +-0 = x) for finite betas -- and the betas are finite for finite inputs (denominators are
+// >= zrtrn, numerators bounded by 2*zbig).  Identical bits up to the sign of a zero flux; half the MIN chain is skipped.
+__device__ __forceinline__ double limit_coef_sel(double flux, double bdo_here, double bup_next, double bup_here, double bdo_next)
+{
+    return (flux >= 0.0) ? dmin(dmin(1.0, bdo_here), bup_next) : dmin(dmin(1.0, bup_here), bdo_next);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // nonosc P7: monotonic fluxes, in place (traadv_fct.F90:404-425)
 // ------------------------------------------------------------------------------------------------------------
@@ -400,48 +411,100 @@ template <bool FROM_T> struct Masks {
     }
 };
 
+// ---- per-thread asynchronous prefetch ring ---------------------------------------------------------------------
+// The column-marching kernels are latency bound when every level waits for its own HBM loads (ncu: long-scoreboard
+// stalls, ~6 dependent load groups per level).  Each thread therefore streams the values of ITS OWN column two
+// levels ahead with cp.async (LDGSTS) into private shared-memory slots: no registers are held while the loads are
+// in flight and no barrier is needed, because a thread only ever reads the slots it filled itself.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+constexpr int kPfStages = 3;
+enum { F_PTB = 0, F_PTN, F_PTA, F_ZTW, F_PUN, F_PVN, F_PWN, F_E3B, F_E3N, F_E3A, F_TM, F_LOW_COUNT };
+
 // P1-P5 on the inner region with the 4th-order Laplacian zltu/zltv evaluated in place (:195-208 folded into :211-221)
 template <int H, int V, bool FROM_T>
 __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff_inner(const FctArgs a)
 {
+    extern __shared__ double pf_smem[];                 // [kPfStages][F_LOW_COUNT][kThreads]
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
     const size_t toff = (size_t)blockIdx.z * a.n3;
-    const double *ptb = a.ptb + toff, *ptn = a.ptn + toff;
-    double *pta = a.pta + toff, *zwi = a.zwi + toff, *zwx = a.zwx + toff, *zwy = a.zwy + toff, *zwz = a.zwz + toff;
-    const double *ztw = a.ztw + toff;
+    const double *__restrict__ ptb = a.ptb + toff;
+    const double *__restrict__ ptn = a.ptn + toff;
+    double *__restrict__ pta = a.pta + toff;
+    double *__restrict__ zwi = a.zwi + toff;
+    double *__restrict__ zwx = a.zwx + toff;
+    double *__restrict__ zwy = a.zwy + toff;
+    double *__restrict__ zwz = a.zwz + toff;
+    const double *__restrict__ ztw = a.ztw + toff;
+    const double *__restrict__ tmask = a.tmask;
     const Masks<FROM_T> msk{a};
-    const int jpi = a.jpi;
+    const int jpi = a.jpi, jpk = a.jpk;
     const size_t jpij = a.jpij;
     const size_t c2 = (size_t)(jj - 1) * jpi + (ji - 1);
     const double r1 = a.r1_e1e2t[c2];
-    const int mik = a.ln_isfcav ? a.mikt[c2] : 1;
+    const int ktop = a.ln_linssh ? (a.ln_isfcav ? a.mikt[c2] : 1) : 0;     // level whose top flux is pwn*ptb (:146-156)
     const double p2dt = a.p2dt;
     const double r1_6 = 1.0 / 6.0;
 
-    // upstream vertical flux through the top face of level k, wmask through msk (same arithmetic as upstream_w)
-    auto upw = [&](int k) -> double {
+    auto slot = [&](int lev, int f) -> double * { return pf_smem + ((size_t)((lev % kPfStages) * F_LOW_COUNT + f) * kThreads + threadIdx.x); };
+    auto issue = [&](int lev) {                          // own-column values of level `lev`
+        if (lev <= jpk) {
+            const size_t o = c2 + (size_t)(lev - 1) * jpij;
+            cp_async8(slot(lev, F_PTB), ptb + o); cp_async8(slot(lev, F_PTN), ptn + o); cp_async8(slot(lev, F_PTA), pta + o);
+            if (V == 4) cp_async8(slot(lev, F_ZTW), ztw + o);
+            cp_async8(slot(lev, F_PUN), a.pun + o); cp_async8(slot(lev, F_PVN), a.pvn + o); cp_async8(slot(lev, F_PWN), a.pwn + o);
+            cp_async8(slot(lev, F_E3B), a.e3t_b + o); cp_async8(slot(lev, F_E3N), a.e3t_n + o); cp_async8(slot(lev, F_E3A), a.e3t_a + o);
+            cp_async8(slot(lev, F_TM), tmask + o);
+        }
+        cp_async_commit();
+    };
+    // upstream vertical flux through the top face of level k from column values (P2 + P2b, :137-156)
+    auto upw = [&](int k, double w, double tb_k, double tb_km1, double wm) -> double {
         double v = 0.0;
-        if (k >= 2 && k <= a.jpk - 1) {
-            const size_t o = c2 + (size_t)(k - 1) * jpij;
-            const double w = a.pwn[o];
+        if (k >= 2 && k <= jpk - 1) {
             const double zfp_wk = w + fabs(w), zfm_wk = w - fabs(w);
-            v = 0.5 * (zfp_wk * ptb[o] + zfm_wk * ptb[o - jpij]) * msk.w(o, k);
+            v = 0.5 * (zfp_wk * tb_k + zfm_wk * tb_km1) * wm;
         }
-        if (a.ln_linssh) {
-            const int ktop = a.ln_isfcav ? mik : 1;
-            if (k == ktop) { const size_t o = c2 + (size_t)(k - 1) * jpij; v = a.pwn[o] * ptb[o]; }
-        }
+        if (k == ktop) v = w * tb_k;
         return v;
     };
 
-    double upz_k = upw(ka);
-    double tn_m = (ka >= 2) ? ptn[c2 + (size_t)(ka - 2) * jpij] : 0.0;
+    issue(ka); issue(ka + 1);
+    // values of the level above the chunk (once per chunk)
+    double tb_m = 0.0, tn_m = 0.0, tm_m = 0.0;
+    if (ka >= 2) { const size_t om = c2 + (size_t)(ka - 2) * jpij; tb_m = ptb[om]; tn_m = ptn[om]; tm_m = tmask[om]; }
+    double upz_k = 0.0;
+    bool first = true;
     for (int k = ka; k <= kb; ++k) {
         const size_t o = c2 + (size_t)(k - 1) * jpij;
-        const double tb_c = ptb[o], tb_w = ptb[o - 1], tb_e = ptb[o + 1], tb_s = ptb[o - jpi], tb_n = ptb[o + jpi];
-        const double u_c = a.pun[o], u_w = a.pun[o - 1], v_c = a.pvn[o], v_s = a.pvn[o - jpi];
+        issue(k + 2);
+        // neighbour columns: plain loads (L1/L2 hits on lines the neighbouring threads stream), issued before the wait
+        const double tb_w = ptb[o - 1], tb_e = ptb[o + 1], tb_s = ptb[o - jpi], tb_n = ptb[o + jpi];
+        const double u_w = a.pun[o - 1], v_s = a.pvn[o - jpi];
+        const double tn_e = ptn[o + 1], tn_n = ptn[o + jpi];
+        double tn_w = 0.0, tn_ee = 0.0, tn_s = 0.0, tn_nn = 0.0, mu_w = 0.0, mu_c = 0.0, mu_e = 0.0, mv_s = 0.0, mv_c = 0.0, mv_n = 0.0;
+        if (H == 4) {
+            tn_w = ptn[o - 1]; tn_ee = ptn[o + 2]; tn_s = ptn[o - jpi]; tn_nn = ptn[o + 2 * (size_t)jpi];
+            mu_w = msk.u(o - 1); mu_c = msk.u(o); mu_e = msk.u(o + 1);
+            mv_s = msk.v(o - jpi); mv_c = msk.v(o); mv_n = msk.v(o + jpi);
+        }
+        double wm_c = 0.0, wm_p = 0.0;
+        if (!FROM_T) { wm_c = a.wmask[o]; wm_p = a.wmask[o + jpij]; }
+        cp_async_wait<1>();                              // levels k and k+1 of this column have landed
+        const double tb_c = *slot(k, F_PTB), tn_c = *slot(k, F_PTN), ta_c = *slot(k, F_PTA);
+        const double u_c = *slot(k, F_PUN), v_c = *slot(k, F_PVN), w_c = *slot(k, F_PWN);
+        const double e3b = *slot(k, F_E3B), e3n = *slot(k, F_E3N), e3a = *slot(k, F_E3A), tm = *slot(k, F_TM);
+        const double tb_p = *slot(k + 1, F_PTB), w_p = *slot(k + 1, F_PWN), tm_p = *slot(k + 1, F_TM);
+        if (FROM_T) { wm_c = (k == 1) ? tm : tm * tm_m; wm_p = tm_p * tm; }
+        if (first) { upz_k = upw(k, w_c, tb_c, tb_m, wm_c); first = false; }
         double zfp, zfm;
         zfp = u_c + fabs(u_c); zfm = u_c - fabs(u_c);
         const double upx_c = 0.5 * (zfp * tb_c + zfm * tb_e);
@@ -451,20 +514,17 @@ __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff_inner(const FctAr
         const double upy_c = 0.5 * (zfp * tb_c + zfm * tb_n);
         zfp = v_s + fabs(v_s); zfm = v_s - fabs(v_s);
         const double upy_s = 0.5 * (zfp * tb_s + zfm * tb_c);
-        const double upz_kp1 = upw(k + 1);
+        const double upz_kp1 = upw(k + 1, w_p, tb_p, tb_c, wm_p);
         const double ztra = -(upx_c - upx_w + upy_c - upy_s + upz_k - upz_kp1) * r1;
-        const double tm = a.tmask[o];
-        pta[o] = pta[o] + ztra / a.e3t_n[o] * tm;
-        zwi[o] = (a.e3t_b[o] * tb_c + p2dt * ztra) / a.e3t_a[o] * tm;
-        const double tn_c = ptn[o], tn_e = ptn[o + 1], tn_n = ptn[o + jpi];
+        pta[o] = ta_c + ztra / e3n * tm;
+        zwi[o] = (e3b * tb_c + p2dt * ztra) / e3a * tm;
         if (H == 2) {
             zwx[o] = 0.5 * u_c * (tn_c + tn_e) - upx_c;
             zwy[o] = 0.5 * v_c * (tn_c + tn_n) - upy_c;
         } else {
             // ztu(i) = (ptn(i+1)-ptn(i))*umask(i);  zltu(i) = (ztu(i) + ztu(i-1))*r1_6   (:198, :204)
-            const double tn_w = ptn[o - 1], tn_ee = ptn[o + 2], tn_s = ptn[o - jpi], tn_nn = ptn[o + 2 * (size_t)jpi];
-            const double ztu_w = (tn_c - tn_w) * msk.u(o - 1), ztu_c = (tn_e - tn_c) * msk.u(o), ztu_e = (tn_ee - tn_e) * msk.u(o + 1);
-            const double ztv_s = (tn_c - tn_s) * msk.v(o - jpi), ztv_c = (tn_n - tn_c) * msk.v(o), ztv_n = (tn_nn - tn_n) * msk.v(o + jpi);
+            const double ztu_w = (tn_c - tn_w) * mu_w, ztu_c = (tn_e - tn_c) * mu_c, ztu_e = (tn_ee - tn_e) * mu_e;
+            const double ztv_s = (tn_c - tn_s) * mv_s, ztv_c = (tn_n - tn_c) * mv_c, ztv_n = (tn_nn - tn_n) * mv_n;
             const double zltu_c = (ztu_c + ztu_w) * r1_6, zltu_e = (ztu_e + ztu_c) * r1_6;
             const double zltv_c = (ztv_c + ztv_s) * r1_6, zltv_n = (ztv_n + ztv_c) * r1_6;
             const double zC2t_u = tn_c + tn_e, zC2t_v = tn_c + tn_n;
@@ -473,11 +533,196 @@ __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff_inner(const FctAr
         }
         double fz = 0.0;
         if (k >= 2) {
-            if (V == 2) fz = (a.pwn[o] * 0.5 * (tn_c + tn_m) - upz_k) * msk.w(o, k);
-            else        fz = (a.pwn[o] * ztw[o] - upz_k) * msk.w(o, k);
+            if (V == 2) fz = (w_c * 0.5 * (tn_c + tn_m) - upz_k) * wm_c;
+            else        fz = (w_c * (*slot(k, F_ZTW)) - upz_k) * wm_c;
         }
         zwz[o] = fz;
-        upz_k = upz_kp1; tn_m = tn_c;
+        upz_k = upz_kp1; tn_m = tn_c; tm_m = tm; tb_m = tb_c;
+    }
+    cp_async_wait<0>();
+}
+
+// ---- TMA-tiled variant of the inner P1-P5 kernel ----------------------------------------------------------------
+// Same arithmetic as k_fct_low_antidiff_inner, different data movement.  The cp.async variant still issues ~35
+// 8-byte memory instructions per level and thread (ncu: LSU/MIO-throttle bound, L1 hit rate 20 %).  Here one elected
+// thread issues ONE bulk tensor copy (TMA, cp.async.bulk.tensor.3d -> SASS UTMALDG) per array and level for the
+// whole 32x8 tile -- with a 2-column/2-row halo for the arrays that are read at neighbours -- into a 3-stage
+// shared-memory ring guarded by mbarriers; all 256 threads then read own and neighbour values from shared memory.
+// Requires jpi even (TMA global strides are multiples of 16 bytes); otherwise the cp.async variant is used.
+// Box origins are never negative (measured on B200: a negative tile coordinate raises an illegal-instruction error;
+// overhang on the high side is zero-filled): the stencil needs 1 halo cell to the west/south and 2 to the east/north,
+// so the 36x12 box starts at (tile origin - 1) >= 0.  The innermost box coordinate must also be EVEN for fp64 (16-byte
+// aligned start address, measured the same way): tiles start at odd 0-based columns (i0 = 2), so every box -- also
+// the ones without halo -- starts one column west of the tile.
+constexpr int TTX = 32, TTY = 8, TTH = 2, TBW = TTX + 2 * TTH, TBH = TTY + 2 * TTH, TSTAGES = 3;
+enum { TH_PTB = 0, TH_PTN, TH_TM, TH_PUN, TH_PVN, TH_COUNT };                    // boxes with halo
+enum { TP_PTA = 0, TP_ZTW, TP_PWN, TP_E3B, TP_E3N, TP_E3A, TP_COUNT };           // plain boxes
+constexpr int TPW = TTX + 2;                        // plain boxes carry one pad column west (+1 east to stay even)
+constexpr int kTileHaloBytes = TBW * TBH * 8, kTilePlainBytes = TPW * TTY * 8;
+constexpr int kTileStageBytes = TH_COUNT * kTileHaloBytes + TP_COUNT * kTilePlainBytes;
+
+struct TileMaps { CUtensorMap h[TH_COUNT]; CUtensorMap p[TP_COUNT]; };
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+template <int H, int V, bool FROM_T>
+__global__ void __launch_bounds__(TTX * TTY) k_fct_low_antidiff_tma(const FctArgs a, const __grid_constant__ TileMaps maps, Rect rc)
+{
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(tile_smem + TSTAGES * kTileStageBytes);
+    const int lx = threadIdx.x % TTX, ly = threadIdx.x / TTX;
+    const int ox = rc.i0 - 1 + (int)blockIdx.x * TTX, oy = rc.j0 - 1 + (int)blockIdx.y * TTY;   // 0-based tile origin
+    const int jn = (int)blockIdx.z / a.nkchunk, chunk = (int)blockIdx.z % a.nkchunk;
+    const int jpi = a.jpi, jpk = a.jpk;
+    const size_t jpij = a.jpij;
+    int ka, kb;
+    { const int per = (jpk - 1 + a.nkchunk - 1) / a.nkchunk; ka = 1 + chunk * per; kb = min(jpk - 1, ka + per - 1); }
+    const int gi = ox + lx + 1, gj = oy + ly + 1;                                 // 1-based column of this thread
+    const bool active = gi <= rc.i1 && gj <= rc.j1;
+    const int ci = min(gi, jpi - 2), cj = min(gj, a.jpj - 2);                     // clamped: addresses of inactive threads stay legal
+    const size_t toff = (size_t)jn * a.n3;
+    const size_t c2 = (size_t)(cj - 1) * jpi + (ci - 1);
+    double *__restrict__ pta = a.pta + toff;
+    double *__restrict__ zwi = a.zwi + toff;
+    double *__restrict__ zwx = a.zwx + toff;
+    double *__restrict__ zwy = a.zwy + toff;
+    double *__restrict__ zwz = a.zwz + toff;
+    const double r1 = a.r1_e1e2t[c2];
+    const int ktop = a.ln_linssh ? (a.ln_isfcav ? a.mikt[c2] : 1) : 0;
+    const double p2dt = a.p2dt;
+    const double r1_6 = 1.0 / 6.0;
+
+    // descriptor addresses must stay in the kernel-parameter space: take them here, not through a by-reference closure
+    const CUtensorMap *mh = maps.h, *mp = maps.p;
+    auto stage = [&](int lev) -> unsigned char * { return tile_smem + (size_t)(lev % TSTAGES) * kTileStageBytes; };
+    auto issue = [=](int lev) {                          // one thread: all boxes of level `lev`
+        unsigned char *st = tile_smem + (size_t)(lev % TSTAGES) * kTileStageBytes;
+        unsigned long long *bar = &full[lev % TSTAGES];
+        const unsigned bytes = TH_COUNT * kTileHaloBytes + (TP_COUNT - (V == 4 ? 0 : 1)) * kTilePlainBytes;
+        mbar_expect_tx(bar, bytes);
+        const int z3 = lev - 1, z4 = jn * jpk + lev - 1;
+        tma_load_3d(st + TH_PTB * kTileHaloBytes, &mh[TH_PTB], bar, ox - 1, oy - 1, z4);
+        tma_load_3d(st + TH_PTN * kTileHaloBytes, &mh[TH_PTN], bar, ox - 1, oy - 1, z4);
+        tma_load_3d(st + TH_TM * kTileHaloBytes, &mh[TH_TM], bar, ox - 1, oy - 1, z3);
+        tma_load_3d(st + TH_PUN * kTileHaloBytes, &mh[TH_PUN], bar, ox - 1, oy - 1, z3);
+        tma_load_3d(st + TH_PVN * kTileHaloBytes, &mh[TH_PVN], bar, ox - 1, oy - 1, z3);
+        unsigned char *pl = st + TH_COUNT * kTileHaloBytes;
+        tma_load_3d(pl + TP_PTA * kTilePlainBytes, &mp[TP_PTA], bar, ox - 1, oy, z4);
+        if (V == 4) tma_load_3d(pl + TP_ZTW * kTilePlainBytes, &mp[TP_ZTW], bar, ox - 1, oy, z4);
+        tma_load_3d(pl + TP_PWN * kTilePlainBytes, &mp[TP_PWN], bar, ox - 1, oy, z3);
+        tma_load_3d(pl + TP_E3B * kTilePlainBytes, &mp[TP_E3B], bar, ox - 1, oy, z3);
+        tma_load_3d(pl + TP_E3N * kTilePlainBytes, &mp[TP_E3N], bar, ox - 1, oy, z3);
+        tma_load_3d(pl + TP_E3A * kTilePlainBytes, &mp[TP_E3A], bar, ox - 1, oy, z3);
+    };
+    auto upw = [&](int k, double w, double tb_k, double tb_km1, double wm) -> double {
+        double v = 0.0;
+        if (k >= 2 && k <= jpk - 1) {
+            const double zfp_wk = w + fabs(w), zfm_wk = w - fabs(w);
+            v = 0.5 * (zfp_wk * tb_k + zfm_wk * tb_km1) * wm;
+        }
+        if (k == ktop) v = w * tb_k;
+        return v;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TSTAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        issue(ka);
+        issue(ka + 1);                                   // ka + 1 <= jpk always
+    }
+    double tb_m = 0.0, tn_m = 0.0, tm_m = 0.0;
+    if (ka >= 2) { const size_t om = c2 + (size_t)(ka - 2) * jpij; tb_m = a.ptb[toff + om]; tn_m = a.ptn[toff + om]; tm_m = a.tmask[om]; }
+    double upz_k = 0.0;
+    bool first = true;
+    const int hc = (ly + 1) * TBW + (lx + 1), pc = ly * TPW + lx + 1;   // every box starts one cell west (halo boxes also one cell south) of the tile
+    for (int k = ka; k <= kb; ++k) {
+        __syncthreads();                                 // every thread is done with level k-1: its stage is free
+        if (threadIdx.x == 0 && k + 2 <= kb + 1) issue(k + 2);
+        mbar_wait(&full[k % TSTAGES], ((k - ka) / TSTAGES) & 1);
+        mbar_wait(&full[(k + 1) % TSTAGES], ((k + 1 - ka) / TSTAGES) & 1);
+        const double *sh = reinterpret_cast<const double *>(stage(k));
+        const double *sp = sh + TH_COUNT * TBW * TBH;
+        const double *sh1 = reinterpret_cast<const double *>(stage(k + 1));
+        const double *sp1 = sh1 + TH_COUNT * TBW * TBH;
+        const double *s_tb = sh + TH_PTB * TBW * TBH, *s_tn = sh + TH_PTN * TBW * TBH, *s_tm = sh + TH_TM * TBW * TBH;
+        const double *s_u = sh + TH_PUN * TBW * TBH, *s_v = sh + TH_PVN * TBW * TBH;
+        const double tb_c = s_tb[hc], tb_w = s_tb[hc - 1], tb_e = s_tb[hc + 1], tb_s = s_tb[hc - TBW], tb_n = s_tb[hc + TBW];
+        const double u_c = s_u[hc], u_w = s_u[hc - 1], v_c = s_v[hc], v_s = s_v[hc - TBW];
+        const double tn_c = s_tn[hc], tn_e = s_tn[hc + 1], tn_n = s_tn[hc + TBW];
+        const double tm = s_tm[hc];
+        const double ta_c = sp[TP_PTA * TPW * TTY + pc], w_c = sp[TP_PWN * TPW * TTY + pc];
+        const double e3b = sp[TP_E3B * TPW * TTY + pc], e3n = sp[TP_E3N * TPW * TTY + pc], e3a = sp[TP_E3A * TPW * TTY + pc];
+        const double tb_p = sh1[TH_PTB * TBW * TBH + hc], tm_p = sh1[TH_TM * TBW * TBH + hc], w_p = sp1[TP_PWN * TPW * TTY + pc];
+        const size_t o = c2 + (size_t)(k - 1) * jpij;
+        double wm_c, wm_p;
+        if (FROM_T) { wm_c = (k == 1) ? tm : tm * tm_m; wm_p = tm_p * tm; }
+        else { wm_c = a.wmask[o]; wm_p = a.wmask[o + jpij]; }
+        if (first) { upz_k = upw(k, w_c, tb_c, tb_m, wm_c); first = false; }
+        double zfp, zfm;
+        zfp = u_c + fabs(u_c); zfm = u_c - fabs(u_c);
+        const double upx_c = 0.5 * (zfp * tb_c + zfm * tb_e);
+        zfp = u_w + fabs(u_w); zfm = u_w - fabs(u_w);
+        const double upx_w = 0.5 * (zfp * tb_w + zfm * tb_c);
+        zfp = v_c + fabs(v_c); zfm = v_c - fabs(v_c);
+        const double upy_c = 0.5 * (zfp * tb_c + zfm * tb_n);
+        zfp = v_s + fabs(v_s); zfm = v_s - fabs(v_s);
+        const double upy_s = 0.5 * (zfp * tb_s + zfm * tb_c);
+        const double upz_kp1 = upw(k + 1, w_p, tb_p, tb_c, wm_p);
+        const double ztra = -(upx_c - upx_w + upy_c - upy_s + upz_k - upz_kp1) * r1;
+        const double new_ta = ta_c + ztra / e3n * tm;
+        const double new_wi = (e3b * tb_c + p2dt * ztra) / e3a * tm;
+        double fx, fy;
+        if (H == 2) {
+            fx = 0.5 * u_c * (tn_c + tn_e) - upx_c;
+            fy = 0.5 * v_c * (tn_c + tn_n) - upy_c;
+        } else {
+            const double tn_w = s_tn[hc - 1], tn_ee = s_tn[hc + 2], tn_s = s_tn[hc - TBW], tn_nn = s_tn[hc + 2 * TBW];
+            double mu_w, mu_c, mu_e, mv_s, mv_c, mv_n;
+            if (FROM_T) {
+                const double tm_w = s_tm[hc - 1], tm_e = s_tm[hc + 1], tm_ee = s_tm[hc + 2];
+                const double tm_s = s_tm[hc - TBW], tm_n = s_tm[hc + TBW], tm_nn = s_tm[hc + 2 * TBW];
+                mu_w = tm_w * tm; mu_c = tm * tm_e; mu_e = tm_e * tm_ee;
+                mv_s = tm_s * tm; mv_c = tm * tm_n; mv_n = tm_n * tm_nn;
+            } else {
+                mu_w = a.umask[o - 1]; mu_c = a.umask[o]; mu_e = a.umask[o + 1];
+                mv_s = a.vmask[o - jpi]; mv_c = a.vmask[o]; mv_n = a.vmask[o + jpi];
+            }
+            const double ztu_w = (tn_c - tn_w) * mu_w, ztu_c = (tn_e - tn_c) * mu_c, ztu_e = (tn_ee - tn_e) * mu_e;
+            const double ztv_s = (tn_c - tn_s) * mv_s, ztv_c = (tn_n - tn_c) * mv_c, ztv_n = (tn_nn - tn_n) * mv_n;
+            const double zltu_c = (ztu_c + ztu_w) * r1_6, zltu_e = (ztu_e + ztu_c) * r1_6;
+            const double zltv_c = (ztv_c + ztv_s) * r1_6, zltv_n = (ztv_n + ztv_c) * r1_6;
+            const double zC2t_u = tn_c + tn_e, zC2t_v = tn_c + tn_n;
+            fx = 0.5 * u_c * (zC2t_u + zltu_c - zltu_e) - upx_c;
+            fy = 0.5 * v_c * (zC2t_v + zltv_c - zltv_n) - upy_c;
+        }
+        double fz = 0.0;
+        if (k >= 2) {
+            if (V == 2) fz = (w_c * 0.5 * (tn_c + tn_m) - upz_k) * wm_c;
+            else        fz = (w_c * sp[TP_ZTW * TPW * TTY + pc] - upz_k) * wm_c;
+        }
+        if (active) { pta[o] = new_ta; zwi[o] = new_wi; zwx[o] = fx; zwy[o] = fy; zwz[o] = fz; }
+        upz_k = upz_kp1; tn_m = tn_c; tm_m = tm; tb_m = tb_c;
     }
 }
 
@@ -489,7 +734,7 @@ __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff_inner(const FctAr
 // fluxes ever reach HBM; X3 / X4 are not needed because no cell of the tile is touched by an exchange.
 constexpr int NX = 32, NY = 16, NHALO = 2;
 
-__global__ void __launch_bounds__(NX * NY) k_fct_nonosc_final(const FctArgs a)
+__global__ void __launch_bounds__(NX * NY, 2) k_fct_nonosc_final(const FctArgs a)
 {
     extern __shared__ double fct_smem[];
     double(*sA)[4][NY][NX] = reinterpret_cast<double(*)[4][NY][NX]>(fct_smem);                          // [level % 3][zbup, zbdo, paa, pbb]
@@ -560,13 +805,13 @@ __global__ void __launch_bounds__(NX * NY) k_fct_nonosc_final(const FctArgs a)
             const double bup_e = Bm[0][ty][tx + 1], bdo_e = Bm[1][ty][tx + 1], bup_w = Bm[0][ty][tx - 1], bdo_w = Bm[1][ty][tx - 1];
             const double bup_n = Bm[0][ty + 1][tx], bdo_n = Bm[1][ty + 1][tx], bup_s = Bm[0][ty - 1][tx], bdo_s = Bm[1][ty - 1][tx];
             const double paa_w = Am[2][ty][tx - 1], pbb_s = Am[3][ty - 1][tx];
-            const double lx_e = paa_m * limit_coef(paa_m, bdo_m, bup_e, bup_m, bdo_e);
-            const double lx_w = paa_w * limit_coef(paa_w, bdo_w, bup_m, bup_w, bdo_m);
-            const double ly_n = pbb_m * limit_coef(pbb_m, bdo_m, bup_n, bup_m, bdo_n);
-            const double ly_s = pbb_s * limit_coef(pbb_s, bdo_s, bup_m, bup_s, bdo_m);
+            const double lx_e = paa_m * limit_coef_sel(paa_m, bdo_m, bup_e, bup_m, bdo_e);
+            const double lx_w = paa_w * limit_coef_sel(paa_w, bdo_w, bup_m, bup_w, bdo_m);
+            const double ly_n = pbb_m * limit_coef_sel(pbb_m, bdo_m, bup_n, bup_m, bdo_n);
+            const double ly_s = pbb_s * limit_coef_sel(pbb_s, bdo_s, bup_m, bup_s, bdo_m);
             // pcc(jk+1) is limited with betas(jk), betas(jk+1) (:419-422); pcc(:,:,1) is never limited
-            const double lz_t = (kk == 1) ? pcc_m : pcc_m * limit_coef(pcc_m, bdo_m, bup_mm, bup_m, bdo_mm);
-            const double lz_b = pcc_k * limit_coef(pcc_k, bdo_c, bup_m, bup_c, bdo_m);
+            const double lz_t = (kk == 1) ? pcc_m : pcc_m * limit_coef_sel(pcc_m, bdo_m, bup_mm, bup_m, bdo_mm);
+            const double lz_b = pcc_k * limit_coef_sel(pcc_k, bdo_c, bup_m, bup_c, bdo_m);
             const size_t om = o - jpij;
             pta[om] = pta[om] - (lx_e - lx_w + ly_n - ly_s + lz_t - lz_b) * r1 / e3n_m;
         }
@@ -604,13 +849,69 @@ void launch_fct_low_antidiff_inner(const FctArgs &a, cudaStream_t s)
 {
     const dim3 g = column_grid(a);
     const bool ft = a.masks_from_t != 0;
-#define LAI(H, V) (ft ? k_fct_low_antidiff_inner<H, V, true><<<g, kThreads, 0, s>>>(a) : k_fct_low_antidiff_inner<H, V, false><<<g, kThreads, 0, s>>>(a))
+    const size_t smem = (size_t)kPfStages * F_LOW_COUNT * kThreads * sizeof(double);   // 33 KB: below the 48 KB opt-in limit
+#define LAI(H, V) (ft ? k_fct_low_antidiff_inner<H, V, true><<<g, kThreads, smem, s>>>(a) : k_fct_low_antidiff_inner<H, V, false><<<g, kThreads, smem, s>>>(a))
     if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LAI(2, 2);
     else if (a.kn_fct_h == 2)               LAI(2, 4);
     else if (a.kn_fct_v == 2)               LAI(4, 2);
     else                                    LAI(4, 4);
 #undef LAI
     note_launch();
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+static bool make_tile_map(CUtensorMap *m, const double *base, int jpi, int jpj, long long nlev, int bw, int bh)
+{
+    auto enc = tensor_map_encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15u)) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)jpi, (cuuint64_t)jpj, (cuuint64_t)nlev};
+    cuuint64_t strides[2] = {(cuuint64_t)jpi * 8, (cuuint64_t)jpi * jpj * 8};
+    cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool launch_fct_low_antidiff_tma(const FctArgs &a, cudaStream_t s)
+{
+    if ((a.jpi & 1) || a.reg.n != 1 || (a.reg.r[0].i0 & 1)) return false;   // 16-byte strides and even box origins
+    TileMaps tm;
+    const long long n4 = (long long)a.jpk * a.kjpt, n3 = a.jpk;
+    bool ok = make_tile_map(&tm.h[TH_PTB], a.ptb, a.jpi, a.jpj, n4, TBW, TBH) && make_tile_map(&tm.h[TH_PTN], a.ptn, a.jpi, a.jpj, n4, TBW, TBH) &&
+              make_tile_map(&tm.h[TH_TM], a.tmask, a.jpi, a.jpj, n3, TBW, TBH) && make_tile_map(&tm.h[TH_PUN], a.pun, a.jpi, a.jpj, n3, TBW, TBH) &&
+              make_tile_map(&tm.h[TH_PVN], a.pvn, a.jpi, a.jpj, n3, TBW, TBH) && make_tile_map(&tm.p[TP_PTA], a.pta, a.jpi, a.jpj, n4, TPW, TTY) &&
+              make_tile_map(&tm.p[TP_ZTW], a.kn_fct_v == 4 ? a.ztw : a.pta, a.jpi, a.jpj, n4, TPW, TTY) &&
+              make_tile_map(&tm.p[TP_PWN], a.pwn, a.jpi, a.jpj, n3, TPW, TTY) && make_tile_map(&tm.p[TP_E3B], a.e3t_b, a.jpi, a.jpj, n3, TPW, TTY) &&
+              make_tile_map(&tm.p[TP_E3N], a.e3t_n, a.jpi, a.jpj, n3, TPW, TTY) && make_tile_map(&tm.p[TP_E3A], a.e3t_a, a.jpi, a.jpj, n3, TPW, TTY);
+    if (!ok) return false;
+    const Rect rc = a.reg.r[0];
+    const size_t smem = (size_t)TSTAGES * kTileStageBytes + 64;
+    const dim3 g((unsigned)((rc.i1 - rc.i0 + 1 + TTX - 1) / TTX), (unsigned)((rc.j1 - rc.j0 + 1 + TTY - 1) / TTY), (unsigned)(a.kjpt * a.nkchunk));
+    const bool ft = a.masks_from_t != 0;
+#define LAT(H, V, F) do { static bool set = false; if (!set) { cudaFuncSetAttribute(k_fct_low_antidiff_tma<H, V, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; } \
+                          k_fct_low_antidiff_tma<H, V, F><<<g, TTX * TTY, smem, s>>>(a, tm, rc); } while (0)
+#define LAT2(H, V) do { if (ft) LAT(H, V, true); else LAT(H, V, false); } while (0)
+    if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LAT2(2, 2);
+    else if (a.kn_fct_h == 2)               LAT2(2, 4);
+    else if (a.kn_fct_v == 2)               LAT2(4, 2);
+    else                                    LAT2(4, 4);
+#undef LAT2
+#undef LAT
+    note_launch();
+    return true;
 }
 
 void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s)

@@ -58,6 +58,8 @@ void launch_fct_limit(const FctArgs &a, cudaStream_t s);
 void launch_fct_final(const FctArgs &a, cudaStream_t s);
 // schedule 1, inner region: P1-P5 with the 4th-order Laplacian computed in place (no zltu/zltv arrays, no X1)
 void launch_fct_low_antidiff_inner(const FctArgs &a, cudaStream_t s);
+// same, with TMA-staged 32x8 tiles (+halo) in a 3-stage shared-memory ring; false if TMA cannot be used (odd jpi)
+bool launch_fct_low_antidiff_tma(const FctArgs &a, cudaStream_t s);
 // schedule 1, inner region: nonosc (P6, P7) + final trend (P8) in one kernel, betas shared through shared memory
 void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s);
 

@@ -529,7 +529,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
 
     if (v == 4) CPT();                                                                             // ztw, whole interior
     CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
-    EACH(P_LOW_INNER, launch_fct_low_antidiff_inner(k1[m], c->stream));
+    EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1[m], c->stream))) launch_fct_low_antidiff_inner(k1[m], c->stream));
     CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
     EACH(P_NONOSC_FINAL, launch_fct_nonosc_final(k2[m], c->stream));
     // frame
@@ -707,7 +707,7 @@ int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int n
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule)
 {
     if (!h) return fail("NULL handle");
-    if (schedule < 0 || schedule > 1) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
+    if (schedule < 0 || schedule > 2) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
     for (Ctx *o : h->group) o->schedule = schedule;
     return 0;
 }

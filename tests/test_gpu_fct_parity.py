@@ -123,3 +123,43 @@ def test_schedule1_repeated_steps_and_non_product_masks(N, O):
     ref2, _, _ = H.oracle_fct(O, gf2, G, GJ, K, 1, 1, 1, 2, 4, 4)
     got2, _ = H.device_fct(N, gf2, G, GJ, K, 1, 1, 1, 2, 4, 4, schedule=1)
     assert np.array_equal(got2, ref2) and not np.array_equal(ref2, ref["pta"])
+
+
+# ---- schedule 2: the inner P1-P5 kernel with TMA-staged tiles (even jpi) ------------------------------------------
+@pytest.mark.parametrize("jperio", [0, 1, 4, 6])
+@pytest.mark.parametrize("hv", [(2, 2), (4, 2), (2, 4), (4, 4)])
+def test_schedule2_tma_tiles_bit_exact(N, O, jperio, hv):
+    h, v = hv
+    G, GJ, K = 76, 45, 11                       # even jpiglo: TMA path; tiles overhang the inner rectangle
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=200 + 10 * jperio + h + v)
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, 2, h, v)
+    got, _ = H.device_fct(N, gf, G, GJ, K, jperio, 1, 1, 2, h, v, schedule=2)
+    bad = np.argwhere(got != ref)
+    assert np.array_equal(got, ref), "first mismatches (jn,k,j,i): %s of %d" % (bad[:6].tolist(), len(bad))
+
+
+def test_schedule2_variants(N, O):
+    """linssh / isfcav, non-product masks (array-reading template), odd jpi (falls back to the cp.async kernel),
+    in-process 2x2 group, 3 steps."""
+    G, GJ, K = 64, 50, 9
+    for ln_linssh, ln_isfcav in [(True, False), (True, True)]:
+        gf = H.random_fields(O, G, GJ, K, 4, kjpt=2, seed=31, ln_linssh=ln_linssh, ln_isfcav=ln_isfcav)
+        ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, 4, 1, 1, 2, 4, 2, ln_linssh=ln_linssh, ln_isfcav=ln_isfcav)
+        got, _ = H.device_fct(N, gf, G, GJ, K, 4, 1, 1, 2, 4, 2, ln_linssh=ln_linssh, ln_isfcav=ln_isfcav, schedule=2)
+        assert np.array_equal(got, ref)
+    gf = H.random_fields(O, G, GJ, K, 1, kjpt=3, seed=32)
+    gf["vmask"] = gf["vmask"].copy(); gf["vmask"][1, 20:24, 10:30] = 0.0
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, 1, 1, 1, 3, 4, 4)
+    got, _ = H.device_fct(N, gf, G, GJ, K, 1, 1, 1, 3, 4, 4, schedule=2)
+    assert np.array_equal(got, ref)
+    gf = H.random_fields(O, 63, GJ, K, 6, kjpt=2, seed=33)
+    ref, _, _ = H.oracle_fct(O, gf, 63, GJ, K, 6, 1, 1, 2, 4, 4)
+    got, _ = H.device_fct(N, gf, 63, GJ, K, 6, 1, 1, 2, 4, 4, schedule=2)
+    assert np.array_equal(got, ref)
+    gf = H.random_fields(O, 90, 70, K, 4, kjpt=2, seed=34)
+    ref = gf
+    for _ in range(3):
+        out, _, _ = H.oracle_fct(O, ref, 90, 70, K, 4, 1, 1, 2, 4, 4)
+        ref = dict(ref); ref["pta"] = out
+    got, _ = H.device_fct(N, gf, 90, 70, K, 4, 2, 2, 2, 4, 4, schedule=2, nsteps=3)
+    assert np.array_equal(got, ref["pta"])
