@@ -822,6 +822,124 @@ __global__ void __launch_bounds__(NX * NY, 2) k_fct_nonosc_final(const FctArgs a
     }
 }
 
+// ---- TMA-fed variant of the fused nonosc + final kernel ---------------------------------------------------------
+// Same tile, same arithmetic; the six streamed arrays (ptb, zwi, tmask, zwz of level jk+1; zwx, zwy of level jk) arrive
+// as 32x16 boxes through a 2-stage TMA ring one level ahead instead of per-thread loads consumed on arrival (ncu on the
+// LDG variant: 2 barriers per level with every warp waiting for HBM).  zbup/zbdo/paa/pbb and the betas are exchanged
+// through single-buffered shared planes (two barriers per level order the reuse).  Needs even jpi and an odd out.i0.
+enum { NQ_PTB = 0, NQ_ZWI, NQ_TM, NQ_PCC, NQ_PAA, NQ_PBB, NQ_COUNT };
+constexpr int kNqBoxBytes = NX * NY * 8, kNqStageBytes = NQ_COUNT * kNqBoxBytes;
+struct NonoscMaps { CUtensorMap m[NQ_COUNT]; };
+
+__global__ void __launch_bounds__(NX * NY, 2) k_fct_nonosc_final_tma(const FctArgs a, const __grid_constant__ NonoscMaps maps)
+{
+    extern __shared__ __align__(128) unsigned char nq_smem[];
+    double(*sA)[NY][NX] = reinterpret_cast<double(*)[NY][NX]>(nq_smem + 2 * kNqStageBytes);                     // zbup, zbdo, paa, pbb
+    double(*sB)[NY][NX] = reinterpret_cast<double(*)[NY][NX]>(nq_smem + 2 * kNqStageBytes + 4 * kNqBoxBytes);   // zbetup, zbetdo
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(nq_smem + 2 * kNqStageBytes + 6 * kNqBoxBytes);
+    const CUtensorMap *mq = maps.m;
+    const int tx = threadIdx.x % NX, ty = threadIdx.x / NX;
+    const int ox = NX - 2 * NHALO, oy = NY - 2 * NHALO;
+    const int bx0 = a.out.i0 - 1 + (int)blockIdx.x * ox - NHALO, by0 = a.out.j0 - 1 + (int)blockIdx.y * oy - NHALO;   // 0-based box origin
+    const int gi = bx0 + tx + 1, gj = by0 + ty + 1;
+    const int ji = min(gi, a.out.i1 + NHALO), jj = min(gj, a.out.j1 + NHALO);
+    const bool is_out = tx >= NHALO && tx < NX - NHALO && ty >= NHALO && ty < NY - NHALO && gi <= a.out.i1 && gj <= a.out.j1;
+    const bool is_beta = tx >= 1 && tx < NX - 1 && ty >= 1 && ty < NY - 1;
+    const int jn = (int)blockIdx.z;
+    const size_t toff = (size_t)jn * a.n3;
+    double *__restrict__ pta = a.pta + toff;
+    const double *__restrict__ e3t_n = a.e3t_n;
+    const int jpi = a.jpi, jpk = a.jpk;
+    const size_t jpij = a.jpij;
+    const size_t c2 = (size_t)(jj - 1) * jpi + (ji - 1);
+    const double zrtrn = 1.e-15;
+    const double e12 = a.e1e2t[c2], r1 = a.r1_e1e2t[c2];
+    const double p2dt = a.p2dt;
+    const int cell = ty * NX + tx;
+
+    auto issue = [=](int lev) {                          // one thread: the six boxes of level `lev` -> stage lev % 2
+        unsigned char *st = nq_smem + (size_t)(lev & 1) * kNqStageBytes;
+        unsigned long long *bar = &full[lev & 1];
+        mbar_expect_tx(bar, kNqStageBytes);
+        const int z3 = lev - 1, z4 = jn * jpk + lev - 1;
+        tma_load_3d(st + NQ_PTB * kNqBoxBytes, &mq[NQ_PTB], bar, bx0, by0, z4);
+        tma_load_3d(st + NQ_ZWI * kNqBoxBytes, &mq[NQ_ZWI], bar, bx0, by0, z4);
+        tma_load_3d(st + NQ_TM * kNqBoxBytes, &mq[NQ_TM], bar, bx0, by0, z3);
+        tma_load_3d(st + NQ_PCC * kNqBoxBytes, &mq[NQ_PCC], bar, bx0, by0, z4);
+        tma_load_3d(st + NQ_PAA * kNqBoxBytes, &mq[NQ_PAA], bar, bx0, by0, z4);
+        tma_load_3d(st + NQ_PBB * kNqBoxBytes, &mq[NQ_PBB], bar, bx0, by0, z4);
+    };
+    auto stg = [&](int lev, int q) -> const double * { return reinterpret_cast<const double *>(nq_smem + (size_t)(lev & 1) * kNqStageBytes + (size_t)q * kNqBoxBytes); };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        issue(1);
+        issue(2);                                        // jpk >= 3
+    }
+    __syncthreads();
+    mbar_wait(&full[1], 0);                              // level 1
+    double up_m, do_m, up_c, do_c, up_p = 0.0, do_p = 0.0;
+    double aft_c = stg(1, NQ_ZWI)[cell];
+    bup_bdo(stg(1, NQ_PTB)[cell], aft_c, stg(1, NQ_TM)[cell], up_c, do_c);
+    up_m = up_c; do_m = do_c;
+    double pcc_k = stg(1, NQ_PCC)[cell];
+    double bup_mm = 0.0, bdo_mm = 0.0, bup_m = 0.0, bdo_m = 0.0;
+    double paa_m = 0.0, pbb_m = 0.0, pcc_m = 0.0, paa_w_m = 0.0, pbb_s_m = 0.0;
+    double e3n_c = e3t_n[c2], e3n_m = 1.0, pta_m = 0.0;
+
+    for (int k = 1; k <= jpk; ++k) {
+        const size_t o = c2 + (size_t)(k - 1) * jpij;
+        const bool lev = k <= jpk - 1;
+        double paa_c = 0.0, pbb_c = 0.0, pcc_p = 0.0, aft_p = 0.0, e3n_p = 1.0, pta_c = 0.0;
+        if (lev) {
+            e3n_p = e3t_n[o + jpij];                     // consumed one level later
+            if (is_out) pta_c = pta[o];
+            mbar_wait(&full[(k + 1) & 1], (k / 2) & 1);  // level k+1: use index (k+1-1)/2 of its stage
+            aft_p = stg(k + 1, NQ_ZWI)[cell];
+            bup_bdo(stg(k + 1, NQ_PTB)[cell], aft_p, stg(k + 1, NQ_TM)[cell], up_p, do_p);
+            pcc_p = stg(k + 1, NQ_PCC)[cell];
+            paa_c = stg(k, NQ_PAA)[cell]; pbb_c = stg(k, NQ_PBB)[cell];
+            sA[0][ty][tx] = up_c; sA[1][ty][tx] = do_c; sA[2][ty][tx] = paa_c; sA[3][ty][tx] = pbb_c;
+        }
+        __syncthreads();                                 // sA(k) visible; stage k%2 no longer read
+        if (threadIdx.x == 0 && k + 2 <= jpk) issue(k + 2);
+        double bup_c = 0.0, bdo_c = 0.0, paa_w = 0.0, pbb_s = 0.0;
+        if (lev && is_beta) {
+            const double zup = dmax(dmax(dmax(dmax(dmax(dmax(up_c, sA[0][ty][tx - 1]), sA[0][ty][tx + 1]), sA[0][ty - 1][tx]), sA[0][ty + 1][tx]), up_m), up_p);
+            const double zdo = dmin(dmin(dmin(dmin(dmin(dmin(do_c, sA[1][ty][tx - 1]), sA[1][ty][tx + 1]), sA[1][ty - 1][tx]), sA[1][ty + 1][tx]), do_m), do_p);
+            paa_w = sA[2][ty][tx - 1]; pbb_s = sA[3][ty - 1][tx];
+            const double zpos = dmax(0., paa_w) - dmin(0., paa_c) + dmax(0., pbb_s) - dmin(0., pbb_c)
+                              + dmax(0., pcc_p) - dmin(0., pcc_k);
+            const double zneg = dmax(0., paa_c) - dmin(0., paa_w) + dmax(0., pbb_c) - dmin(0., pbb_s)
+                              + dmax(0., pcc_k) - dmin(0., pcc_p);
+            const double zbt = e12 * e3n_c / p2dt;
+            bup_c = (zup - aft_c) / (zpos + zrtrn) * zbt;
+            bdo_c = (aft_c - zdo) / (zneg + zrtrn) * zbt;
+        }
+        if (k >= 2 && is_out) {
+            // final trend of level kk = k-1: the neighbours' betas(kk) are in sB (written at the end of iteration k-1)
+            const int kk = k - 1;
+            const double bup_e = sB[0][ty][tx + 1], bdo_e = sB[1][ty][tx + 1], bup_w = sB[0][ty][tx - 1], bdo_w = sB[1][ty][tx - 1];
+            const double bup_n = sB[0][ty + 1][tx], bdo_n = sB[1][ty + 1][tx], bup_s = sB[0][ty - 1][tx], bdo_s = sB[1][ty - 1][tx];
+            const double lx_e = paa_m * limit_coef_sel(paa_m, bdo_m, bup_e, bup_m, bdo_e);
+            const double lx_w = paa_w_m * limit_coef_sel(paa_w_m, bdo_w, bup_m, bup_w, bdo_m);
+            const double ly_n = pbb_m * limit_coef_sel(pbb_m, bdo_m, bup_n, bup_m, bdo_n);
+            const double ly_s = pbb_s_m * limit_coef_sel(pbb_s_m, bdo_s, bup_m, bup_s, bdo_m);
+            const double lz_t = (kk == 1) ? pcc_m : pcc_m * limit_coef_sel(pcc_m, bdo_m, bup_mm, bup_m, bdo_mm);
+            const double lz_b = pcc_k * limit_coef_sel(pcc_k, bdo_c, bup_m, bup_c, bdo_m);
+            pta[o - jpij] = pta_m - (lx_e - lx_w + ly_n - ly_s + lz_t - lz_b) * r1 / e3n_m;
+        }
+        __syncthreads();                                 // every read of sB(k-1) and sA(k) is done
+        sB[0][ty][tx] = bup_c; sB[1][ty][tx] = bdo_c;
+        up_m = up_c; do_m = do_c; up_c = up_p; do_c = do_p; aft_c = aft_p;
+        bup_mm = bup_m; bdo_mm = bdo_m; bup_m = bup_c; bdo_m = bdo_c;
+        paa_m = paa_c; pbb_m = pbb_c; paa_w_m = paa_w; pbb_s_m = pbb_s; pcc_m = pcc_k; pcc_k = pcc_p;
+        e3n_m = e3n_c; e3n_c = e3n_p; pta_m = pta_c;
+    }
+}
+
 inline dim3 column_grid(const FctArgs &a)
 {
     const long long ncol = a.reg.ncol();
@@ -910,6 +1028,27 @@ bool launch_fct_low_antidiff_tma(const FctArgs &a, cudaStream_t s)
     else                                    LAT2(4, 4);
 #undef LAT2
 #undef LAT
+    note_launch();
+    return true;
+}
+
+bool launch_fct_nonosc_final_tma(const FctArgs &a, cudaStream_t s)
+{
+    const int ni = a.out.i1 - a.out.i0 + 1, nj = a.out.j1 - a.out.j0 + 1;
+    if (ni <= 0 || nj <= 0) return true;
+    if ((a.jpi & 1) || !(a.out.i0 & 1) || a.out.i0 - 1 - NHALO < 0 || a.out.j0 - 1 - NHALO < 0 || a.jpk < 3) return false;
+    NonoscMaps tm;
+    const long long n4 = (long long)a.jpk * a.kjpt, n3 = a.jpk;
+    const bool ok = make_tile_map(&tm.m[NQ_PTB], a.ptb, a.jpi, a.jpj, n4, NX, NY) && make_tile_map(&tm.m[NQ_ZWI], a.zwi, a.jpi, a.jpj, n4, NX, NY) &&
+                    make_tile_map(&tm.m[NQ_TM], a.tmask, a.jpi, a.jpj, n3, NX, NY) && make_tile_map(&tm.m[NQ_PCC], a.zwz, a.jpi, a.jpj, n4, NX, NY) &&
+                    make_tile_map(&tm.m[NQ_PAA], a.zwx, a.jpi, a.jpj, n4, NX, NY) && make_tile_map(&tm.m[NQ_PBB], a.zwy, a.jpi, a.jpj, n4, NX, NY);
+    if (!ok) return false;
+    static bool attr_set = false;
+    const size_t smem = (size_t)2 * kNqStageBytes + 6 * kNqBoxBytes + 64;
+    if (!attr_set) { cudaFuncSetAttribute(k_fct_nonosc_final_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    const int ox = NX - 2 * NHALO, oy = NY - 2 * NHALO;
+    const dim3 g((unsigned)((ni + ox - 1) / ox), (unsigned)((nj + oy - 1) / oy), (unsigned)a.kjpt);
+    k_fct_nonosc_final_tma<<<g, NX * NY, smem, s>>>(a, tm);
     note_launch();
     return true;
 }

@@ -62,6 +62,8 @@ void launch_fct_low_antidiff_inner(const FctArgs &a, cudaStream_t s);
 bool launch_fct_low_antidiff_tma(const FctArgs &a, cudaStream_t s);
 // schedule 1, inner region: nonosc (P6, P7) + final trend (P8) in one kernel, betas shared through shared memory
 void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s);
+// same, streamed arrays through a 2-stage TMA ring; false if TMA cannot be used
+bool launch_fct_nonosc_final_tma(const FctArgs &a, cudaStream_t s);
 
 // interp_4th_cpt                                                            traadv_fct.F90:517-616
 void launch_cpt_pivots(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt,

@@ -510,12 +510,12 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
             return r;
         };
         k1[m].reg = Region(); k1[m].reg.add(2, jpi - 2, 2, jpj - 2 - f);
-        k2[m].out = Rect{4, jpi - 4, 4, jpj - 4 - f};
+        k2[m].out = Rect{5, jpi - 4, 4, jpj - 4 - f};          // i0 odd: even TMA box origin
         lowf[m].reg = Region(); lowf[m].reg.add(jpi - 1, jpi - 1, 2, jpj - 1); lowf[m].reg.add(2, jpi - 2, jpj - 1 - f, jpj - 1);
         lap[m].reg = band(1, 1, 1, 2 + f);
-        fin[m].reg = band(2, 3, 2, 3 + f);
-        lim[m].reg = band(3, 4, 3, 4 + f);
-        bet[m].reg = band(4, 5, 4, 5 + f);
+        fin[m].reg = band(3, 3, 2, 3 + f);
+        lim[m].reg = band(4, 4, 3, 4 + f);
+        bet[m].reg = band(5, 5, 4, 5 + f);
         for (FctArgs *x : {&lim[m], &fin[m]}) { x->zlx = c->zlx.p; x->zly = c->zly.p; x->zlz = c->zlz.p; }
         // small launches: one jk chunk is enough for the bands
         for (FctArgs *x : {&lap[m], &lowf[m], &bet[m], &lim[m], &fin[m]}) x->nkchunk = std::max(1, std::min(8, (c->dom.jpk - 1) / 8));
@@ -531,7 +531,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
     EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1[m], c->stream))) launch_fct_low_antidiff_inner(k1[m], c->stream));
     CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
-    EACH(P_NONOSC_FINAL, launch_fct_nonosc_final(k2[m], c->stream));
+    EACH(P_NONOSC_FINAL, if (!(c->schedule >= 2 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
     // frame
     to_side();
     CU(cudaStreamWaitEvent(side, g[0]->ev_a, 0));

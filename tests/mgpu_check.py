@@ -1,0 +1,73 @@
+"""Multi-GPU parity check (one process per GPU, NCCL halo / north-fold exchange).  Launch on an N-GPU box:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+Every rank builds the same global random inputs on the CPU, runs the ORACLE mono-domain once, runs the product on its
+own subdomain (jpni x jpnj = best partition for N) and compares its interior with the oracle bit for bit, for
+closed / cyclic / T-pivot / F-pivot domains and every kernel schedule."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H          # noqa: E402
+import nemo_fct_b200 as N    # noqa: E402
+from oracle import oracle as O   # noqa: E402
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    dist.init_process_group("nccl", device_id=dev)
+    part = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
+    G, GJ, K, kjpt = 130, 96, 12, 2
+    ok_all = True
+    for jperio in (0, 1, 4, 6):
+        gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=50 + jperio)
+        for (h, v) in ((2, 2), (4, 4)):
+            ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v)
+            for schedule in (0, 1, 2):
+                w = O.World(G, GJ, K, jperio, part[0], part[1])
+                loc = {k: w.scatter(gf[k])[rank] for k in H.DOM_KEYS + ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
+                od = w.doms[rank]
+                dom = N.mpp_init(G, GJ, K, jperio, part[0], part[1], rank + 1)
+                ctx = N.FctContext(dom, lr)
+                ctx.set_schedule(schedule)
+                if world > 1:
+                    idt = torch.zeros(N.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+                    if rank == 0:
+                        idt.copy_(torch.frombuffer(bytearray(N.comm_unique_id()), dtype=torch.uint8))
+                    dist.broadcast(idt, 0)
+                    ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+                ctx.set_domain_arrays(loc["tmask"], loc["umask"], loc["vmask"], loc["wmask"], loc["e1e2t"], loc["r1_e1e2t"],
+                                      loc["mikt"], loc["mbkt"], False, False)
+                ctx.set_e3t(loc["e3t_b"], loc["e3t_n"], loc["e3t_a"])
+                t = {k: torch.from_numpy(loc[k]).to(dev) for k in ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
+                ctx.tra_adv_fct(1, 1, "TRA", gf["p2dt"], t["pun"], t["pvn"], t["pwn"], t["ptb"], t["ptn"], t["pta"], kjpt, h, v)
+                ctx.synchronize()
+                got = t["pta"].cpu().numpy()
+                j0, i0 = od.njmpp - 1, od.nimpp - 1
+                want = ref[..., j0 + od.nldj - 1:j0 + od.nlej, i0 + od.nldi - 1:i0 + od.nlei]
+                mine = got[..., od.nldj - 1:od.nlej, od.nldi - 1:od.nlei]
+                ok = bool(np.array_equal(mine, want))
+                nex, nby = ctx.comm_report()
+                flag = torch.tensor([1 if ok else 0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if rank == 0:
+                    print("jperio=%d h%d/v%d schedule=%d %dx%d: %s (rank0: %d exchanges, %d bytes sent)" %
+                          (jperio, h, v, schedule, part[0], part[1], "BIT-IDENTICAL" if flag.item() else "MISMATCH", nex, nby), flush=True)
+                ok_all = ok_all and bool(flag.item())
+                ctx.close()
+                w.close()
+    if rank == 0:
+        print("MGPU_CHECK", "PASS" if ok_all else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok_all else 1)
+
+
+if __name__ == "__main__":
+    main()
