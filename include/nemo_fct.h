@@ -160,8 +160,14 @@ int nemo_fct_comm_report(nemo_fct_handle h, long long *n_exchanges, long long *b
 int nemo_fct_set_profiling(nemo_fct_handle h, int on);
 int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int name_stride, double *total_ms,
                           long long *calls);
-/* Select the kernel schedule: 0 = reference pass structure (one kernel per pass group, exchanges X1..X4 as in
- * traadv_fct.F90:209,280,400,426); higher = fused schedules.  Results are identical.              */
+/* Select the kernel schedule (results are identical, bit for bit):
+ *   0 = reference pass structure: one kernel per pass group on the whole interior, exchanges X1..X4 as in
+ *       traadv_fct.F90:209,280,400,426;
+ *   1 = fused inner region (P1-P5 with in-place Laplacian; nonosc + final trend in one shared-memory kernel) on the main
+ *       stream, boundary frame + X1..X4 on a side stream; per-thread cp.async prefetch;
+ *   2 = (default) as 1 with TMA-staged tiles for the inner kernels when jpi is even, else falls back to 1.
+ *   3 = as 2, and the fused nonosc kernel also fed by a 2-stage TMA ring (measured slower than 2 on B200: kept for study).
+ * Subdomains smaller than 20 x 20 always use 0.                                                                    */
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule);
 
 #ifdef __cplusplus

@@ -30,6 +30,16 @@ constexpr int kThreads = 128;
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 
+// cp.async (LDGSTS) helpers: 8-byte asynchronous global -> shared copies, grouped
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+
 // interior column owned by this thread: ji in 2..jpim1, jj in 2..jpjm1; returns false when out of range
 __device__ __forceinline__ bool interior_column(int jpi, int jpj, int &ji, int &jj)
 {
@@ -243,7 +253,9 @@ __device__ __forceinline__ double limit_coef(double flux, double bdo_here, doubl
 // >= zrtrn, numerators bounded by 2*zbig).  Identical bits up to the sign of a zero flux; half the MIN chain is skipped.
 __device__ __forceinline__ double limit_coef_sel(double flux, double bdo_here, double bup_next, double bup_here, double bdo_next)
 {
-    return (flux >= 0.0) ? dmin(dmin(1.0, bdo_here), bup_next) : dmin(dmin(1.0, bup_here), bdo_next);
+    const bool pos = flux >= 0.0;
+    const double here = pos ? bdo_here : bup_here, next = pos ? bup_next : bdo_next;
+    return dmin(dmin(1.0, here), next);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -331,45 +343,77 @@ __global__ void __launch_bounds__(kThreads) k_cpt_pivots(int jpi, int jpj, int j
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_interp_4th_cpt(int jpi, int jpj, int jpk, const double *wmask,
-                                                             const int *mikt, const int *mbkt, int ln_isfcav,
-                                                             const double *zwt, const double *pt_in_all,
-                                                             double *pt_out_all)
+// "Simple" columns (no ice-shelf cavity, wet from level 1 to mbkt: every column of tests/BENCH and most of a real ocean)
+// have pivots and masks that follow from mbkt alone: zwt(k) = U(k) for k < mbkt and 1 below, with U the pivot sequence
+// of a full-depth column; wmask(k) = 1 down to mbkt.  k_cpt_classify verifies this per column ONCE against the arrays
+// (bitwise) and the solver then streams only ptn in and ztw out for them.
+__global__ void __launch_bounds__(kThreads) k_cpt_classify(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt,
+                                                           const double *zwt, const double *utab, unsigned char *simple)
+{
+    int ji, jj;
+    if (!interior_column(jpi, jpj, ji, jj)) return;
+    const size_t jpij = (size_t)jpi * jpj, c2 = (size_t)(jj - 1) * jpi + (ji - 1);
+    const int ikb = mbkt[c2];
+    bool ok = mikt[c2] == 1;
+    for (int k = 2; k <= jpk - 1 && ok; ++k) {
+        const size_t o = c2 + (size_t)(k - 1) * jpij;
+        const double zw = (k < ikb) ? utab[k] : 1.0, wm = (k <= ikb) ? 1.0 : 0.0;
+        ok = (zwt[o] == zw) && (wmask[o] == wm);
+    }
+    simple[c2] = ok ? 1 : 0;
+}
+
+// Thomas solve, one thread per column.  Each sweep is strictly sequential in jk; the loads of the next two levels are
+// issued before the current level's dependent arithmetic (division chain) so that they overlap it.
+__global__ void __launch_bounds__(kThreads) k_interp_4th_cpt(int jpi, int jpj, int jpk, const double *__restrict__ wmask,
+                                                             const int *__restrict__ mikt, const int *__restrict__ mbkt,
+                                                             const double *__restrict__ zwt, const unsigned char *__restrict__ simple,
+                                                             const double *__restrict__ utab, const double *__restrict__ pt_in_all,
+                                                             double *__restrict__ pt_out_all)
 {
     int ji, jj;
     if (!interior_column(jpi, jpj, ji, jj)) return;
     const size_t jpij = (size_t)jpi * jpj, n3 = jpij * jpk, c2 = (size_t)(jj - 1) * jpi + (ji - 1);
-    const double *pt_in = pt_in_all + (size_t)blockIdx.z * n3;
-    double *pt_out = pt_out_all + (size_t)blockIdx.z * n3;
+    const double *__restrict__ pt_in = pt_in_all + (size_t)blockIdx.z * n3;
+    double *__restrict__ pt_out = pt_out_all + (size_t)blockIdx.z * n3;
     const int ikt = mikt[c2] + 1, ikb = mbkt[c2];
     const int jpkm1 = jpk - 1;
-    (void)ln_isfcav;
+    const bool smp = simple && simple[c2] != 0;
+    auto pivot = [&](int k) -> double { return smp ? ((k < ikb) ? utab[k] : 1.0) : zwt[c2 + (size_t)(k - 1) * jpij]; };
+    auto wmsk = [&](int k) -> double { return smp ? ((k <= ikb) ? 1.0 : 0.0) : wmask[c2 + (size_t)(k - 1) * jpij]; };
+    auto clampk = [&](int k) -> int { return k < 1 ? 1 : (k > jpk ? jpk : k); };
     // forward sweep: pt_out(k) = zwrm(k) - zwi(k)/zwt(k-1)*pt_out(k-1)   (:590-601)
     double t_km1 = pt_in[c2], z_m = 0.0, zwt_m = 1.0;
+    double t_a = pt_in[c2 + (size_t)(clampk(2) - 1) * jpij], t_b = pt_in[c2 + (size_t)(clampk(3) - 1) * jpij];
+    double p_a = pivot(2), p_b = pivot(clampk(3)), w_a = wmsk(2), w_b = wmsk(clampk(3));
     for (int k = 2; k <= jpkm1; ++k) {
-        const size_t o = c2 + (size_t)(k - 1) * jpij;
-        const double t_k = pt_in[o];
-        const double wm = wmask[o];
+        const double t_k = t_a, zw = p_a, wm = w_a;
+        t_a = t_b; p_a = p_b; w_a = w_b;
+        { const int kn = clampk(k + 2); t_b = pt_in[c2 + (size_t)(kn - 1) * jpij]; p_b = pivot(kn); w_b = wmsk(kn); }
         double rhs, wi;
         if (k == ikt || k == ikb) { rhs = 0.5 * (t_km1 + t_k); wi = 0.0; }        // (:563-571)
         else if (k == 2)          { rhs = 0.0; wi = 0.0; }                         // ln_isfcav preset (:554-556)
         else                      { rhs = 3.0 * wm * (t_k + t_km1); wi = wm; }     // (:538-542)
         double z = rhs;
         if (k >= 3) z = rhs - wi / zwt_m * z_m;
-        pt_out[o] = z;
-        z_m = z; zwt_m = zwt[o]; t_km1 = t_k;
+        pt_out[c2 + (size_t)(k - 1) * jpij] = z;
+        z_m = z; zwt_m = zw; t_km1 = t_k;
     }
-    // back substitution (:603-614)
+    // back substitution (:603-614).  NB pt_out is read back here: the loads below are of levels this thread wrote.
     {
-        const size_t o = c2 + (size_t)(jpkm1 - 1) * jpij;
-        double x = pt_out[o] / zwt[o];
-        pt_out[o] = x;
+        double x = z_m / zwt_m;                                                    // level jpkm1: still in registers
+        pt_out[c2 + (size_t)(jpkm1 - 1) * jpij] = x;
+        const double *rd = pt_out;
+        double z_a = rd[c2 + (size_t)(clampk(jpk - 2) - 1) * jpij], z_b = rd[c2 + (size_t)(clampk(jpk - 3) - 1) * jpij];
+        p_a = pivot(clampk(jpk - 2)); p_b = pivot(clampk(jpk - 3)); w_a = wmsk(clampk(jpk - 2)); w_b = wmsk(clampk(jpk - 3));
         for (int k = jpk - 2; k >= 2; --k) {
-            const size_t q = c2 + (size_t)(k - 1) * jpij;
+            const double z = z_a, zw = p_a, wm = w_a;
+            z_a = z_b; p_a = p_b; w_a = w_b;
+            { const int kn = clampk(k - 2); z_b = rd[c2 + (size_t)(kn - 1) * jpij]; p_b = pivot(kn); w_b = wmsk(kn); }
             double d, s;
-            cpt_row(k, ikt, ikb, wmask[q], d, s);
-            x = (pt_out[q] - s * x) / zwt[q];
-            pt_out[q] = x;
+            cpt_row(k, ikt, ikb, wm, d, s);
+            x = (z - s * x) / zw;
+            pt_out[c2 + (size_t)(k - 1) * jpij] = x;
         }
     }
 }
@@ -416,14 +460,6 @@ template <bool FROM_T> struct Masks {
 // stalls, ~6 dependent load groups per level).  Each thread therefore streams the values of ITS OWN column two
 // levels ahead with cp.async (LDGSTS) into private shared-memory slots: no registers are held while the loads are
 // in flight and no barrier is needed, because a thread only ever reads the slots it filled itself.
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 constexpr int kPfStages = 3;
 enum { F_PTB = 0, F_PTN, F_PTA, F_ZTW, F_PUN, F_PVN, F_PWN, F_E3B, F_E3N, F_E3A, F_TM, F_LOW_COUNT };
 
@@ -765,13 +801,14 @@ __global__ void __launch_bounds__(NX * NY, 2) k_fct_nonosc_final(const FctArgs a
     double pcc_k = pcc[c2];                             // anti-diffusive pcc(jk), pcc(jk+1) rolling
     double bup_mm = 0.0, bdo_mm = 0.0, bup_m = 0.0, bdo_m = 0.0;   // betas of this column at jk-2, jk-1
     double paa_m = 0.0, pbb_m = 0.0, pcc_m = 0.0;       // own fluxes of level jk-1 (pcc_m = pcc(jk-1))
-    double e3n_m = 1.0;
+    double e3n_m = 1.0, pta_m = 0.0;
 
     for (int k = 1; k <= jpk; ++k) {
         const size_t o = c2 + (size_t)(k - 1) * jpij;
         const bool lev = k <= jpk - 1;                  // betas are computed for jk = 1..jpkm1, zbetup/do(jpk) = 0
-        double paa_c = 0.0, pbb_c = 0.0, pcc_p = 0.0, aft_p = 0.0, e3n_c = 1.0;
+        double paa_c = 0.0, pbb_c = 0.0, pcc_p = 0.0, aft_p = 0.0, e3n_c = 1.0, pta_c = 0.0;
         if (lev) {
+            if (is_out) pta_c = pta[o];                  // consumed one level later by the final trend
             aft_p = paft[o + jpij];
             bup_bdo(pbef[o + jpij], aft_p, a.tmask[o + jpij], up_p, do_p);
             paa_c = paa[o]; pbb_c = pbb[o]; pcc_p = pcc[o + jpij];
@@ -813,12 +850,12 @@ __global__ void __launch_bounds__(NX * NY, 2) k_fct_nonosc_final(const FctArgs a
             const double lz_t = (kk == 1) ? pcc_m : pcc_m * limit_coef_sel(pcc_m, bdo_m, bup_mm, bup_m, bdo_mm);
             const double lz_b = pcc_k * limit_coef_sel(pcc_k, bdo_c, bup_m, bup_c, bdo_m);
             const size_t om = o - jpij;
-            pta[om] = pta[om] - (lx_e - lx_w + ly_n - ly_s + lz_t - lz_b) * r1 / e3n_m;
+            pta[om] = pta_m - (lx_e - lx_w + ly_n - ly_s + lz_t - lz_b) * r1 / e3n_m;
         }
         // rotate the column registers
         up_m = up_c; do_m = do_c; up_c = up_p; do_c = do_p; aft_c = aft_p;
         bup_mm = bup_m; bdo_mm = bdo_m; bup_m = bup_c; bdo_m = bdo_c;
-        paa_m = paa_c; pbb_m = pbb_c; pcc_m = pcc_k; pcc_k = pcc_p; e3n_m = e3n_c;
+        paa_m = paa_c; pbb_m = pbb_c; pcc_m = pcc_k; pcc_k = pcc_p; e3n_m = e3n_c; pta_m = pta_c;
     }
 }
 
@@ -1079,12 +1116,22 @@ void launch_cpt_pivots(int jpi, int jpj, int jpk, const double *wmask, const int
     note_launch();
 }
 
+void launch_cpt_classify(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt, const double *zwt,
+                         const double *utab, unsigned char *simple, cudaStream_t s)
+{
+    const long long ncol = (long long)(jpi - 2) * (jpj - 2);
+    k_cpt_classify<<<(unsigned)((ncol + kThreads - 1) / kThreads), kThreads, 0, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, utab, simple);
+    note_launch();
+}
+
 void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
-                           int ln_isfcav, const double *zwt, const double *pt_in, double *pt_out, cudaStream_t s)
+                           int ln_isfcav, const double *zwt, const unsigned char *simple, const double *utab,
+                           const double *pt_in, double *pt_out, cudaStream_t s)
 {
     const long long ncol = (long long)(jpi - 2) * (jpj - 2);
     const dim3 g((unsigned)((ncol + kThreads - 1) / kThreads), 1, (unsigned)nfld);
-    k_interp_4th_cpt<<<g, kThreads, 0, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, ln_isfcav, zwt, pt_in, pt_out);
+    (void)ln_isfcav;
+    k_interp_4th_cpt<<<g, kThreads, 0, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_in, pt_out);
     note_launch();
 }
 

@@ -68,8 +68,12 @@ bool launch_fct_nonosc_final_tma(const FctArgs &a, cudaStream_t s);
 // interp_4th_cpt                                                            traadv_fct.F90:517-616
 void launch_cpt_pivots(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt,
                        int ln_isfcav, double *zwt, cudaStream_t s);
+// per-column check that pivots and wmask follow from mbkt alone (utab = pivots of a full-depth column)
+void launch_cpt_classify(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt, const double *zwt,
+                         const double *utab, unsigned char *simple, cudaStream_t s);
 void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
-                           int ln_isfcav, const double *zwt, const double *pt_in, double *pt_out, cudaStream_t s);
+                           int ln_isfcav, const double *zwt, const unsigned char *simple, const double *utab,
+                           const double *pt_in, double *pt_out, cudaStream_t s);
 // tra_adv transports                                                        traadv.F90:100-124
 void launch_transports(int jpi, int jpj, int jpk, const double *e2u, const double *e1v, const double *e1e2t,
                        const double *e3u_n, const double *e3v_n, const double *un, const double *vn,

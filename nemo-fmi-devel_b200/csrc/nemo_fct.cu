@@ -112,7 +112,8 @@ struct nemo_fct_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     size_t jpij = 0, n3 = 0;
     // dom_oce arrays
-    DevBuf<double> tmask, umask, vmask, wmask, e1e2t, r1_e1e2t, e3t_own[3], cpt_zwt;
+    DevBuf<double> tmask, umask, vmask, wmask, e1e2t, r1_e1e2t, e3t_own[3], cpt_zwt, cpt_utab;
+    DevBuf<unsigned char> cpt_simple;
     DevBuf<int> mikt, mbkt;
     const double *e3t[3] = {nullptr, nullptr, nullptr};
     bool have_dom = false;
@@ -136,7 +137,7 @@ struct nemo_fct_ctx {
     std::vector<nemo_fct_ctx *> group;                                 // in-process communicator (incl. self)
     void *nccl_comm = nullptr; int nccl_nranks = 0;
     long long n_exchanges = 0, bytes_sent = 0;
-    int schedule = 0;
+    int schedule = 2;                                                  // fused inner kernels with TMA tiles where possible
     // per-kernel CUDA-event timing (bench.py's roofline): off by default
     bool profiling = false;
     struct ProfRec { int id; cudaEvent_t a, b; };
@@ -452,7 +453,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     };
 #define EACH(id, stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); ProfScope ps(c, id); stmt; }
 #define CPT() EACH(P_CPT, launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p, \
-                                                 c->ln_isfcav, c->cpt_zwt.p, fa[m].ptn, c->ztw.p, c->stream))
+                                                 c->ln_isfcav, c->cpt_zwt.p, c->cpt_simple.p, c->cpt_utab.p, fa[m].ptn, c->ztw.p, c->stream))
     // schedule 1 needs room for the fused inner region on every subdomain
     bool fused = g[0]->schedule >= 1;
     for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < 20 || g[m]->dom.jpj < 20) fused = false;
@@ -531,7 +532,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
     EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1[m], c->stream))) launch_fct_low_antidiff_inner(k1[m], c->stream));
     CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
-    EACH(P_NONOSC_FINAL, if (!(c->schedule >= 2 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
+    EACH(P_NONOSC_FINAL, if (!(c->schedule >= 3 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
     // frame
     to_side();
     CU(cudaStreamWaitEvent(side, g[0]->ev_a, 0));
@@ -707,7 +708,7 @@ int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int n
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule)
 {
     if (!h) return fail("NULL handle");
-    if (schedule < 0 || schedule > 2) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
+    if (schedule < 0 || schedule > 3) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
     for (Ctx *o : h->group) o->schedule = schedule;
     return 0;
 }
@@ -750,6 +751,15 @@ int nemo_fct_set_domain_arrays(nemo_fct_handle h, const double *tmask, const dou
         h->cpt_zwt.alloc(h->n3);
         CUTHROW(cudaMemset(h->cpt_zwt.p, 0, h->n3 * sizeof(double)));
         launch_cpt_pivots(h->dom.jpi, h->dom.jpj, h->dom.jpk, h->wmask.p, h->mikt.p, h->mbkt.p, ln_isfcav, h->cpt_zwt.p, h->stream);
+        {   // pivots of a full-depth, cavity-free column: row 2 is the 2nd-order top row, rows 3.. are (4,1,1) (traadv_fct.F90:577-588)
+            std::vector<double> u(h->dom.jpk + 1, 1.0);
+            double t_m = 1.0, s_m = 0.0;
+            for (int k = 3; k <= h->dom.jpk - 1; ++k) { const double t = 4.0 - 1.0 * s_m / t_m; u[k] = t; t_m = t; s_m = 1.0; }
+            h->cpt_utab.upload(u);
+            h->cpt_simple.alloc(h->jpij);
+            CUTHROW(cudaMemset(h->cpt_simple.p, 0, h->jpij));
+            launch_cpt_classify(h->dom.jpi, h->dom.jpj, h->dom.jpk, h->wmask.p, h->mikt.p, h->mbkt.p, h->cpt_zwt.p, h->cpt_utab.p, h->cpt_simple.p, h->stream);
+        }
         CUTHROW(cudaStreamSynchronize(h->stream));
         CUTHROW(cudaGetLastError());
     } catch (const std::exception &e) { return fail("nemo_fct_set_domain_arrays: %s", e.what()); }
@@ -884,7 +894,7 @@ int nemo_interp_4th_cpt_dev(nemo_fct_handle h, const double *pt_in, double *pt_o
     if (h->dom.jpk < 3) return fail("interp_4th_cpt: jpk must be >= 3");
     CU(cudaSetDevice(h->device));
     launch_interp_4th_cpt(h->dom.jpi, h->dom.jpj, h->dom.jpk, 1, h->wmask.p, h->mikt.p, h->mbkt.p, h->ln_isfcav,
-                          h->cpt_zwt.p, pt_in, pt_out, h->stream);
+                          h->cpt_zwt.p, h->cpt_simple.p, h->cpt_utab.p, pt_in, pt_out, h->stream);
     CU(cudaGetLastError());
     return 0;
 }

@@ -133,9 +133,10 @@ def test_schedule2_tma_tiles_bit_exact(N, O, jperio, hv):
     G, GJ, K = 76, 45, 11                       # even jpiglo: TMA path; tiles overhang the inner rectangle
     gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=200 + 10 * jperio + h + v)
     ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, 2, h, v)
-    got, _ = H.device_fct(N, gf, G, GJ, K, jperio, 1, 1, 2, h, v, schedule=2)
-    bad = np.argwhere(got != ref)
-    assert np.array_equal(got, ref), "first mismatches (jn,k,j,i): %s of %d" % (bad[:6].tolist(), len(bad))
+    for schedule in (2, 3):
+        got, _ = H.device_fct(N, gf, G, GJ, K, jperio, 1, 1, 2, h, v, schedule=schedule)
+        bad = np.argwhere(got != ref)
+        assert np.array_equal(got, ref), "schedule %d: first mismatches (jn,k,j,i): %s of %d" % (schedule, bad[:6].tolist(), len(bad))
 
 
 def test_schedule2_variants(N, O):
