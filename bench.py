@@ -317,8 +317,21 @@ def main():
         kern[name] = ent
     dominant = max((k for k in kern if k in kbytes), key=lambda k: kern[k]["ms"] * kern[k]["launches_per_step"], default=None)
     achieved = b_alg / (ms_max * 1e-3) / 1e9
+    # measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the committed `ncu --set full`
+    # capture of this workload / schedule at N = 1 (profiles/ncu_traffic.json), summed over the kernels of one step
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as tf:
+            ent = json.load(tf).get("%s:schedule%d" % (args.workload, sched))
+        if ent and world == 1:
+            traffic = int(sum(ent["kernels"].values()))
+            for name in kern:
+                if name in ent["kernels"]:
+                    kern[name]["traffic"] = int(ent["kernels"][name])
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "scope": "whole step per GPU: B_alg = N_local*(32*kjpt+56) bytes over the step time (all kernels + exchanges)",
                 "alg_bytes_per_step": b_alg, "dominant_kernel": dominant, "kernels": kern}
 
