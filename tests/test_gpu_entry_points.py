@@ -1,0 +1,121 @@
+"""The other entry points of the C ABI on the device: interp_4th_cpt (public in the reference, also used by
+tra_adv_cen), the tra_adv transport build, lbc_lnk_multi on device-resident fields with a land value, and the error
+behaviour (non-zero return + message, the shim's ctl_stop path)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(N, O, G, GJ, K, jperio, gf, ln_isfcav=False):
+    dom = N.mpp_init(G, GJ, K, jperio)
+    ctx = N.FctContext(dom, 0)
+    ctx.set_domain_arrays(gf["tmask"], gf["umask"], gf["vmask"], gf["wmask"], gf["e1e2t"], gf["r1_e1e2t"], gf["mikt"], gf["mbkt"],
+                          False, ln_isfcav)
+    ctx.set_e3t(gf["e3t_b"], gf["e3t_n"], gf["e3t_a"])
+    return dom, ctx
+
+
+@pytest.mark.parametrize("ln_isfcav", [False, True])
+def test_interp_4th_cpt_host_and_device(N, O, ln_isfcav):
+    G, GJ, K = 40, 31, 17
+    gf = H.random_fields(O, G, GJ, K, 1, kjpt=1, seed=3, ln_isfcav=ln_isfcav)
+    w = O.World(G, GJ, K, 1)
+    w.doms[0].set_fields(*[gf[k] for k in H.DOM_KEYS], ln_isfcav=ln_isfcav)
+    pt_in = np.ascontiguousarray(gf["ptn"][0])
+    ref = np.full(pt_in.shape, -777.0)
+    O.lib().interp_4th_cpt(w.doms[0].h, pt_in.ctypes.data, ref.ctypes.data)
+    dom, ctx = _ctx(N, O, G, GJ, K, 1, gf, ln_isfcav)
+    got = np.full(pt_in.shape, -777.0)
+    ctx.interp_4th_cpt(pt_in, got)                                 # host pointers
+    sl = (slice(1, -1), slice(1, -1), slice(1, -1))                # defined on (2:jpim1, 2:jpjm1, 2:jpkm1) only
+    assert np.array_equal(got[sl], ref[sl])
+    assert np.all(got[0] == -777.0) and np.all(got[-1] == -777.0) and np.all(got[:, 0] == -777.0)   # nothing else is touched
+    tin = torch.from_numpy(pt_in).cuda(); tout = torch.full_like(tin, -777.0)
+    ctx.interp_4th_cpt(tin, tout); ctx.synchronize()               # device pointers
+    assert np.array_equal(tout.cpu().numpy()[sl], ref[sl])
+    ctx.close(); w.close()
+
+
+def test_tra_adv_transports(N, O):
+    """zun = e2u*e3u_n*un, zvn = e1v*e3v_n*vn, zwn = e1e2t*wn, level jpk zeroed (traadv.F90:100-124)"""
+    G, GJ, K = 33, 26, 9
+    gf = H.random_fields(O, G, GJ, K, 0, kjpt=1, seed=8)
+    rng = np.random.default_rng(0)
+    e2u, e1v = rng.random((GJ, G)) + 1.0, rng.random((GJ, G)) + 1.0
+    e3u, e3v = rng.random((K, GJ, G)) + 1.0, rng.random((K, GJ, G)) + 1.0
+    un, vn, wn = (rng.standard_normal((K, GJ, G)) for _ in range(3))
+    w = O.World(G, GJ, K, 0)
+    w.doms[0].set_fields(*[gf[k] for k in H.DOM_KEYS])
+    ref = [np.full((K, GJ, G), np.nan) for _ in range(3)]
+    O.lib().tra_adv_transports(w.doms[0].h, *[a.ctypes.data for a in (e2u, e1v, e3u, e3v, un, vn, wn)], *[a.ctypes.data for a in ref])
+    dom, ctx = _ctx(N, O, G, GJ, K, 0, gf)
+    t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (e2u, e1v, e3u, e3v, un, vn, wn)]
+    out = [torch.full((K, GJ, G), float("nan"), dtype=torch.float64, device="cuda") for _ in range(3)]
+    ctx.tra_adv_transports(*t, *out); ctx.synchronize()
+    for a, b in zip(out, ref):
+        assert np.array_equal(a.cpu().numpy(), b)
+    ctx.close(); w.close()
+
+
+@pytest.mark.parametrize("jperio", [0, 4, 6])
+def test_lbc_lnk_multi_device_fields_with_pval(N, O, jperio):
+    G, GJ, K = 30, 24, 5
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=1, seed=2)
+    rng = np.random.default_rng(jperio)
+    fields = [rng.standard_normal((K, GJ, G)) for _ in range(4)]
+    w = O.World(G, GJ, K, jperio)
+    ref = [f.copy() for f in fields]
+    import ctypes
+    # oracle with pval = 1 (e.g. masks): call lbc_lnk_multi directly on the single subdomain
+    tab = (ctypes.c_void_p * 4)(*[a.ctypes.data for a in ref])
+    sg = (ctypes.c_double * 4)(1.0, -1.0, -1.0, 1.0)
+    L = O.lib()
+    L.lbc_lnk_multi.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p,
+                                ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int, ctypes.c_double]
+    L.lbc_lnk_multi(w.doms[0].h, b"test", 4, tab, b"TUVF", sg, K, 1, 1.0)
+    dom, ctx = _ctx(N, O, G, GJ, K, jperio, gf)
+    t = [torch.from_numpy(f).cuda() for f in fields]
+    ctx.lbc_lnk_multi("test", t[0], "T", 1.0, t[1], "U", -1.0, t[2], "V", -1.0, t[3], "F", 1.0, pval=1.0)
+    ctx.synchronize()
+    for a, b in zip(t, ref):
+        assert np.array_equal(a.cpu().numpy(), b)
+    ctx.close(); w.close()
+
+
+def test_errors_are_reported_not_swallowed(N, O):
+    G, GJ, K = 24, 22, 6
+    gf = H.random_fields(O, G, GJ, K, 0, kjpt=1, seed=1)
+    dom = N.mpp_init(G, GJ, K, 0)
+    ctx = N.FctContext(dom, 0)
+    a3 = torch.zeros((K, GJ, G), dtype=torch.float64, device="cuda"); a4 = torch.zeros((1, K, GJ, G), dtype=torch.float64, device="cuda")
+    with pytest.raises(N.NemoFctError, match="set_domain_arrays"):
+        ctx.tra_adv_fct(1, 1, "TRA", 1.0, a3, a3, a3, a4, a4, a4, 1, 2, 2)
+    bad = gf["mbkt"].copy(); bad[3, 3] = K + 5
+    with pytest.raises(N.NemoFctError, match="mikt/mbkt"):
+        ctx.set_domain_arrays(gf["tmask"], gf["umask"], gf["vmask"], gf["wmask"], gf["e1e2t"], gf["r1_e1e2t"], gf["mikt"], bad)
+    ctx.set_domain_arrays(gf["tmask"], gf["umask"], gf["vmask"], gf["wmask"], gf["e1e2t"], gf["r1_e1e2t"], gf["mikt"], gf["mbkt"])
+    with pytest.raises(N.NemoFctError, match="set_e3t"):
+        ctx.tra_adv_fct(1, 1, "TRA", 1.0, a3, a3, a3, a4, a4, a4, 1, 2, 2)
+    ctx.set_e3t(gf["e3t_b"], gf["e3t_n"], gf["e3t_a"])
+    with pytest.raises(N.NemoFctError, match="41"):
+        ctx.tra_adv_fct(1, 1, "TRA", 1.0, a3, a3, a3, a4, a4, a4, 1, 41, 2)      # untested scheme of the reference: refused
+    with pytest.raises(N.NemoFctError, match="cd_nat"):
+        ctx.lbc_lnk_multi("x", a3, "Q", 1.0)
+    with pytest.raises(ValueError):
+        ctx.tra_adv_fct(1, 1, "TRA", 1.0, a3, a3, a3, a4, a4, a3, 1, 2, 2)       # wrong shape
+    with pytest.raises(N.NemoFctError, match="schedule"):
+        ctx.set_schedule(9)
+    ctx.close()
+    # a multi-rank subdomain without a communicator cannot exchange: loud error, not a silent local copy
+    dom2 = N.mpp_init(60, 44, K, 1, 2, 1, 1)
+    c2 = N.FctContext(dom2, 0)
+    f = torch.zeros((K, dom2.jpj, dom2.jpi), dtype=torch.float64, device="cuda")
+    with pytest.raises(N.NemoFctError, match="comm_init"):
+        c2.lbc_lnk_multi("x", f, "T", 1.0)
+    c2.close()
