@@ -496,7 +496,11 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
                 c->have_zl = true;
             }
             if (!c->side_stream) {
-                CUTHROW(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+                // highest priority: the frame kernels and NCCL transfers are tiny but sit on the critical path of the
+                // exchange chain; without it their blocks queue behind thousands of pending blocks of the inner kernels
+                int prio_lo = 0, prio_hi = 0;
+                CUTHROW(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+                CUTHROW(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi));
                 CUTHROW(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
                 CUTHROW(cudaEventCreateWithFlags(&c->ev_k1, cudaEventDisableTiming));
                 CUTHROW(cudaEventCreateWithFlags(&c->ev_t, cudaEventDisableTiming));
@@ -528,11 +532,30 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     auto to_main = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = mainst[m]; };
     struct Restore { std::function<void()> f; ~Restore() { f(); } } restore{to_main};
 
+    // K1 is split: a band of 8 columns/rows along the edges of its rectangle (everything X2 and the frame read) goes to
+    // the side stream, so the whole exchange chain X2..X4 starts after a small launch and hides behind K1-centre + K2
+    // on the main stream (what matters at N > 1, where each exchange costs an NCCL round trip).
+    bool split = true;
+    std::vector<FctArgs> k1b(k1), k1c(k1);
+    for (int m = 0; m < ng; ++m) {
+        const Rect r1 = k1[m].reg.r[0];
+        const int w = 8;
+        if (r1.i1 - r1.i0 + 1 < 2 * w + 4 || r1.j1 - r1.j0 + 1 < 2 * w + 3) { split = false; break; }
+        k1b[m].reg = Region();
+        k1b[m].reg.add(r1.i0, r1.i0 + w - 1, r1.j0, r1.j1);                     // i0 = 2: the centre starts at an even column (TMA)
+        k1b[m].reg.add(r1.i1 - w + 1, r1.i1, r1.j0, r1.j1);
+        k1b[m].reg.add(r1.i0 + w, r1.i1 - w, r1.j0, r1.j0 + w - 2);
+        k1b[m].reg.add(r1.i0 + w, r1.i1 - w, r1.j1 - w + 1, r1.j1);
+        k1b[m].nkchunk = std::max(1, std::min(8, (g[m]->dom.jpk - 1) / 8));
+        k1c[m].reg = Region();
+        k1c[m].reg.add(r1.i0 + w, r1.i1 - w, r1.j0 + w - 1, r1.j1 - w);
+    }
+    if (!split) k1c = k1;
+
     if (v == 4) CPT();                                                                             // ztw, whole interior
     CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
-    EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1[m], c->stream))) launch_fct_low_antidiff_inner(k1[m], c->stream));
-    CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
-    EACH(P_NONOSC_FINAL, if (!(c->schedule >= 3 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
+    EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1c[m], c->stream))) launch_fct_low_antidiff_inner(k1c[m], c->stream));
+    if (!split) CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
     // frame
     to_side();
     CU(cudaStreamWaitEvent(side, g[0]->ev_a, 0));
@@ -541,7 +564,12 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         if (exch({&Ctx::zltu, &Ctx::zltv}, "TT", {1.0, 1.0})) return 1;                            // X1
     }
     EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff(lowf[m], c->stream));
-    CU(cudaStreamWaitEvent(side, g[0]->ev_k1, 0));
+    if (split) {
+        EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff_inner(k1b[m], c->stream));
+        CU(cudaEventRecord(g[0]->ev_k1, side));
+    } else {
+        CU(cudaStreamWaitEvent(side, g[0]->ev_k1, 0));
+    }
     if (exch({&Ctx::zwi, &Ctx::zwx, &Ctx::zwy, &Ctx::zwz}, "TUVW", {1.0, -1.0, -1.0, 1.0})) return 1;       // X2
     EACH(P_BETAS, launch_fct_betas(bet[m], c->stream));
     if (exch({&Ctx::zbetup, &Ctx::zbetdo}, "TT", {1.0, 1.0})) return 1;                            // X3
@@ -550,6 +578,8 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     EACH(P_FINAL, launch_fct_final(fin[m], c->stream));
     CU(cudaEventRecord(g[0]->ev_t, side));
     to_main();
+    if (split) CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_k1, 0));                                 // K2 reads the band as well
+    EACH(P_NONOSC_FINAL, if (!(c->schedule >= 3 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
     CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_t, 0));
 #undef EACH
 #undef CPT
