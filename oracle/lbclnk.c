@@ -110,7 +110,6 @@ void oce_world_run(oce_world *w, void (*fn)(oce_dom *, void *), void *arg)
     for (int r = 0; r < w->jpnij; ++r) pthread_join(th[r], NULL);
     free(th); free(ta);
 }
-void oracle_set_num_threads(int n) { (void)n; }
 
 /* --------------------------------------------------------------------------------------------------------- */
 /*  indexing helpers                                                                                         */

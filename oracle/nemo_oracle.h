@@ -103,8 +103,6 @@ void lbc_nfd_generic(const oce_dom *d, int ipi, int ipj_arr, int ipj, int nfld, 
 void oce_world_run(oce_world *w, void (*fn)(oce_dom *, void *), void *arg);
 /* convenience: collective lbc_lnk_multi over all subdomains; ptabs[rank][f] */
 void oce_world_lbc_lnk(oce_world *w, int nfld, double ***ptabs, const char *cd_nat, const double *psgn, int ipk);
-void oracle_set_num_threads(int n);   /* cap on concurrently running subdomain threads is NOT applied: n only
-                                         sets the OpenMP pool used inside single-domain sweeps (0 = default) */
 
 /* ---- traadv_fct.c ---- */
 void tra_adv_fct(oce_dom *d, int kt, int kit000, const char *cdtype, double p2dt,
