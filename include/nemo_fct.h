@@ -14,6 +14,7 @@
  *     (call sites         src/OCE/TRA/traadv.F90:150, src/TOP/TRP/trcadv.F90:127)
  *   interp_4th_cpt        src/OCE/TRA/traadv_fct.F90:517-527      ->  nemo_interp_4th_cpt[_dev]
  *   tra_adv transports    src/OCE/TRA/traadv.F90:100-124          ->  nemo_tra_adv_transports_dev
+ *   tra_adv / trc_adv     src/OCE/TRA/traadv.F90:77, src/TOP/TRP/trcadv.F90:70 -> nemo_tra_adv_dev / nemo_trc_adv_dev
  *   lbc_lnk_multi         src/OCE/LBC/lbc_lnk_multi_generic.h90:16-29 -> nemo_lbc_lnk_multi[_dev]
  *   mynode / MPI_Init     src/OCE/LBC/lib_mpp.F90:197-331         ->  nemo_fct_comm_unique_id / nemo_fct_comm_init
  *   ctl_stop              src/OCE/LBC/lib_mpp.F90:1868-1907       ->  non-zero return + nemo_fct_last_error
@@ -134,6 +135,17 @@ int nemo_interp_4th_cpt_dev(nemo_fct_handle h, const double *pt_in, double *pt_o
 int nemo_tra_adv_transports_dev(nemo_fct_handle h, const double *e2u, const double *e1v, const double *e3u_n,
                                 const double *e3v_n, const double *un, const double *vn, const double *wn,
                                 double *zun, double *zvn, double *zwn);
+
+/* tra_adv (traadv.F90:77-175) for device-resident state, FCT branch (nadv = np_FCT): sets r2dt from (kt, nit000, neuler,
+ * rdt) as :95-97, builds the effective transports from un, vn, wn (Eulerian branch :110-124; Stokes drift, z-tilde, eiv and
+ * mle additions are not applied) into work arrays owned by the context, and calls tra_adv_fct on tsb, tsn, tsa (jpts tracers).
+ * nemo_trc_adv_dev is trc_adv (trcadv.F90:70-145) for the passive tracers: it REUSES the transports of the last
+ * nemo_tra_adv_dev call instead of rebuilding them (the reference recomputes the same three arrays, trcadv.F90:93-108).   */
+int nemo_tra_adv_dev(nemo_fct_handle h, int kt, int nit000, int neuler, double rdt, const double *e2u, const double *e1v,
+                     const double *e3u_n, const double *e3v_n, const double *un, const double *vn, const double *wn,
+                     const double *tsb, const double *tsn, double *tsa, int jpts, int nn_fct_h, int nn_fct_v);
+int nemo_trc_adv_dev(nemo_fct_handle h, int kt, int nittrc000, double r2dttrc, const double *trb, const double *trn,
+                     double *tra, int jptra, int nn_fct_h, int nn_fct_v);
 
 /* lbc_lnk_multi (lbc_lnk_multi_generic.h90:16-29): nfld fields ptab[f] of (jpi,jpj,ipk) each (a 4-D field is a
  * 3-D field with ipk*ipl levels), grid-point type cd_nat[f] in "TUVWF", fold sign psgn[f]; has_pval/pval = the

@@ -95,6 +95,8 @@ def lib():
         "nemo_interp_4th_cpt": [vp, vp, vp],
         "nemo_interp_4th_cpt_dev": [vp, vp, vp],
         "nemo_tra_adv_transports_dev": [vp] * 11,
+        "nemo_tra_adv_dev": [vp, i, i, i, d] + [vp] * 10 + [i, i, i],
+        "nemo_trc_adv_dev": [vp, i, i, d] + [vp] * 3 + [i, i, i],
         "nemo_lbc_lnk_multi": [vp, C.c_char_p, i, C.POINTER(vp), C.c_char_p, dp, i, i, d],
         "nemo_lbc_lnk_multi_dev": [vp, C.c_char_p, i, C.POINTER(vp), C.c_char_p, dp, i, i, d],
         "nemo_group_lbc_lnk_multi_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.c_char_p, dp, i, i, d],
@@ -118,7 +120,7 @@ ABI_SYMBOLS = (
     "nemo_mpp_init nemo_mpp_basic_decomposition nemo_lbc_plan_query nemo_fct_create nemo_fct_destroy "
     "nemo_fct_set_domain_arrays nemo_fct_set_e3t nemo_fct_set_stream nemo_fct_synchronize nemo_fct_comm_unique_id "
     "nemo_fct_comm_init nemo_fct_comm_init_local nemo_tra_adv_fct nemo_tra_adv_fct_dev nemo_group_tra_adv_fct_dev "
-    "nemo_interp_4th_cpt nemo_interp_4th_cpt_dev nemo_tra_adv_transports_dev nemo_lbc_lnk_multi "
+    "nemo_interp_4th_cpt nemo_interp_4th_cpt_dev nemo_tra_adv_transports_dev nemo_tra_adv_dev nemo_trc_adv_dev nemo_lbc_lnk_multi "
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
     "nemo_fct_profile_read").split()
@@ -297,6 +299,19 @@ class FctContext:
         if not all(_is_dev(a) for a in arrs):
             raise ValueError("tra_adv_transports: device tensors only")
         _check(lib().nemo_tra_adv_transports_dev(self._h, *[_ptr(a) for a in arrs]))
+
+    def tra_adv(self, kt, nit000, neuler, rdt, e2u, e1v, e3u_n, e3v_n, un, vn, wn, tsb, tsn, tsa, jpts, nn_fct_h, nn_fct_v):
+        """tra_adv( kt ) of traadv.F90:77 with nadv = np_FCT, module state passed explicitly; device tensors only."""
+        arrs = (e2u, e1v, e3u_n, e3v_n, un, vn, wn, tsb, tsn, tsa)
+        if not all(_is_dev(a) for a in arrs):
+            raise ValueError("tra_adv: device tensors only")
+        _check(lib().nemo_tra_adv_dev(self._h, kt, nit000, neuler, float(rdt), *[_ptr(a) for a in arrs], jpts, nn_fct_h, nn_fct_v))
+
+    def trc_adv(self, kt, nittrc000, r2dttrc, trb, trn, tra, jptra, nn_fct_h, nn_fct_v):
+        """trc_adv( kt ) of trcadv.F90:70 with nadv = np_FCT; reuses the transports built by the last tra_adv call."""
+        if not all(_is_dev(a) for a in (trb, trn, tra)):
+            raise ValueError("trc_adv: device tensors only")
+        _check(lib().nemo_trc_adv_dev(self._h, kt, nittrc000, float(r2dttrc), _ptr(trb), _ptr(trn), _ptr(tra), jptra, nn_fct_h, nn_fct_v))
 
     def lbc_lnk_multi(self, cdname, *triplets, pval=None):
         """lbc_lnk_multi( cdname, pt1, cdna1, psgn1 [, pt2, cdna2, psgn2, ...] [, pval] )

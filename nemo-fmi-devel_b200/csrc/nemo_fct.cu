@@ -122,6 +122,9 @@ struct nemo_fct_ctx {
     int kjpt_cap = 0; bool have_h4 = false, have_v4 = false;
     DevBuf<double> zwi, zwx, zwy, zwz, zltu, zltv, ztw, zbetup, zbetdo;
     DevBuf<double> zlx, zly, zlz;                                      // schedule 1: limited fluxes of the frame path
+    DevBuf<double> zun, zvn, zwn;                                      // effective transports of tra_adv, reused by trc_adv
+    bool have_trp = false;
+    double r2dt = 0.0;                                                 // tracer time step of tra_adv (traadv.F90:95-97), persists across calls
     bool have_zl = false;
     int masks_from_t = 0;                                              // umask/vmask/wmask verified to be tmask products
     cudaStream_t side_stream = nullptr;                                // schedule 1: frame kernels + exchanges
@@ -954,6 +957,34 @@ int nemo_tra_adv_transports_dev(nemo_fct_handle h, const double *e2u, const doub
     launch_transports(h->dom.jpi, h->dom.jpj, h->dom.jpk, e2u, e1v, h->e1e2t.p, e3u_n, e3v_n, un, vn, wn, zun, zvn, zwn, h->stream);
     CU(cudaGetLastError());
     return 0;
+}
+
+int nemo_tra_adv_dev(nemo_fct_handle h, int kt, int nit000, int neuler, double rdt, const double *e2u, const double *e1v,
+                     const double *e3u_n, const double *e3v_n, const double *un, const double *vn, const double *wn,
+                     const double *tsb, const double *tsn, double *tsa, int jpts, int nn_fct_h, int nn_fct_v)
+{
+    if (need_single(h, "nemo_tra_adv_dev")) return 1;
+    if (!e2u || !e1v || !e3u_n || !e3v_n || !un || !vn || !wn || !tsb || !tsn || !tsa) return fail("tra_adv: NULL array");
+    // set time step (traadv.F90:95-97): Euler at nit000 when neuler = 0, else leap-frog; unchanged after nit000+1
+    if (neuler == 0 && kt == nit000) h->r2dt = rdt;
+    else if (kt <= nit000 + 1)       h->r2dt = 2.0 * rdt;
+    if (h->r2dt == 0.0) return fail("tra_adv: called with kt = %d > nit000 + 1 = %d before the time step was set", kt, nit000 + 1);
+    CU(cudaSetDevice(h->device));
+    try {
+        if (h->zun.n != h->n3) { h->zun.alloc(h->n3); h->zvn.alloc(h->n3); h->zwn.alloc(h->n3); }
+    } catch (const std::exception &e) { return fail("tra_adv: %s", e.what()); }
+    if (nemo_tra_adv_transports_dev(h, e2u, e1v, e3u_n, e3v_n, un, vn, wn, h->zun.p, h->zvn.p, h->zwn.p)) return 1;
+    h->have_trp = true;
+    return nemo_tra_adv_fct_dev(h, kt, nit000, "TRA", h->r2dt, h->zun.p, h->zvn.p, h->zwn.p, tsb, tsn, tsa, jpts, nn_fct_h, nn_fct_v);
+}
+
+int nemo_trc_adv_dev(nemo_fct_handle h, int kt, int nittrc000, double r2dttrc, const double *trb, const double *trn, double *tra,
+                     int jptra, int nn_fct_h, int nn_fct_v)
+{
+    if (need_single(h, "nemo_trc_adv_dev")) return 1;
+    if (!h->have_trp) return fail("trc_adv: the effective transports have not been built yet (call nemo_tra_adv_dev first)");
+    if (!trb || !trn || !tra) return fail("trc_adv: NULL array");
+    return nemo_tra_adv_fct_dev(h, kt, nittrc000, "TRC", r2dttrc, h->zun.p, h->zvn.p, h->zwn.p, trb, trn, tra, jptra, nn_fct_h, nn_fct_v);
 }
 
 static int lnk_common(std::vector<Ctx *> &g, int nfld, double *const *const *ptab, const char *cd_nat, const double *psgn,

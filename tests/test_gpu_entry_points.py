@@ -119,3 +119,52 @@ def test_errors_are_reported_not_swallowed(N, O):
     with pytest.raises(N.NemoFctError, match="comm_init"):
         c2.lbc_lnk_multi("x", f, "T", 1.0)
     c2.close()
+
+
+def test_tra_adv_and_trc_adv_device_resident(N, O):
+    """tra_adv (traadv.F90:77-175, FCT branch) and trc_adv (trcadv.F90:70-145) on device-resident state: r2dt rule of
+    :95-97 (Euler at nit000 when neuler = 0, leap-frog afterwards), transports built once and reused by the passive
+    tracers.  Oracle: tra_adv_transports + tra_adv_fct with the same r2dt."""
+    G, GJ, K, jperio = 52, 40, 9, 4
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=12)
+    rng = np.random.default_rng(5)
+    e2u = np.full((GJ, G), 1.0e5) * (1.0 + 0.05 * rng.random((GJ, G))); e1v = np.full((GJ, G), 1.0e5) * (1.0 + 0.05 * rng.random((GJ, G)))
+    e3u = gf["e3t_n"] * (1.0 + 0.01 * rng.random((K, GJ, G))); e3v = gf["e3t_n"] * (1.0 + 0.01 * rng.random((K, GJ, G)))
+    un = 0.3 * 1.0e5 / 7200.0 * rng.uniform(-1, 1, (K, GJ, G)) * gf["umask"]
+    vn = 0.3 * 1.0e5 / 7200.0 * rng.uniform(-1, 1, (K, GJ, G)) * gf["vmask"]
+    wn = 1.0e-4 * rng.uniform(-1, 1, (K, GJ, G)) * gf["wmask"]
+    w = O.World(G, GJ, K, jperio)
+    w.lbc_lnk([[un], [vn], [wn]], "UVW", [-1.0, -1.0, 1.0])
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS])
+    zu, zv, zw = (np.zeros((K, GJ, G)) for _ in range(3))
+    O.lib().tra_adv_transports(d.h, *[a.ctypes.data for a in (e2u, e1v, e3u, e3v, un, vn, wn)], zu.ctypes.data, zv.ctypes.data, zw.ctypes.data)
+    rdt, nit000 = 3600.0, 11
+    trb = np.ascontiguousarray(np.stack([gf["ptb"][0] * (1 + 0.1 * n) for n in range(5)]))      # 5 passive tracers
+    trn = np.ascontiguousarray(np.stack([gf["ptn"][0] * (1 + 0.1 * n) for n in range(5)]))
+    dom = N.mpp_init(G, GJ, K, jperio)
+    ctx = N.FctContext(dom, 0)
+    ctx.set_domain_arrays(gf["tmask"], gf["umask"], gf["vmask"], gf["wmask"], gf["e1e2t"], gf["r1_e1e2t"], gf["mikt"], gf["mbkt"])
+    ctx.set_e3t(gf["e3t_b"], gf["e3t_n"], gf["e3t_a"])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    t = [dev(a) for a in (e2u, e1v, e3u, e3v, un, vn, wn, gf["ptb"], gf["ptn"])]
+    for kt, neuler, want_r2dt in ((nit000, 0, rdt), (nit000 + 1, 0, 2 * rdt), (nit000 + 5, 0, 2 * rdt)):
+        ref = gf["pta"].copy()
+        w.tra_adv_fct(want_r2dt, [zu], [zv], [zw], [gf["ptb"]], [gf["ptn"]], [ref], 2, 4, 4)
+        tsa = dev(gf["pta"])
+        ctx.tra_adv(kt, nit000, neuler, rdt, *t, tsa, 2, 4, 4)
+        ctx.synchronize()
+        assert np.array_equal(tsa.cpu().numpy(), ref), (kt, neuler)
+    ref = np.zeros_like(trb)
+    w.tra_adv_fct(2 * rdt, [zu], [zv], [zw], [trb], [trn], [ref], 5, 2, 2)
+    tra = torch.zeros(trb.shape, dtype=torch.float64, device="cuda")
+    ctx.trc_adv(nit000 + 5, nit000, 2 * rdt, dev(trb), dev(trn), tra, 5, 2, 2)
+    ctx.synchronize()
+    assert np.array_equal(tra.cpu().numpy(), ref)
+    ctx.close()
+    c2 = N.FctContext(dom, 0)
+    c2.set_domain_arrays(gf["tmask"], gf["umask"], gf["vmask"], gf["wmask"], gf["e1e2t"], gf["r1_e1e2t"], gf["mikt"], gf["mbkt"])
+    c2.set_e3t(gf["e3t_b"], gf["e3t_n"], gf["e3t_a"])
+    with pytest.raises(N.NemoFctError, match="tra_adv"):
+        c2.trc_adv(1, 1, rdt, dev(trb), dev(trn), tra, 5, 2, 2)       # transports not built yet
+    c2.close(); w.close()
