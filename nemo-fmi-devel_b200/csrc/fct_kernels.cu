@@ -836,7 +836,8 @@ __global__ void __launch_bounds__(NX * NY, 2) k_fct_nonosc_final(const FctArgs a
             bdo_c = (aft_c - zdo) / (zneg + zrtrn) * zbt;
         }
         sB[k % 2][0][ty][tx] = bup_c; sB[k % 2][1][ty][tx] = bdo_c;
-        __syncthreads();
+        // No second barrier: the betas of level k-1 read below were published before this iteration's barrier, sB[k % 2]
+        // was last read (as level k-2) before it too, and sA[(k+1) % 3] is not rewritten until after the next one.
         if (k >= 2 && is_out) {
             // final trend of level kk = k-1: betas(kk) of the neighbours from sB, own betas at kk-1, kk, kk+1
             const int kk = k - 1;
