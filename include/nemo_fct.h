@@ -147,6 +147,50 @@ int nemo_tra_adv_dev(nemo_fct_handle h, int kt, int nit000, int neuler, double r
 int nemo_trc_adv_dev(nemo_fct_handle h, int kt, int nittrc000, double r2dttrc, const double *trb, const double *trn,
                      double *tra, int jptra, int nn_fct_h, int nn_fct_v);
 
+/* ---- tra_adv_mus: MUSCL scheme (traadv_mus.F90:55-273), the scheme BENCH and ORCA2_ICE_PISCES select for TOP ---------- */
+/* Extra module arrays it reads: r1_e1e2u, r1_e1e2v (jpi,jpj) (dom_oce.F90:118; HOST pointers, time-invariant, copied) and
+ * e3u_n, e3v_n, e3w_n (jpi,jpj,jpk) (dom_oce.F90:132-136; time-varying with ln_linssh = F: is_device != 0 borrows device
+ * pointers that must stay valid until replaced, else host arrays are copied).                                           */
+int nemo_fct_set_mus_metrics(nemo_fct_handle h, const double *r1_e1e2u, const double *r1_e1e2v);
+int nemo_fct_set_e3uvw(nemo_fct_handle h, const double *e3u_n, const double *e3v_n, const double *e3w_n, int is_device);
+/* Upstream indicator xind (traadv_mus.F90:99-113, built by the reference at kt == kit000): ld_msc_ups = 0 -> xind = 1
+ * (default, nothing stored); else xind = 1 - MAX(rnfmsk*rnfmsk_z(jk), upsmsk = 0)*tmask from HOST rnfmsk (jpi,jpj), rnfmsk_z (jpk) */
+int nemo_fct_set_mus_upstream(nemo_fct_handle h, int ld_msc_ups, const double *rnfmsk, const double *rnfmsk_z);
+/* CALL tra_adv_mus( kt, kit000, cdtype, p2dt, pun, pvn, pwn, ptb, pta, kjpt, ld_msc_ups ) -- ld_msc_ups is the state set by
+ * nemo_fct_set_mus_upstream.  Only pta(2:jpim1, 2:jpjm1, 1:jpkm1, :) is modified.  Collective like tra_adv_fct (2 exchanges).
+ * Schedules (nemo_fct_set_schedule): 0 = three reference-structured kernels on the whole interior; >= 1 = one fused kernel
+ * on the exchange-free inner columns + the reference-structured kernels on the two-cell frame, overlapped on a side stream. */
+int nemo_tra_adv_mus(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
+                     const double *pvn, const double *pwn, const double *ptb, double *pta, int kjpt);
+int nemo_tra_adv_mus_dev(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
+                         const double *pvn, const double *pwn, const double *ptb, double *pta, int kjpt);
+int nemo_group_tra_adv_mus_dev(nemo_fct_handle *hs, int n, int kt, int kit000, const char *cdtype, double p2dt,
+                               const double *const *pun, const double *const *pvn, const double *const *pwn,
+                               const double *const *ptb, double *const *pta, int kjpt);
+
+/* ---- tra_nxt / trc_nxt: lateral boundary conditions on the after field, Asselin filter, swap ---------------------------- */
+/* Module variables read by tra_nxt_vvl (tranxt.F90:262-343; sbc_oce, sbcrnf, sbcisf, traqsr, phycst).  All pointers are
+ * DEVICE pointers; a NULL 2-D flux array stands for zeros.  The arrays behind an enabled switch must be non-NULL.          */
+typedef struct nemo_nxt_forcing {
+    double atfp, r1_rau0;                              /* dom_oce.F90:58, phycst.F90:42 */
+    int ln_traqsr, ln_rnf, ln_isf, ln_rnf_depth, nksr;
+    const double *emp_b, *emp, *fwfisf_b, *fwfisf, *rnf_b, *rnf;        /* (jpi,jpj) */
+    const double *qsr_hc, *qsr_hc_b;                                    /* (jpi,jpj,jpk) */
+    const int *nk_rnf; const double *h_rnf, *rnf_tsc, *rnf_tsc_b;       /* (jpi,jpj), (jpi,jpj,jpts) */
+    const int *misfkt, *misfkb;                                         /* (jpi,jpj) */
+    const double *risf_tsc, *risf_tsc_b, *r1_hisf_tbl, *ralpha;         /* (jpi,jpj,jpts), (jpi,jpj) */
+} nemo_nxt_forcing;
+/* tra_nxt (cdtype "TRA", tranxt.F90:65-187) / trc_nxt (cdtype "TRC", trcnxt.F90:56-183) on device-resident ptb, ptn, pta
+ * (jpi,jpj,jpk,kjpt): lbc_lnk on pta; then, if l_euler (neuler == 0 .AND. kt == nit000 [.OR. ln_top_euler]) the Euler swap
+ * ptn = pta (and ptb = ptn for TRC), else tra_nxt_fix (ln_linssh) or tra_nxt_vvl(p2dt = rdt; psbc_tc, psbc_tc_b (jpi,jpj,kjpt)
+ * device pointers or NULL) followed by lbc_lnk on ptb, ptn, pta.  AGRIF, ln_bdy and the l_trdtra trends are not applied.   */
+int nemo_tra_nxt_dev(nemo_fct_handle h, int kt, int nit000, int l_euler, double rdt, const char *cdtype,
+                     const nemo_nxt_forcing *f, double *ptb, double *ptn, double *pta, const double *psbc_tc,
+                     const double *psbc_tc_b, int kjpt);
+int nemo_group_tra_nxt_dev(nemo_fct_handle *hs, int n, int kt, int nit000, int l_euler, double rdt, const char *cdtype,
+                           const nemo_nxt_forcing *const *f, double *const *ptb, double *const *ptn, double *const *pta,
+                           const double *const *psbc_tc, const double *const *psbc_tc_b, int kjpt);
+
 /* lbc_lnk_multi (lbc_lnk_multi_generic.h90:16-29): nfld fields ptab[f] of (jpi,jpj,ipk) each (a 4-D field is a
  * 3-D field with ipk*ipl levels), grid-point type cd_nat[f] in "TUVWF", fold sign psgn[f]; has_pval/pval = the
  * optional land value.  cd_mpp is not supported (not used on this path).                                          */

@@ -97,6 +97,14 @@ def lib():
         "nemo_tra_adv_transports_dev": [vp] * 11,
         "nemo_tra_adv_dev": [vp, i, i, i, d] + [vp] * 10 + [i, i, i],
         "nemo_trc_adv_dev": [vp, i, i, d] + [vp] * 3 + [i, i, i],
+        "nemo_fct_set_mus_metrics": [vp, vp, vp],
+        "nemo_fct_set_e3uvw": [vp, vp, vp, vp, i],
+        "nemo_fct_set_mus_upstream": [vp, i, vp, vp],
+        "nemo_tra_adv_mus": [vp, i, i, C.c_char_p, d] + [vp] * 5 + [i],
+        "nemo_tra_adv_mus_dev": [vp, i, i, C.c_char_p, d] + [vp] * 5 + [i],
+        "nemo_group_tra_adv_mus_dev": [C.POINTER(vp), i, i, i, C.c_char_p, d] + [C.POINTER(vp)] * 5 + [i],
+        "nemo_tra_nxt_dev": [vp, i, i, i, d, C.c_char_p, vp, vp, vp, vp, vp, vp, i],
+        "nemo_group_tra_nxt_dev": [C.POINTER(vp), i, i, i, i, d, C.c_char_p] + [C.POINTER(vp)] * 6 + [i],
         "nemo_lbc_lnk_multi": [vp, C.c_char_p, i, C.POINTER(vp), C.c_char_p, dp, i, i, d],
         "nemo_lbc_lnk_multi_dev": [vp, C.c_char_p, i, C.POINTER(vp), C.c_char_p, dp, i, i, d],
         "nemo_group_lbc_lnk_multi_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.c_char_p, dp, i, i, d],
@@ -121,9 +129,33 @@ ABI_SYMBOLS = (
     "nemo_fct_set_domain_arrays nemo_fct_set_e3t nemo_fct_set_stream nemo_fct_synchronize nemo_fct_comm_unique_id "
     "nemo_fct_comm_init nemo_fct_comm_init_local nemo_tra_adv_fct nemo_tra_adv_fct_dev nemo_group_tra_adv_fct_dev "
     "nemo_interp_4th_cpt nemo_interp_4th_cpt_dev nemo_tra_adv_transports_dev nemo_tra_adv_dev nemo_trc_adv_dev nemo_lbc_lnk_multi "
+    "nemo_fct_set_mus_metrics nemo_fct_set_e3uvw nemo_fct_set_mus_upstream nemo_tra_adv_mus nemo_tra_adv_mus_dev "
+    "nemo_group_tra_adv_mus_dev nemo_tra_nxt_dev nemo_group_tra_nxt_dev "
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
     "nemo_fct_profile_read").split()
+
+
+class NxtForcing(C.Structure):
+    """nemo_nxt_forcing: the module variables tra_nxt_vvl reads (tranxt.F90:262-343).  Keyword arguments: scalars
+    (atfp, r1_rau0, ln_traqsr, ln_rnf, ln_isf, ln_rnf_depth, nksr) or CUDA tensors (emp_b, emp, ..., ralpha)."""
+    _fields_ = ([("atfp", C.c_double), ("r1_rau0", C.c_double)]
+                + [(n, C.c_int) for n in "ln_traqsr ln_rnf ln_isf ln_rnf_depth nksr".split()]
+                + [(n, C.c_void_p) for n in ("emp_b emp fwfisf_b fwfisf rnf_b rnf qsr_hc qsr_hc_b nk_rnf h_rnf rnf_tsc "
+                                             "rnf_tsc_b misfkt misfkb risf_tsc risf_tsc_b r1_hisf_tbl ralpha").split()])
+
+    def __init__(self, atfp=0.1, r1_rau0=1.0 / 1026.0, **kw):
+        super().__init__()
+        self.atfp, self.r1_rau0 = atfp, r1_rau0
+        self._keep = {}
+        for k, v in kw.items():
+            if hasattr(v, "data_ptr"):
+                if not v.is_cuda:
+                    raise ValueError(f"NxtForcing.{k}: device tensors only")
+                self._keep[k] = v
+                setattr(self, k, v.data_ptr())
+            else:
+                setattr(self, k, int(v))
 
 
 def _check(rc):
@@ -250,7 +282,7 @@ class FctContext:
 
     def profile(self):
         """{kernel name: (total ms, launches)} since set_profiling(True)"""
-        stride, mx = 32, 16
+        stride, mx = 32, 24
         names = C.create_string_buffer(stride * mx)
         ms = (C.c_double * mx)()
         calls = (C.c_longlong * mx)()
@@ -313,6 +345,61 @@ class FctContext:
             raise ValueError("trc_adv: device tensors only")
         _check(lib().nemo_trc_adv_dev(self._h, kt, nittrc000, float(r2dttrc), _ptr(trb), _ptr(trn), _ptr(tra), jptra, nn_fct_h, nn_fct_v))
 
+    # -- MUSCL (the scheme of the TOP namelists) and the time-stepping swap -----------------------------------------
+    def set_mus_metrics(self, r1_e1e2u, r1_e1e2v):
+        """r1_e1e2u, r1_e1e2v (jpj,jpi) host numpy (dom_oce.F90:118)"""
+        arrs = [np.ascontiguousarray(_f64(a, "set_mus_metrics")) for a in (r1_e1e2u, r1_e1e2v)]
+        for a in arrs:
+            assert tuple(a.shape) == (self.dom.jpj, self.dom.jpi)
+        _check(lib().nemo_fct_set_mus_metrics(self._h, _ptr(arrs[0]), _ptr(arrs[1])))
+
+    def set_e3uvw(self, e3u_n, e3v_n, e3w_n):
+        """e3u_n, e3v_n, e3w_n (jpk,jpj,jpi): numpy -> copied to the device; CUDA tensors -> borrowed in place."""
+        dev = _is_dev(e3u_n)
+        for a in (e3u_n, e3v_n, e3w_n):
+            assert tuple(a.shape) == self.dom.shape3 and _is_dev(a) == dev
+            _f64(a, "set_e3uvw")
+        if dev:
+            self._keep["e3uvw"] = (e3u_n, e3v_n, e3w_n)
+        _check(lib().nemo_fct_set_e3uvw(self._h, _ptr(e3u_n), _ptr(e3v_n), _ptr(e3w_n), int(dev)))
+
+    def set_mus_upstream(self, ld_msc_ups, rnfmsk=None, rnfmsk_z=None):
+        """xind of traadv_mus.F90:99-113 from host rnfmsk (jpj,jpi), rnfmsk_z (jpk); ld_msc_ups = False -> xind = 1"""
+        if not ld_msc_ups:
+            _check(lib().nemo_fct_set_mus_upstream(self._h, 0, None, None))
+            return
+        a = np.ascontiguousarray(_f64(rnfmsk, "set_mus_upstream"))
+        z = np.ascontiguousarray(_f64(rnfmsk_z, "set_mus_upstream"))
+        assert tuple(a.shape) == (self.dom.jpj, self.dom.jpi) and z.shape == (self.dom.jpk,)
+        _check(lib().nemo_fct_set_mus_upstream(self._h, 1, _ptr(a), _ptr(z)))
+
+    def tra_adv_mus(self, kt, kit000, cdtype, p2dt, pun, pvn, pwn, ptb, pta, kjpt):
+        """tra_adv_mus( kt, kit000, cdtype, p2dt, pun, pvn, pwn, ptb, pta, kjpt, ld_msc_ups ) (traadv_mus.F90:55-56);
+        ld_msc_ups is the state set by :meth:`set_mus_upstream`.  pta updated on (2:jpim1, 2:jpjm1, 1:jpkm1, :)."""
+        s3, s4 = self.dom.shape3, (kjpt,) + self.dom.shape3
+        dev = _is_dev(pta)
+        for a, shp in ((pun, s3), (pvn, s3), (pwn, s3), (ptb, s4), (pta, s4)):
+            if tuple(a.shape) != shp:
+                raise ValueError(f"tra_adv_mus: array of shape {tuple(a.shape)}, expected {shp}")
+            if _is_dev(a) != dev:
+                raise ValueError("tra_adv_mus: all arrays must live on the same side (all host or all device)")
+            _f64(a, "tra_adv_mus")
+        fn = lib().nemo_tra_adv_mus_dev if dev else lib().nemo_tra_adv_mus
+        _check(fn(self._h, kt, kit000, cdtype.encode(), float(p2dt), _ptr(pun), _ptr(pvn), _ptr(pwn), _ptr(ptb), _ptr(pta), kjpt))
+
+    def tra_nxt(self, kt, nit000, l_euler, rdt, cdtype, forcing, ptb, ptn, pta, kjpt, sbc_tc=None, sbc_tc_b=None):
+        """tra_nxt( kt ) (tranxt.F90:65) for cdtype 'TRA' / trc_nxt( kt ) (trcnxt.F90:56) for 'TRC', module state passed
+        explicitly; device tensors only.  forcing: :class:`NxtForcing` (may be None for an Euler step)."""
+        s4 = (kjpt,) + self.dom.shape3
+        for a in (ptb, ptn, pta):
+            if not _is_dev(a) or tuple(a.shape) != s4:
+                raise ValueError("tra_nxt: device tensors of shape (kjpt, jpk, jpj, jpi) only")
+            _f64(a, "tra_nxt")
+        _check(lib().nemo_tra_nxt_dev(self._h, kt, nit000, int(l_euler), float(rdt), cdtype.encode(),
+                                      C.byref(forcing) if forcing is not None else None, _ptr(ptb), _ptr(ptn), _ptr(pta),
+                                      _ptr(sbc_tc) if sbc_tc is not None else None,
+                                      _ptr(sbc_tc_b) if sbc_tc_b is not None else None, kjpt))
+
     def lbc_lnk_multi(self, cdname, *triplets, pval=None):
         """lbc_lnk_multi( cdname, pt1, cdna1, psgn1 [, pt2, cdna2, psgn2, ...] [, pval] )
         (lbc_lnk_multi_generic.h90:16-29).  Fields (ipk,jpj,jpi) or (jpj,jpi), all with the same ipk."""
@@ -365,6 +452,23 @@ class LocalGroup:
         _check(lib().nemo_group_tra_adv_fct_dev(self._hs, self.n, kt, kit000, cdtype.encode(), float(p2dt),
                                                 self._tab(pun), self._tab(pvn), self._tab(pwn), self._tab(ptb),
                                                 self._tab(ptn), self._tab(pta), kjpt, kn_fct_h, kn_fct_v))
+
+    def tra_adv_mus(self, kt, kit000, cdtype, p2dt, pun, pvn, pwn, ptb, pta, kjpt):
+        for lst in (pun, pvn, pwn, ptb, pta):
+            assert len(lst) == self.n and all(_is_dev(a) for a in lst)
+        _check(lib().nemo_group_tra_adv_mus_dev(self._hs, self.n, kt, kit000, cdtype.encode(), float(p2dt),
+                                                self._tab(pun), self._tab(pvn), self._tab(pwn), self._tab(ptb),
+                                                self._tab(pta), kjpt))
+
+    def tra_nxt(self, kt, nit000, l_euler, rdt, cdtype, forcing, ptb, ptn, pta, kjpt, sbc_tc=None, sbc_tc_b=None):
+        """forcing: list over ranks of NxtForcing (or None for an Euler step)"""
+        for lst in (ptb, ptn, pta):
+            assert len(lst) == self.n and all(_is_dev(a) for a in lst)
+        ft = None if forcing is None else (C.c_void_p * self.n)(*[C.addressof(f) for f in forcing])
+        _check(lib().nemo_group_tra_nxt_dev(self._hs, self.n, kt, nit000, int(l_euler), float(rdt), cdtype.encode(), ft,
+                                            self._tab(ptb), self._tab(ptn), self._tab(pta),
+                                            None if sbc_tc is None else self._tab(sbc_tc),
+                                            None if sbc_tc_b is None else self._tab(sbc_tc_b), kjpt))
 
     def lbc_lnk_multi(self, cdname, fields, nats, sgns, pval=None):
         """fields[f][rank]: device tensors (ipk,jpj,jpi)"""

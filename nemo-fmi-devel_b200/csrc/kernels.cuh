@@ -79,6 +79,47 @@ void launch_transports(int jpi, int jpj, int jpk, const double *e2u, const doubl
                        const double *e3u_n, const double *e3v_n, const double *un, const double *vn,
                        const double *wn, double *zun, double *zvn, double *zwn, cudaStream_t s);
 
+// ---- tra_adv_mus (MUSCL)                                                    traadv_mus.F90:55-273 ----
+struct MusArgs {
+    Region reg;                            // columns this launch works on
+    int jpi, jpj, jpk;
+    size_t jpij, n3;
+    const double *tmask, *umask, *vmask, *wmask, *e3t_n, *r1_e1e2t;
+    const double *r1_e1e2u, *r1_e1e2v, *e3u_n, *e3v_n, *e3w_n;
+    const double *xind;                    // upstream indicator, NULL = 1 everywhere (ld_msc_ups = .FALSE.)
+    const int *mikt;
+    const double *pun, *pvn, *pwn, *ptb;
+    double *pta;
+    double *zwx, *zwy, *fx, *fy;           // first-guess differences and horizontal fluxes (jpi,jpj,jpk,kjpt)
+    double p2dt;
+    int kjpt, ln_linssh, ln_isfcav, nkchunk;
+};
+void launch_mus_grad(const MusArgs &a, cudaStream_t s);     // first guess of the slopes         :134-141
+void launch_mus_hflux(const MusArgs &a, cudaStream_t s);    // slopes, limitation, fluxes        :145-191
+void launch_mus_trend(const MusArgs &a, cudaStream_t s);    // horizontal trend + vertical part  :194-272
+void launch_mus_inner(const MusArgs &a, cudaStream_t s);    // everything, exchange-free columns
+void launch_mus_xind(int jpi, int jpj, int jpk, const double *rnfmsk, const double *rnfmsk_z, const double *tmask, double *xind,
+                     cudaStream_t s);                        // :99-113
+
+// ---- tra_nxt_fix / tra_nxt_vvl / Euler swap                                 tranxt.F90:148-153, 190-380 ----
+struct NxtArgs {
+    int jpi, jpj, jpk, kjpt;
+    size_t jpij, n3;
+    const double *e3t_b, *e3t_n, *e3t_a;
+    const int *mikt;
+    double *ptb, *ptn, *pta;
+    double atfp, zfact1, zfact2;           // atfp, atfp*p2dt, atfp*p2dt*r1_rau0   (:283-284)
+    int ll_traqsr, ll_rnf, ll_isf, ln_rnf_depth, nksr;
+    const double *sbc_tc, *sbc_tc_b;       // (jpi,jpj,kjpt) or NULL
+    const double *emp_b, *emp, *fwfisf_b, *fwfisf, *rnf_b, *rnf;     // (jpi,jpj) or NULL (= zeros)
+    const double *qsr_hc, *qsr_hc_b;       // (jpi,jpj,jpk)
+    const int *nk_rnf; const double *h_rnf, *rnf_tsc, *rnf_tsc_b;
+    const int *misfkt, *misfkb; const double *risf_tsc, *risf_tsc_b, *r1_hisf_tbl, *ralpha;
+};
+void launch_nxt_fix(const NxtArgs &a, cudaStream_t s);
+void launch_nxt_vvl(const NxtArgs &a, cudaStream_t s);
+void launch_nxt_euler(const NxtArgs &a, int also_before, cudaStream_t s);
+
 // ---- lbc_lnk on the device: gather plan execution -------------------------------------------------------------
 // One job = one (peer, field) pair: `ncell` cells x `nlev` levels.
 struct PackJob   { const double *field; const int *src; double *buf; int ncell; };                       // buf[k*ncell+c] = field[src[c] + k*jpij]

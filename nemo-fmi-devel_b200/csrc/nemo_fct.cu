@@ -124,6 +124,10 @@ struct nemo_fct_ctx {
     DevBuf<double> zlx, zly, zlz;                                      // schedule 1: limited fluxes of the frame path
     DevBuf<double> zun, zvn, zwn;                                      // effective transports of tra_adv, reused by trc_adv
     bool have_trp = false;
+    // tra_adv_mus: extra metrics / thicknesses, upstream indicator (NULL pointer = 1 everywhere)
+    DevBuf<double> r1_e1e2u, r1_e1e2v, e3uvw_own[3], xind;
+    const double *e3uvw[3] = {nullptr, nullptr, nullptr};
+    bool have_mus_metrics = false, msc_ups = false;
     double r2dt = 0.0;                                                 // tracer time step of tra_adv (traadv.F90:95-97), persists across calls
     bool have_zl = false;
     int masks_from_t = 0;                                              // umask/vmask/wmask verified to be tmask products
@@ -146,16 +150,19 @@ struct nemo_fct_ctx {
     struct ProfRec { int id; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_open;
     std::vector<cudaEvent_t> prof_pool;
-    double prof_ms[16] = {0}; long long prof_calls[16] = {0};
+    double prof_ms[24] = {0}; long long prof_calls[24] = {0};
 };
 typedef nemo_fct_ctx Ctx;
 
 // ------------------------------------------------------------------------------------------------------------
 // per-kernel timing with CUDA events on the launching stream
 // ------------------------------------------------------------------------------------------------------------
-enum ProfId { P_LAPLACIAN = 0, P_CPT, P_LOW_ANTIDIFF, P_BETAS, P_LIMIT, P_FINAL, P_LOW_INNER, P_NONOSC_FINAL, P_PACK, P_MOVE, P_UNPACK, P_COUNT };
+enum ProfId { P_LAPLACIAN = 0, P_CPT, P_LOW_ANTIDIFF, P_BETAS, P_LIMIT, P_FINAL, P_LOW_INNER, P_NONOSC_FINAL, P_PACK, P_MOVE, P_UNPACK,
+              P_MUS_GRAD, P_MUS_HFLUX, P_MUS_TREND, P_MUS_INNER, P_NXT, P_COUNT };
+static_assert(P_COUNT <= 24, "prof_ms / prof_calls too small");
 static const char *kProfName[P_COUNT] = {"fct_laplacian", "interp_4th_cpt", "fct_low_antidiff", "fct_betas", "fct_limit",
-                                         "fct_final", "fct_low_antidiff_inner", "fct_nonosc_final", "lbc_pack", "lbc_move_nccl", "lbc_fill_unpack"};
+                                         "fct_final", "fct_low_antidiff_inner", "fct_nonosc_final", "lbc_pack", "lbc_move_nccl", "lbc_fill_unpack",
+                                         "mus_grad", "mus_hflux", "mus_trend", "mus_inner", "tra_nxt"};
 struct ProfScope {
     nemo_fct_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int id;
     static cudaEvent_t get(nemo_fct_ctx *c) {
@@ -407,6 +414,20 @@ static int ensure_work(Ctx *c, int kjpt, int h, int v)
     return 0;
 }
 
+// side stream of the boundary-frame path (throws).  Highest priority: the frame kernels and NCCL transfers are tiny but
+// sit on the critical path of the exchange chain; without it their blocks queue behind thousands of pending blocks of
+// the inner kernels.
+static void ensure_side(Ctx *c)
+{
+    if (c->side_stream) return;
+    int prio_lo = 0, prio_hi = 0;
+    CUTHROW(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUTHROW(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi));
+    CUTHROW(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    CUTHROW(cudaEventCreateWithFlags(&c->ev_k1, cudaEventDisableTiming));
+    CUTHROW(cudaEventCreateWithFlags(&c->ev_t, cudaEventDisableTiming));
+}
+
 static int pick_nkchunk(const Ctx *c, int kjpt)
 {
     const long long ncol = (long long)(c->dom.jpi - 2) * (c->dom.jpj - 2) * kjpt;
@@ -498,16 +519,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
                 for (auto *a : arrs) { a->alloc(n); CUTHROW(cudaMemset(a->p, 0, n * sizeof(double))); }
                 c->have_zl = true;
             }
-            if (!c->side_stream) {
-                // highest priority: the frame kernels and NCCL transfers are tiny but sit on the critical path of the
-                // exchange chain; without it their blocks queue behind thousands of pending blocks of the inner kernels
-                int prio_lo = 0, prio_hi = 0;
-                CUTHROW(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-                CUTHROW(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi));
-                CUTHROW(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
-                CUTHROW(cudaEventCreateWithFlags(&c->ev_k1, cudaEventDisableTiming));
-                CUTHROW(cudaEventCreateWithFlags(&c->ev_t, cudaEventDisableTiming));
-            }
+            ensure_side(c);
         } catch (const std::exception &e) { return fail("tra_adv_fct: schedule 1 set-up: %s", e.what()); }
         auto band = [&](int wW, int wE, int wS, int wN) {
             Region r;
@@ -586,6 +598,177 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_t, 0));
 #undef EACH
 #undef CPT
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// MUSCL step over a set of in-process subdomains (traadv_mus.F90:55-273)
+// ------------------------------------------------------------------------------------------------------------
+struct MusCall { const double *pun, *pvn, *pwn, *ptb; double *pta; };
+
+static int run_mus(std::vector<Ctx *> &g, const std::vector<MusCall> &args, double p2dt, int kjpt)
+{
+    const int ng = (int)g.size();
+    if (kjpt < 1) return fail("tra_adv_mus: kjpt = %d", kjpt);
+    std::vector<MusArgs> ma(ng);
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m];
+        if (!c->have_dom) return fail("tra_adv_mus: nemo_fct_set_domain_arrays has not been called");
+        if (!c->e3t[1]) return fail("tra_adv_mus: nemo_fct_set_e3t has not been called");
+        if (!c->have_mus_metrics) return fail("tra_adv_mus: nemo_fct_set_mus_metrics has not been called");
+        if (!c->e3uvw[0] || !c->e3uvw[1] || !c->e3uvw[2]) return fail("tra_adv_mus: nemo_fct_set_e3uvw has not been called");
+        if (c->dom.jpk < 3) return fail("tra_adv_mus: jpk must be >= 3");
+        if (ensure_work(c, kjpt, 2, 2)) return 1;
+        MusArgs &a = ma[m];
+        a.jpi = c->dom.jpi; a.jpj = c->dom.jpj; a.jpk = c->dom.jpk; a.jpij = c->jpij; a.n3 = c->n3;
+        a.tmask = c->tmask.p; a.umask = c->umask.p; a.vmask = c->vmask.p; a.wmask = c->wmask.p;
+        a.e3t_n = c->e3t[1]; a.r1_e1e2t = c->r1_e1e2t.p; a.r1_e1e2u = c->r1_e1e2u.p; a.r1_e1e2v = c->r1_e1e2v.p;
+        a.e3u_n = c->e3uvw[0]; a.e3v_n = c->e3uvw[1]; a.e3w_n = c->e3uvw[2];
+        a.xind = c->msc_ups ? c->xind.p : nullptr; a.mikt = c->mikt.p;
+        a.pun = args[m].pun; a.pvn = args[m].pvn; a.pwn = args[m].pwn; a.ptb = args[m].ptb; a.pta = args[m].pta;
+        a.zwx = c->zwx.p; a.zwy = c->zwy.p; a.fx = c->zwi.p; a.fy = c->zwz.p;   // the FCT work arrays, levels 1..jpkm1 only
+        a.p2dt = p2dt; a.kjpt = kjpt; a.ln_linssh = c->ln_linssh; a.ln_isfcav = c->ln_isfcav;
+        a.nkchunk = pick_nkchunk(c, kjpt);
+        a.reg = Region();
+    }
+    auto exch = [&](const std::vector<DevBuf<double> Ctx::*> &fields) {
+        LnkCall call; call.nfld = (int)fields.size(); call.nat = "UV"; call.sgn = {-1.0, -1.0}; call.has_pval = 0; call.pval = 0.0;
+        call.nlev = g[0]->dom.jpk * kjpt;
+        call.ptab.resize(ng);
+        for (int m = 0; m < ng; ++m) for (auto f : fields) call.ptab[m].push_back((g[m]->*f).p);
+        return lbc_exchange(g, call);
+    };
+#define EACH(id, stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); ProfScope ps(c, id); stmt; }
+    bool fused = g[0]->schedule >= 1;
+    for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < 20 || g[m]->dom.jpj < 20) fused = false;
+
+    std::vector<MusArgs> grad(ma), hfl(ma), trd(ma), inner(ma);
+    if (!fused) {
+        for (int m = 0; m < ng; ++m) {
+            const int jpi = ma[m].jpi, jpj = ma[m].jpj;
+            grad[m].reg.add(1, jpi - 1, 1, jpj - 1);                        // :134-141
+            hfl[m].reg.add(2, jpi - 1, 2, jpj - 1);                         // :171-191
+            trd[m].reg.add(2, jpi - 1, 2, jpj - 1);                         // :194-202, :266-272
+        }
+        EACH(P_MUS_GRAD, launch_mus_grad(grad[m], c->stream));
+        if (exch({&Ctx::zwx, &Ctx::zwy})) return 1;                         // :143
+        EACH(P_MUS_HFLUX, launch_mus_hflux(hfl[m], c->stream));
+        if (exch({&Ctx::zwi, &Ctx::zwz})) return 1;                         // :192
+        EACH(P_MUS_TREND, launch_mus_trend(trd[m], c->stream));
+        CU(cudaGetLastError());
+        return 0;
+    }
+    // ---- fused: the exchange-free inner columns (4:jpi-2, 4:jpj-2-f) in one kernel on the main stream; the frame around
+    // them through the reference-structured kernels restricted to bands (each band holds everything the next one and the
+    // exchanges read), with the two real exchanges, on the side stream.  f = 1 under a north fold, which rewrites row jpj-1.
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m];
+        const int jpi = c->dom.jpi, jpj = c->dom.jpj, f = c->dom.npolj != 0 ? 1 : 0;
+        try { CUTHROW(cudaSetDevice(c->device)); ensure_side(c); }
+        catch (const std::exception &e) { return fail("tra_adv_mus: side stream: %s", e.what()); }
+        auto band = [&](int i_lo, int wW, int wE, int j_lo, int wS, int wN) {      // W: i_lo..wW, E: jpi-wE..jpi-1, S: j_lo..wS, N: jpj-wN..jpj-1
+            Region r;
+            r.add(i_lo, wW, j_lo, jpj - 1);
+            r.add(jpi - wE, jpi - 1, j_lo, jpj - 1);
+            r.add(wW + 1, jpi - wE - 1, j_lo, wS);
+            r.add(wW + 1, jpi - wE - 1, jpj - wN, jpj - 1);
+            return r;
+        };
+        inner[m].reg.add(4, jpi - 2, 4, jpj - 2 - f);
+        trd[m].reg = band(2, 3, 1, 2, 3, 1 + f);
+        hfl[m].reg = band(2, 4, 2, 2, 4, 3 + f);
+        grad[m].reg = band(1, 5, 3, 1, 5, 4 + f);
+        for (MusArgs *x : {&grad[m], &hfl[m], &trd[m]}) x->nkchunk = std::max(1, std::min(8, (c->dom.jpk - 1) / 8));
+    }
+    cudaStream_t side = g[0]->side_stream;
+    std::vector<cudaStream_t> mainst(ng);
+    for (int m = 0; m < ng; ++m) mainst[m] = g[m]->stream;
+    auto to_side = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = side; };
+    auto to_main = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = mainst[m]; };
+    struct Restore { std::function<void()> f; ~Restore() { f(); } } restore{to_main};
+
+    CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
+    EACH(P_MUS_INNER, launch_mus_inner(inner[m], c->stream));
+    to_side();
+    CU(cudaStreamWaitEvent(side, g[0]->ev_a, 0));
+    EACH(P_MUS_GRAD, launch_mus_grad(grad[m], c->stream));
+    if (exch({&Ctx::zwx, &Ctx::zwy})) return 1;
+    EACH(P_MUS_HFLUX, launch_mus_hflux(hfl[m], c->stream));
+    if (exch({&Ctx::zwi, &Ctx::zwz})) return 1;
+    EACH(P_MUS_TREND, launch_mus_trend(trd[m], c->stream));
+    CU(cudaEventRecord(g[0]->ev_t, side));
+    to_main();
+    CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_t, 0));
+#undef EACH
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tra_nxt / trc_nxt over a set of in-process subdomains (tranxt.F90:65-187, trcnxt.F90:56-183)
+// ------------------------------------------------------------------------------------------------------------
+struct NxtCall { const nemo_nxt_forcing *f; double *ptb, *ptn, *pta; const double *sbc, *sbc_b; };
+
+static int run_nxt(std::vector<Ctx *> &g, const std::vector<NxtCall> &args, int l_euler, double rdt, const char *cdtype, int kjpt)
+{
+    const int ng = (int)g.size();
+    if (kjpt < 1) return fail("tra_nxt: kjpt = %d", kjpt);
+    if (!cdtype || (strncmp(cdtype, "TRA", 3) != 0 && strncmp(cdtype, "TRC", 3) != 0)) return fail("tra_nxt: cdtype must be 'TRA' or 'TRC'");
+    const bool is_trc = strncmp(cdtype, "TRC", 3) == 0;
+    std::vector<NxtArgs> na(ng);
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m];
+        if (!c->have_dom) return fail("tra_nxt: nemo_fct_set_domain_arrays has not been called");
+        if (!args[m].ptb || !args[m].ptn || !args[m].pta) return fail("tra_nxt: NULL array");
+        NxtArgs &a = na[m];
+        memset(&a, 0, sizeof a);
+        a.jpi = c->dom.jpi; a.jpj = c->dom.jpj; a.jpk = c->dom.jpk; a.kjpt = kjpt; a.jpij = c->jpij; a.n3 = c->n3;
+        a.e3t_b = c->e3t[0]; a.e3t_n = c->e3t[1]; a.e3t_a = c->e3t[2]; a.mikt = c->mikt.p;
+        a.ptb = args[m].ptb; a.ptn = args[m].ptn; a.pta = args[m].pta;
+        if (!l_euler) {
+            const nemo_nxt_forcing *f = args[m].f;
+            if (!f) return fail("tra_nxt: NULL forcing (atfp is needed for the Asselin filter)");
+            a.atfp = f->atfp;
+            if (!c->ln_linssh) {
+                if (!a.e3t_b || !a.e3t_n || !a.e3t_a) return fail("tra_nxt: nemo_fct_set_e3t has not been called");
+                a.zfact1 = f->atfp * rdt;                                   // tranxt.F90:283-284 (p2dt = rdt)
+                a.zfact2 = a.zfact1 * f->r1_rau0;
+                a.ll_traqsr = !is_trc && f->ln_traqsr; a.ll_rnf = !is_trc && f->ln_rnf; a.ll_isf = !is_trc && f->ln_isf;   // :269-277
+                a.ln_rnf_depth = f->ln_rnf_depth; a.nksr = f->nksr;
+                a.sbc_tc = args[m].sbc; a.sbc_tc_b = args[m].sbc_b;
+                a.emp_b = f->emp_b; a.emp = f->emp; a.fwfisf_b = f->fwfisf_b; a.fwfisf = f->fwfisf; a.rnf_b = f->rnf_b; a.rnf = f->rnf;
+                a.qsr_hc = f->qsr_hc; a.qsr_hc_b = f->qsr_hc_b; a.nk_rnf = f->nk_rnf; a.h_rnf = f->h_rnf;
+                a.rnf_tsc = f->rnf_tsc; a.rnf_tsc_b = f->rnf_tsc_b; a.misfkt = f->misfkt; a.misfkb = f->misfkb;
+                a.risf_tsc = f->risf_tsc; a.risf_tsc_b = f->risf_tsc_b; a.r1_hisf_tbl = f->r1_hisf_tbl; a.ralpha = f->ralpha;
+                if (a.ll_traqsr && (!a.qsr_hc || !a.qsr_hc_b)) return fail("tra_nxt: ln_traqsr without qsr_hc / qsr_hc_b");
+                if ((a.ll_rnf || a.ln_rnf_depth) && (!a.nk_rnf || !a.h_rnf)) return fail("tra_nxt: ln_rnf / ln_rnf_depth without nk_rnf / h_rnf");
+                if (a.ll_rnf && (!a.rnf_tsc || !a.rnf_tsc_b)) return fail("tra_nxt: ln_rnf without rnf_tsc / rnf_tsc_b");
+                if (a.ll_isf && (!a.misfkt || !a.misfkb || !a.risf_tsc || !a.risf_tsc_b || !a.r1_hisf_tbl || !a.ralpha))
+                    return fail("tra_nxt: ln_isf without the sbcisf arrays");
+            }
+        }
+    }
+    auto exch = [&](int nblk) {                       // lbc_lnk on pta (nblk = 1) or on ptb, ptn, pta (nblk = 3), all 'T', +1
+        LnkCall call; call.nfld = nblk; call.nat = std::string((size_t)nblk, 'T'); call.sgn.assign((size_t)nblk, 1.0);
+        call.has_pval = 0; call.pval = 0.0; call.nlev = g[0]->dom.jpk * kjpt;   // a 4-D field is a 3-D field with jpk*kjpt levels
+        call.ptab.resize(ng);
+        for (int m = 0; m < ng; ++m) {
+            if (nblk == 1) call.ptab[m] = {na[m].pta};
+            else           call.ptab[m] = {na[m].ptb, na[m].ptn, na[m].pta};
+        }
+        return lbc_exchange(g, call);
+    };
+    if (exch(1)) return 1;                                                  // tranxt.F90:108, trcnxt.F90:100
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m];
+        CU(cudaSetDevice(c->device));
+        ProfScope ps(c, P_NXT);
+        if (l_euler)            launch_nxt_euler(na[m], is_trc ? 1 : 0, c->stream);
+        else if (c->ln_linssh)  launch_nxt_fix(na[m], c->stream);
+        else                    launch_nxt_vvl(na[m], c->stream);
+    }
+    if (!l_euler && exch(3)) return 1;                                      // tranxt.F90:168-170, trcnxt.F90:171
     CU(cudaGetLastError());
     return 0;
 }
@@ -985,6 +1168,130 @@ int nemo_trc_adv_dev(nemo_fct_handle h, int kt, int nittrc000, double r2dttrc, c
     if (!h->have_trp) return fail("trc_adv: the effective transports have not been built yet (call nemo_tra_adv_dev first)");
     if (!trb || !trn || !tra) return fail("trc_adv: NULL array");
     return nemo_tra_adv_fct_dev(h, kt, nittrc000, "TRC", r2dttrc, h->zun.p, h->zvn.p, h->zwn.p, trb, trn, tra, jptra, nn_fct_h, nn_fct_v);
+}
+
+int nemo_fct_set_mus_metrics(nemo_fct_handle h, const double *r1_e1e2u, const double *r1_e1e2v)
+{
+    if (!h) return fail("NULL handle");
+    if (!r1_e1e2u || !r1_e1e2v) return fail("nemo_fct_set_mus_metrics: NULL array");
+    CU(cudaSetDevice(h->device));
+    try {
+        CUTHROW(cudaStreamSynchronize(h->stream));
+        h->r1_e1e2u.alloc(h->jpij); h->r1_e1e2v.alloc(h->jpij);
+        CUTHROW(cudaMemcpy(h->r1_e1e2u.p, r1_e1e2u, h->jpij * sizeof(double), cudaMemcpyHostToDevice));
+        CUTHROW(cudaMemcpy(h->r1_e1e2v.p, r1_e1e2v, h->jpij * sizeof(double), cudaMemcpyHostToDevice));
+    } catch (const std::exception &e) { return fail("nemo_fct_set_mus_metrics: %s", e.what()); }
+    h->have_mus_metrics = true;
+    return 0;
+}
+
+int nemo_fct_set_e3uvw(nemo_fct_handle h, const double *e3u_n, const double *e3v_n, const double *e3w_n, int is_device)
+{
+    if (!h) return fail("NULL handle");
+    if (!e3u_n || !e3v_n || !e3w_n) return fail("nemo_fct_set_e3uvw: NULL array");
+    CU(cudaSetDevice(h->device));
+    const double *src[3] = {e3u_n, e3v_n, e3w_n};
+    if (is_device) { for (int i = 0; i < 3; ++i) h->e3uvw[i] = src[i]; return 0; }
+    try {
+        for (int i = 0; i < 3; ++i) {
+            if (h->e3uvw_own[i].n != h->n3) h->e3uvw_own[i].alloc(h->n3);
+            CUTHROW(cudaMemcpyAsync(h->e3uvw_own[i].p, src[i], h->n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            h->e3uvw[i] = h->e3uvw_own[i].p;
+        }
+        CUTHROW(cudaStreamSynchronize(h->stream));
+    } catch (const std::exception &e) { return fail("nemo_fct_set_e3uvw: %s", e.what()); }
+    return 0;
+}
+
+int nemo_fct_set_mus_upstream(nemo_fct_handle h, int ld_msc_ups, const double *rnfmsk, const double *rnfmsk_z)
+{
+    if (!h) return fail("NULL handle");
+    if (!ld_msc_ups) { h->msc_ups = false; return 0; }
+    if (!h->have_dom) return fail("nemo_fct_set_mus_upstream: nemo_fct_set_domain_arrays has not been called (tmask is needed)");
+    if (!rnfmsk || !rnfmsk_z) return fail("nemo_fct_set_mus_upstream: NULL array");
+    CU(cudaSetDevice(h->device));
+    try {
+        DevBuf<double> d_msk, d_z;
+        d_msk.upload(std::vector<double>(rnfmsk, rnfmsk + h->jpij));
+        d_z.upload(std::vector<double>(rnfmsk_z, rnfmsk_z + h->dom.jpk));
+        h->xind.alloc(h->n3);
+        launch_mus_xind(h->dom.jpi, h->dom.jpj, h->dom.jpk, d_msk.p, d_z.p, h->tmask.p, h->xind.p, h->stream);
+        CUTHROW(cudaStreamSynchronize(h->stream));
+        CUTHROW(cudaGetLastError());
+    } catch (const std::exception &e) { return fail("nemo_fct_set_mus_upstream: %s", e.what()); }
+    h->msc_ups = true;
+    return 0;
+}
+
+int nemo_tra_adv_mus_dev(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
+                         const double *pvn, const double *pwn, const double *ptb, double *pta, int kjpt)
+{
+    (void)kt; (void)kit000; (void)cdtype;
+    if (need_single(h, "nemo_tra_adv_mus_dev")) return 1;
+    if (!pun || !pvn || !pwn || !ptb || !pta) return fail("tra_adv_mus: NULL array");
+    std::vector<Ctx *> g = {h};
+    return run_mus(g, {MusCall{pun, pvn, pwn, ptb, pta}}, p2dt, kjpt);
+}
+
+int nemo_group_tra_adv_mus_dev(nemo_fct_handle *hs, int n, int kt, int kit000, const char *cdtype, double p2dt,
+                               const double *const *pun, const double *const *pvn, const double *const *pwn,
+                               const double *const *ptb, double *const *pta, int kjpt)
+{
+    (void)kt; (void)kit000; (void)cdtype;
+    if (!hs || n < 1) return fail("bad arguments");
+    std::vector<Ctx *> g(hs, hs + n);
+    if ((int)g[0]->group.size() != n) return fail("nemo_group_tra_adv_mus_dev: call nemo_fct_comm_init_local first");
+    std::vector<MusCall> a(n);
+    for (int m = 0; m < n; ++m) a[m] = MusCall{pun[m], pvn[m], pwn[m], ptb[m], pta[m]};
+    return run_mus(g, a, p2dt, kjpt);
+}
+
+int nemo_tra_adv_mus(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
+                     const double *pvn, const double *pwn, const double *ptb, double *pta, int kjpt)
+{
+    if (need_single(h, "nemo_tra_adv_mus")) return 1;
+    if (!pun || !pvn || !pwn || !ptb || !pta) return fail("tra_adv_mus: NULL array");
+    if (kjpt < 1) return fail("tra_adv_mus: kjpt = %d", kjpt);
+    CU(cudaSetDevice(h->device));
+    const size_t n3 = h->n3, n4 = n3 * (size_t)kjpt;
+    try {
+        if (h->s_pun.n != n3) { h->s_pun.alloc(n3); h->s_pvn.alloc(n3); h->s_pwn.alloc(n3); }
+        if (h->stage_kjpt < kjpt) { h->s_ptb.alloc(n4); h->s_ptn.alloc(n4); h->s_pta.alloc(n4); h->stage_kjpt = kjpt; }
+    } catch (const std::exception &e) { return fail("tra_adv_mus: staging buffers: %s", e.what()); }
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->s_pun.p, pun, n3 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_pvn.p, pvn, n3 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_pwn.p, pwn, n3 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_ptb.p, ptb, n4 * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->s_pta.p, pta, n4 * 8, cudaMemcpyHostToDevice, s));
+    if (nemo_tra_adv_mus_dev(h, kt, kit000, cdtype, p2dt, h->s_pun.p, h->s_pvn.p, h->s_pwn.p, h->s_ptb.p, h->s_pta.p, kjpt)) return 1;
+    CU(cudaMemcpyAsync(pta, h->s_pta.p, n4 * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int nemo_tra_nxt_dev(nemo_fct_handle h, int kt, int nit000, int l_euler, double rdt, const char *cdtype,
+                     const nemo_nxt_forcing *f, double *ptb, double *ptn, double *pta, const double *psbc_tc,
+                     const double *psbc_tc_b, int kjpt)
+{
+    (void)kt; (void)nit000;
+    if (need_single(h, "nemo_tra_nxt_dev")) return 1;
+    std::vector<Ctx *> g = {h};
+    return run_nxt(g, {NxtCall{f, ptb, ptn, pta, psbc_tc, psbc_tc_b}}, l_euler, rdt, cdtype, kjpt);
+}
+
+int nemo_group_tra_nxt_dev(nemo_fct_handle *hs, int n, int kt, int nit000, int l_euler, double rdt, const char *cdtype,
+                           const nemo_nxt_forcing *const *f, double *const *ptb, double *const *ptn, double *const *pta,
+                           const double *const *psbc_tc, const double *const *psbc_tc_b, int kjpt)
+{
+    (void)kt; (void)nit000;
+    if (!hs || n < 1 || !ptb || !ptn || !pta) return fail("bad arguments");
+    std::vector<Ctx *> g(hs, hs + n);
+    if ((int)g[0]->group.size() != n) return fail("nemo_group_tra_nxt_dev: call nemo_fct_comm_init_local first");
+    std::vector<NxtCall> a(n);
+    for (int m = 0; m < n; ++m)
+        a[m] = NxtCall{f ? f[m] : nullptr, ptb[m], ptn[m], pta[m], psbc_tc ? psbc_tc[m] : nullptr, psbc_tc_b ? psbc_tc_b[m] : nullptr};
+    return run_nxt(g, a, l_euler, rdt, cdtype, kjpt);
 }
 
 static int lnk_common(std::vector<Ctx *> &g, int nfld, double *const *const *ptab, const char *cd_nat, const double *psgn,

@@ -72,6 +72,44 @@ void oce_world_dom_msk(oce_world *w, const int **k_top, const int **k_bot, doubl
     oce_world_run(w, msk_thr, &a);
 }
 
+void oce_dom_set_mus_fields(oce_dom *d, const double *r1_e1e2u, const double *r1_e1e2v, const double *e3u_n,
+                            const double *e3v_n, const double *e3w_n)
+{
+    d->r1_e1e2u = r1_e1e2u; d->r1_e1e2v = r1_e1e2v; d->e3u_n = e3u_n; d->e3v_n = e3v_n; d->e3w_n = e3w_n;
+}
+
+typedef struct { double p2dt; const double **pun, **pvn, **pwn, **ptb; double **pta; int kjpt; const double **xind; } mus_arg;
+static void mus_thr(oce_dom *d, void *p)
+{
+    mus_arg *a = (mus_arg *)p; int r = d->nproc;
+    tra_adv_mus(d, 1, 1, "TRA", a->p2dt, a->pun[r], a->pvn[r], a->pwn[r], a->ptb[r], a->pta[r], a->kjpt, a->xind[r]);
+}
+void oce_world_tra_adv_mus(oce_world *w, double p2dt, const double **pun, const double **pvn, const double **pwn,
+                           const double **ptb, double **pta, int kjpt, const double **xind)
+{
+    mus_arg a = { p2dt, pun, pvn, pwn, ptb, pta, kjpt, xind };
+    oce_world_run(w, mus_thr, &a);
+}
+
+typedef struct {
+    int kt, kit000, l_euler; double rdt; const char *cdtype; const oce_nxt_forcing **f;
+    double **ptb, **ptn, **pta; const double **sbc, **sbc_b; int kjpt;
+} nxt_arg;
+static void nxt_thr(oce_dom *d, void *p)
+{
+    nxt_arg *a = (nxt_arg *)p; int r = d->nproc;
+    tra_nxt(d, a->kt, a->kit000, a->l_euler, a->rdt, a->cdtype, a->f[r], a->ptb[r], a->ptn[r], a->pta[r],
+            a->sbc ? a->sbc[r] : 0, a->sbc_b ? a->sbc_b[r] : 0, a->kjpt);
+}
+/* tra_nxt / trc_nxt on every subdomain (per-rank forcing structs and pointer tables indexed by nproc) */
+void oce_world_tra_nxt(oce_world *w, int kt, int kit000, int l_euler, double rdt, const char *cdtype,
+                       const oce_nxt_forcing **f, double **ptb, double **ptn, double **pta,
+                       const double **sbc, const double **sbc_b, int kjpt)
+{
+    nxt_arg a = { kt, kit000, l_euler, rdt, cdtype, f, ptb, ptn, pta, sbc, sbc_b, kjpt };
+    oce_world_run(w, nxt_thr, &a);
+}
+
 /* world-level tables for tests of mpp_init */
 void oce_world_tables(const oce_world *w, int *nimppt, int *njmppt, int *nlcit, int *nlcjt)
 {

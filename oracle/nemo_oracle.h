@@ -10,6 +10,8 @@
  *   mpp_nfd (multi-rank north fold)         src/OCE/LBC/mpp_nfd_generic.h90:48-302 (+ lbc_nfd_nogather_generic.h90)
  *   mpp_init / mpp_basic_decomposition      src/OCE/LBC/mppini.F90:110-692, 695-798, 1180-1240
  *   dom_msk (masks)                         src/OCE/DOM/dommsk.F90:135-238
+ *   tra_adv_mus (MUSCL)                     src/OCE/TRA/traadv_mus.F90:55-273
+ *   tra_nxt / tra_nxt_fix / tra_nxt_vvl     src/OCE/TRA/tranxt.F90:65-380 (+ trc_nxt swap, src/TOP/TRP/trcnxt.F90:56-183)
  *   SIGN / DDPDD / glob_sum                 src/OCE/lib_fortran.F90:300-351, lib_fortran_generic.h90:32-65
  *
  * PARITY UNPINNED: the reference tree holds no golden vectors / known-answer tests for this path and the
@@ -66,7 +68,22 @@ typedef struct oce_dom {
     double *dbg_paa, *dbg_pbb, *dbg_pcc;               /* after X4 (:426) */
     double *dbg_ztw;                                   /* interp_4th_cpt output */
     double *dbg_zltu, *dbg_zltv;                       /* after X1 (:209) */
+    /* extra module arrays read by tra_adv_mus (dom_oce.F90:118, 132-136); NULL until set */
+    const double *r1_e1e2u, *r1_e1e2v;                 /* (jpi,jpj)     */
+    const double *e3u_n, *e3v_n, *e3w_n;               /* (jpi,jpj,jpk) */
 } oce_dom;
+
+/* Module variables read by tra_nxt_vvl (tranxt.F90:262-343): sbc_oce, sbcrnf, sbcisf, traqsr, phycst.
+ * A NULL 2-D flux array stands for zeros (that forcing is switched off).                                        */
+typedef struct oce_nxt_forcing {
+    double atfp, r1_rau0;                              /* dom_oce.F90:58, phycst.F90:42 */
+    int ln_traqsr, ln_rnf, ln_isf, ln_rnf_depth, nksr; /* traqsr.F90:54, sbcrnf.F90, sbcisf.F90 */
+    const double *emp_b, *emp, *fwfisf_b, *fwfisf, *rnf_b, *rnf;        /* (jpi,jpj) */
+    const double *qsr_hc, *qsr_hc_b;                                    /* (jpi,jpj,jpk) */
+    const int *nk_rnf; const double *h_rnf, *rnf_tsc, *rnf_tsc_b;       /* (jpi,jpj), (jpi,jpj,jpts) */
+    const int *misfkt, *misfkb;                                         /* (jpi,jpj) */
+    const double *risf_tsc, *risf_tsc_b, *r1_hisf_tbl, *ralpha;         /* (jpi,jpj,jpts), (jpi,jpj) */
+} oce_nxt_forcing;
 
 /* The set of subdomains of one run ("mpi_comm_oce"), with global tables (mppini.F90). */
 typedef struct oce_world {
@@ -112,6 +129,21 @@ void nonosc(oce_dom *d, const double *pbef, double *paa, double *pbb, double *pc
             double p2dt, int jn);
 void interp_4th_cpt(const oce_dom *d, const double *pt_in, double *pt_out);
 void oracle_poison_workspace(int on);  /* fill automatic arrays with NaN before use (catches undefined reads) */
+
+/* ---- traadv_mus.c ---- */
+void tra_adv_mus_xind(const oce_dom *d, int ld_msc_ups, const double *rnfmsk, const double *rnfmsk_z, double *xind);
+void tra_adv_mus(oce_dom *d, int kt, int kit000, const char *cdtype, double p2dt,
+                 const double *pun, const double *pvn, const double *pwn,
+                 const double *ptb, double *pta, int kjpt, const double *xind);  /* traadv_mus.F90:55-273 */
+
+/* ---- tranxt.c ---- */
+void tra_nxt_fix(oce_dom *d, int kt, int kit000, const char *cdtype, double atfp,
+                 double *ptb, double *ptn, double *pta, int kjpt);              /* tranxt.F90:190-234 */
+void tra_nxt_vvl(oce_dom *d, int kt, int kit000, double p2dt, const char *cdtype, const oce_nxt_forcing *f,
+                 double *ptb, double *ptn, double *pta, const double *psbc_tc, const double *psbc_tc_b,
+                 int kjpt);                                                     /* tranxt.F90:237-380 */
+void tra_nxt(oce_dom *d, int kt, int kit000, int l_euler, double rdt, const char *cdtype, const oce_nxt_forcing *f,
+             double *ptb, double *ptn, double *pta, const double *psbc_tc, const double *psbc_tc_b, int kjpt);
 
 /* ---- traadv.c ---- */
 void tra_adv_transports(const oce_dom *d, const double *e2u, const double *e1v, const double *e3u_n,

@@ -56,6 +56,11 @@ def lib():
         L.sign_nosignedzero.restype = C.c_double
         L.sign_nosignedzero.argtypes = [C.c_double, C.c_double]
         L.tra_adv_transports.argtypes = [C.c_void_p] * 11
+        L.oce_dom_set_mus_fields.argtypes = [C.c_void_p] * 6
+        L.tra_adv_mus_xind.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oce_world_tra_adv_mus.argtypes = [C.c_void_p, C.c_double] + [C.POINTER(C.c_void_p)] * 5 + [C.c_int, C.POINTER(C.c_void_p)]
+        L.oce_world_tra_nxt.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_char_p]
+                                        + [C.POINTER(C.c_void_p)] * 6 + [C.c_int])
         _LIB = L
     return _LIB
 
@@ -70,6 +75,25 @@ def _ptr_table(arrs):
     for i, a in enumerate(arrs):
         t[i] = None if a is None else a.ctypes.data
     return t
+
+
+class NxtForcing(C.Structure):
+    """oce_nxt_forcing: module variables read by tra_nxt_vvl (tranxt.F90:262-343); arrays kept alive in _keep."""
+    _fields_ = ([("atfp", C.c_double), ("r1_rau0", C.c_double)]
+                + [(n, C.c_int) for n in "ln_traqsr ln_rnf ln_isf ln_rnf_depth nksr".split()]
+                + [(n, C.c_void_p) for n in ("emp_b emp fwfisf_b fwfisf rnf_b rnf qsr_hc qsr_hc_b nk_rnf h_rnf rnf_tsc "
+                                             "rnf_tsc_b misfkt misfkb risf_tsc risf_tsc_b r1_hisf_tbl ralpha").split()])
+
+    def __init__(self, atfp=0.1, r1_rau0=1.0 / 1026.0, **kw):
+        super().__init__()
+        self.atfp, self.r1_rau0 = atfp, r1_rau0
+        self._keep = {}
+        for k, v in kw.items():
+            if isinstance(v, np.ndarray):
+                self._keep[k] = v
+                setattr(self, k, v.ctypes.data)
+            else:
+                setattr(self, k, int(v))
 
 
 class Dom:
@@ -94,6 +118,18 @@ class Dom:
         assert mikt.dtype == np.int32 and mbkt.dtype == np.int32
         self._keep["fields"] = arrs
         lib().oce_dom_set_fields(self.h, *[_ptr(a) for a in arrs], int(ln_linssh), int(ln_isfcav))
+
+    def set_mus_fields(self, r1_e1e2u, r1_e1e2v, e3u_n, e3v_n, e3w_n):
+        arrs = [r1_e1e2u, r1_e1e2v, e3u_n, e3v_n, e3w_n]
+        self._keep["mus"] = arrs
+        lib().oce_dom_set_mus_fields(self.h, *[_ptr(a) for a in arrs])
+
+    def mus_xind(self, ld_msc_ups=False, rnfmsk=None, rnfmsk_z=None):
+        """xind of traadv_mus.F90:99-113 (needs tmask bound when ld_msc_ups)."""
+        xind = np.empty(self.shape3)
+        lib().tra_adv_mus_xind(self.h, int(ld_msc_ups), None if rnfmsk is None else _ptr(rnfmsk),
+                               None if rnfmsk_z is None else _ptr(rnfmsk_z), _ptr(xind))
+        return xind
 
     def set_dbg(self, jn, **arrs):
         names = "zwi zwx zwy zwz zbetup zbetdo paa pbb pcc ztw zltu zltv".split()
@@ -151,6 +187,18 @@ class World:
         L = lib()
         L.oce_world_tra_adv_fct(self.h, p2dt, _ptr_table(pun), _ptr_table(pvn), _ptr_table(pwn), _ptr_table(ptb),
                                 _ptr_table(ptn), _ptr_table(pta), kjpt, kn_fct_h, kn_fct_v)
+
+    def tra_adv_mus(self, p2dt, pun, pvn, pwn, ptb, pta, kjpt, xind):
+        """tra_adv_mus on every subdomain; pta updated in place; xind: list over ranks."""
+        lib().oce_world_tra_adv_mus(self.h, p2dt, _ptr_table(pun), _ptr_table(pvn), _ptr_table(pwn), _ptr_table(ptb),
+                                    _ptr_table(pta), kjpt, _ptr_table(xind))
+
+    def tra_nxt(self, kt, kit000, l_euler, rdt, cdtype, forcing, ptb, ptn, pta, kjpt, sbc=None, sbc_b=None):
+        """tra_nxt ('TRA') / trc_nxt ('TRC') on every subdomain; forcing: list over ranks of NxtForcing."""
+        ft = (C.c_void_p * self.jpnij)(*[C.addressof(f) for f in forcing])
+        lib().oce_world_tra_nxt(self.h, kt, kit000, int(l_euler), rdt, cdtype.encode(), ft, _ptr_table(ptb),
+                                _ptr_table(ptn), _ptr_table(pta), None if sbc is None else _ptr_table(sbc),
+                                None if sbc_b is None else _ptr_table(sbc_b), kjpt)
 
     def dom_msk(self, k_top, k_bot):
         """returns per-rank dict(tmask, umask, vmask, wmask, tmask_i, mikt, mbkt)."""

@@ -153,3 +153,106 @@ def max_rel_diff(a, b):
     scale = np.abs(b).max()
     den = np.maximum(np.abs(b), 1e-30 * max(scale, 1e-300))
     return float((np.abs(a - b) / den).max())
+
+
+# ---- MUSCL (tra_adv_mus) and tra_nxt helpers ---------------------------------------------------------------------------
+MUS_KEYS = ("r1_e1e2u", "r1_e1e2v", "e3u_n", "e3v_n", "e3w_n")
+
+
+def mus_extra_fields(O, gf, jpiglo, jpjglo, jpk, jperio, seed=1, runoff=False):
+    """Extra module arrays tra_adv_mus reads (global, lbc-consistent): r1_e1e2u/v, e3u_n/e3v_n/e3w_n, and for
+    ld_msc_ups a river-mouth mask rnfmsk (jpj,jpi) + rnfmsk_z (jpk)."""
+    rng = np.random.default_rng(1000 + seed)
+    w = O.World(jpiglo, jpjglo, jpk, jperio, 1, 1)
+    d = w.doms[0]
+    jpi, jpj = d.jpi, d.jpj
+
+    def lbc(arrs, nat, sgn):
+        w.lbc_lnk([[a] for a in arrs], nat, sgn)
+
+    e1e2u = (gf["e1e2t"] * (1.0 + 0.05 * rng.random((jpj, jpi))))[None].copy()
+    e1e2v = (gf["e1e2t"] * (1.0 + 0.05 * rng.random((jpj, jpi))))[None].copy()
+    lbc([e1e2u, e1e2v], "UV", [1.0, 1.0])
+    e1e2u[e1e2u == 0.0] = 1.0e10
+    e1e2v[e1e2v == 0.0] = 1.0e10
+    e3u_n = gf["e3t_n"] * (1.0 + 0.01 * rng.standard_normal((jpk, jpj, jpi)))
+    e3v_n = gf["e3t_n"] * (1.0 + 0.01 * rng.standard_normal((jpk, jpj, jpi)))
+    e3w_n = gf["e3t_n"] * (1.0 + 0.01 * rng.standard_normal((jpk, jpj, jpi)))
+    lbc([e3u_n, e3v_n, e3w_n], "UVW", [1.0, 1.0, 1.0])
+    for a in (e3u_n, e3v_n, e3w_n):
+        a[a == 0.0] = 30.0
+    out = dict(r1_e1e2u=np.ascontiguousarray(1.0 / e1e2u[0]), r1_e1e2v=np.ascontiguousarray(1.0 / e1e2v[0]),
+               e3u_n=e3u_n, e3v_n=e3v_n, e3w_n=e3w_n)
+    if runoff:
+        msk = (rng.random((jpj, jpi)) < 0.2).astype(np.float64) * rng.choice([0.5, 1.0], size=(jpj, jpi))
+        m3 = msk[None].copy(); lbc([m3], "T", [1.0])
+        out["rnfmsk"] = np.ascontiguousarray(m3[0])
+        z = np.zeros(jpk); z[: max(2, jpk // 3)] = 0.5; z[0] = 1.0
+        out["rnfmsk_z"] = z
+    w.close()
+    return out
+
+
+def oracle_mus(O, gf, mx, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, ln_linssh=False, ln_isfcav=False,
+               ld_msc_ups=False, xind_zero=False, key_mpp_mpi=True):
+    """oracle tra_adv_mus on the global fields decomposed jpni x jpnj; returns (global pta, local list)."""
+    w = O.World(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, key_mpp_mpi=key_mpp_mpi)
+    loc = {k: w.scatter(gf[k]) for k in DOM_KEYS + ("pun", "pvn", "pwn", "ptb", "pta")}
+    lx = {k: w.scatter(mx[k]) for k in MUS_KEYS}
+    rn = w.scatter(mx["rnfmsk"]) if ld_msc_ups else None
+    xind = []
+    for r, d in enumerate(w.doms):
+        d.set_fields(*[loc[k][r] for k in DOM_KEYS], ln_linssh=ln_linssh, ln_isfcav=ln_isfcav)
+        d.set_mus_fields(*[lx[k][r] for k in MUS_KEYS])
+        xi = d.mus_xind(ld_msc_ups, rn[r] if ld_msc_ups else None, mx["rnfmsk_z"] if ld_msc_ups else None)
+        if xind_zero:
+            xi[:] = 0.0
+        xind.append(xi)
+    w.tra_adv_mus(gf["p2dt"], loc["pun"], loc["pvn"], loc["pwn"], loc["ptb"], loc["pta"], kjpt, xind)
+    glob = w.gather(loc["pta"], gf["pta"].copy())
+    w.close()
+    return glob, loc["pta"]
+
+
+def device_mus(N, gf, mx, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, ln_linssh=False, ln_isfcav=False,
+               ld_msc_ups=False, schedule=0, host_path=False):
+    """the product's tra_adv_mus on cuda:0 through the C ABI (single subdomain or in-process group)."""
+    from oracle import oracle as O   # scatter/gather bookkeeping of the test itself
+    w = O.World(jpiglo, jpjglo, jpk, jperio, jpni, jpnj)
+    loc = {k: w.scatter(gf[k]) for k in DOM_KEYS + ("pun", "pvn", "pwn", "ptb", "pta")}
+    lx = {k: w.scatter(mx[k]) for k in MUS_KEYS}
+    rn = w.scatter(mx["rnfmsk"]) if ld_msc_ups else None
+    n = jpni * jpnj
+    dev = torch.device("cuda:0")
+    if n == 1:
+        ctxs = [N.FctContext(N.mpp_init(jpiglo, jpjglo, jpk, jperio, 1, 1, 1), 0)]
+    else:
+        grp = N.LocalGroup(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, 0)
+        ctxs = grp.ctx
+    ctxs[0].set_schedule(schedule)
+    for r, c in enumerate(ctxs):
+        c.set_domain_arrays(loc["tmask"][r], loc["umask"][r], loc["vmask"][r], loc["wmask"][r], loc["e1e2t"][r],
+                            loc["r1_e1e2t"][r], loc["mikt"][r], loc["mbkt"][r], ln_linssh, ln_isfcav)
+        c.set_e3t(loc["e3t_b"][r], loc["e3t_n"][r], loc["e3t_a"][r])
+        c.set_mus_metrics(lx["r1_e1e2u"][r], lx["r1_e1e2v"][r])
+        c.set_e3uvw(lx["e3u_n"][r], lx["e3v_n"][r], lx["e3w_n"][r])
+        c.set_mus_upstream(ld_msc_ups, rn[r] if ld_msc_ups else None, mx["rnfmsk_z"] if ld_msc_ups else None)
+    if host_path:
+        assert n == 1
+        pta = loc["pta"][0].copy()
+        ctxs[0].tra_adv_mus(1, 1, "TRC", gf["p2dt"], loc["pun"][0], loc["pvn"][0], loc["pwn"][0], loc["ptb"][0], pta, kjpt)
+        out = [pta]
+    else:
+        t = {k: [torch.from_numpy(a).to(dev) for a in loc[k]] for k in ("pun", "pvn", "pwn", "ptb", "pta")}
+        if n == 1:
+            ctxs[0].tra_adv_mus(1, 1, "TRC", gf["p2dt"], t["pun"][0], t["pvn"][0], t["pwn"][0], t["ptb"][0], t["pta"][0], kjpt)
+            ctxs[0].synchronize()
+        else:
+            grp.tra_adv_mus(1, 1, "TRC", gf["p2dt"], t["pun"], t["pvn"], t["pwn"], t["ptb"], t["pta"], kjpt)
+            grp.synchronize()
+        out = [a.cpu().numpy() for a in t["pta"]]
+    glob = w.gather(out, gf["pta"].copy())
+    w.close()
+    for c in ctxs:
+        c.close()
+    return glob, out
