@@ -182,7 +182,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--schedule", type=int, default=None)
+    ap.add_argument("--scheme", default="fct", choices=["fct", "mus", "nxt"],
+                    help="fct (default, the BASELINE.json metric); mus / nxt time the widened rows tra_adv_mus / tra_nxt "
+                         "on the same workload (device-resident value + roofline only)")
     args = ap.parse_args()
+    if args.scheme != "fct":
+        args.no_e2e = args.no_cpu_baseline = True
 
     BF = importlib.import_module("nemo-fmi-devel_b200.bench_fields")
     cfg = BF.CONFIGS[args.workload]
@@ -244,8 +249,19 @@ def main():
     npts_global = G * GJ * K
     npts_local = dom.jpi * dom.jpj * dom.jpk
 
+    if args.scheme == "mus":                                  # uniform BENCH grid: e1e2u = e1e2v = e1e2t, e3u = e3v = e3w = e3t (zco)
+        r1 = f["r1_e1e2t"].cpu().numpy()
+        ctx.set_mus_metrics(r1, r1)
+        ctx.set_e3uvw(f["e3t_n"], f["e3t_n"], f["e3t_n"])
+    forcing = N.NxtForcing(atfp=0.1) if args.scheme == "nxt" else None
+
     def step():
-        ctx.tra_adv_fct(1, 1, "TRA", f["p2dt"], f["pun"], f["pvn"], f["pwn"], f["ptb"], f["ptn"], f["pta"], kjpt, h, v)
+        if args.scheme == "fct":
+            ctx.tra_adv_fct(1, 1, "TRA", f["p2dt"], f["pun"], f["pvn"], f["pwn"], f["ptb"], f["ptn"], f["pta"], kjpt, h, v)
+        elif args.scheme == "mus":
+            ctx.tra_adv_mus(1, 1, "TRC", f["p2dt"], f["pun"], f["pvn"], f["pwn"], f["ptb"], f["pta"], kjpt)
+        else:                                                 # leap-frog + Asselin (tra_nxt_vvl) + the two lbc_lnk of tra_nxt
+            ctx.tra_nxt(2, 1, False, rdt, "TRA", forcing, f["ptb"], f["ptn"], f["pta"], kjpt)
 
     def barrier():
         if world > 1:
@@ -285,6 +301,13 @@ def main():
     # ---- roofline ---------------------------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
     b_alg = BF.algorithmic_bytes(npts_local, kjpt)            # this GPU's share
+    scope = "whole step per GPU: B_alg = N_local*(32*kjpt+56) bytes over the step time (all kernels + exchanges)"
+    if args.scheme == "mus":      # per tracer-point r ptb, pta, w pta; per point r pun pvn pwn e3u_n e3v_n e3w_n e3t_n tmask
+        b_alg = npts_local * (24 * kjpt + 64)
+        scope = "whole step per GPU: B_alg = N_local*(24*kjpt+64) bytes (tra_adv_mus) over the step time"
+    elif args.scheme == "nxt":    # per tracer-point r ptb ptn pta, w ptb ptn; per point r e3t_b e3t_n e3t_a
+        b_alg = npts_local * (40 * kjpt + 24)
+        scope = "whole step per GPU: B_alg = N_local*(40*kjpt+24) bytes (tra_nxt_vvl) over the step time"
     n3 = npts_local
     # per-kernel algorithmic bytes: the arrays each kernel must read/write once ("kernels").  In the fused
     # schedules the frame kernels run on thin bands on a side stream, overlapped with the inner kernels: their event
@@ -295,6 +318,8 @@ def main():
         "interp_4th_cpt": a3 * (2 * kjpt) + a3 * 2,                                    # r ptn; w ztw; r wmask, zwt
         "fct_low_antidiff_inner": a3 * ((3 + 5 + (1 if v == 4 else 0)) * kjpt) + a3 * 7,   # r ptb ptn pta [ztw]; w pta zwi zwx zwy zwz; r pun pvn pwn e3t_b/n/a tmask
         "fct_nonosc_final": a3 * ((6 + 1) * kjpt) + a3 * 2,                            # r ptb zwi zwx zwy zwz pta; w pta; r tmask e3t_n
+        "mus_inner": a3 * (3 * kjpt) + a3 * 11,                                        # r ptb pta; w pta; r pun pvn pwn e3u e3v e3w e3t tmask umask vmask wmask
+        "tra_nxt": a3 * (5 * kjpt) + a3 * 3,
     }
     if not fused:
         kbytes.update({
@@ -332,7 +357,7 @@ def main():
         traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src,
-                "scope": "whole step per GPU: B_alg = N_local*(32*kjpt+56) bytes over the step time (all kernels + exchanges)",
+                "scope": scope,
                 "alg_bytes_per_step": b_alg, "dominant_kernel": dominant, "kernels": kern}
 
     # ---- e2e: host-pointer entry points, pinned host buffers ---------------------------------------------------------
@@ -379,9 +404,10 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        metric = METRIC if args.scheme == "fct" else {"mus": "MUSCL tracer-advection Mpts/s per step", "nxt": "tra_nxt (Asselin filter + swap) Mpts/s per step"}[args.scheme]
+        line = {"metric": metric, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_max, 4), "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, cfg, world, part, sched),
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(workload_config(args.workload, cfg, world, part, sched), scheme=args.scheme),
                 "tracer_mpts_per_s": round(value * kjpt, 2), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "checksum_abs_pta": checksum}
         print(json.dumps(line), flush=True)
