@@ -63,6 +63,58 @@ def main():
                 ok_all = ok_all and bool(flag.item())
                 ctx.close()
                 w.close()
+    # ---- widened rows over NCCL: tra_adv_mus (both structures) and tra_nxt (Asselin + swap, Euler swap) --------------
+    def make_ctx(jperio, loc, schedule):
+        dom = N.mpp_init(G, GJ, K, jperio, part[0], part[1], rank + 1)
+        ctx = N.FctContext(dom, lr)
+        ctx.set_schedule(schedule)
+        if world > 1:
+            idt = torch.zeros(N.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(N.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+        ctx.set_domain_arrays(loc["tmask"], loc["umask"], loc["vmask"], loc["wmask"], loc["e1e2t"], loc["r1_e1e2t"],
+                              loc["mikt"], loc["mbkt"], False, False)
+        ctx.set_e3t(loc["e3t_b"], loc["e3t_n"], loc["e3t_a"])
+        return ctx
+
+    def agree(ok, what):
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("%s %dx%d: %s" % (what, part[0], part[1], "BIT-IDENTICAL" if flag.item() else "MISMATCH"), flush=True)
+        return bool(flag.item())
+
+    for jperio in (0, 1, 4, 6):
+        gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=70 + jperio)
+        mx = H.mus_extra_fields(O, gf, G, GJ, K, jperio, seed=70 + jperio)
+        _, refl = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, part[0], part[1], kjpt)
+        w = O.World(G, GJ, K, jperio, part[0], part[1])
+        loc = {k: w.scatter(gf[k])[rank] for k in H.DOM_KEYS + ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
+        lx = {k: w.scatter(mx[k])[rank] for k in H.MUS_KEYS}
+        for schedule in (0, 1, 2):
+            ctx = make_ctx(jperio, loc, schedule)
+            ctx.set_mus_metrics(lx["r1_e1e2u"], lx["r1_e1e2v"])
+            ctx.set_e3uvw(lx["e3u_n"], lx["e3v_n"], lx["e3w_n"])
+            t = {k: torch.from_numpy(loc[k]).to(dev) for k in ("pun", "pvn", "pwn", "ptb", "pta")}
+            ctx.tra_adv_mus(1, 1, "TRC", gf["p2dt"], t["pun"], t["pvn"], t["pwn"], t["ptb"], t["pta"], kjpt)
+            ctx.synchronize()
+            ok_all = agree(np.array_equal(t["pta"].cpu().numpy(), refl[rank]), "tra_adv_mus jperio=%d schedule=%d" % (jperio, schedule)) and ok_all
+            ctx.close()
+        for (cdtype, l_euler) in (("TRA", False), ("TRC", True)):
+            oloc = {k: w.scatter(gf[k]) for k in H.DOM_KEYS + ("ptb", "ptn", "pta")}
+            for r, d in enumerate(w.doms):
+                d.set_fields(*[oloc[k][r] for k in H.DOM_KEYS], ln_linssh=False)
+            t = {k: torch.from_numpy(oloc[k][rank].copy()).to(dev) for k in ("ptb", "ptn", "pta")}
+            w.tra_nxt(3, 1, l_euler, 900.0, cdtype, [O.NxtForcing(atfp=0.1) for _ in w.doms], oloc["ptb"], oloc["ptn"], oloc["pta"], kjpt)
+            ctx = make_ctx(jperio, loc, 2)
+            ctx.tra_nxt(3, 1, l_euler, 900.0, cdtype, N.NxtForcing(atfp=0.1), t["ptb"], t["ptn"], t["pta"], kjpt)
+            ctx.synchronize()
+            ok = all(np.array_equal(t[k].cpu().numpy(), oloc[k][rank]) for k in ("ptb", "ptn", "pta"))
+            ok_all = agree(ok, "tra_nxt %s euler=%d jperio=%d" % (cdtype, l_euler, jperio)) and ok_all
+            ctx.close()
+        w.close()
     if rank == 0:
         print("MGPU_CHECK", "PASS" if ok_all else "FAIL", flush=True)
     dist.destroy_process_group()
