@@ -169,6 +169,26 @@ int nemo_group_tra_adv_mus_dev(nemo_fct_handle *hs, int n, int kt, int kit000, c
                                const double *const *pun, const double *const *pvn, const double *const *pwn,
                                const double *const *ptb, double *const *pta, int kjpt);
 
+/* ---- tra_adv_cen: centred scheme (traadv_cen.F90:46-204) -------------------------------------------------------------- */
+/* CALL tra_adv_cen( kt, kit000, cdtype, pun, pvn, pwn, ptn, pta, kjpt, kn_cen_h, kn_cen_v ), kn_cen_h, kn_cen_v in {2, 4}
+ * (4 in the vertical = the compact scheme of interp_4th_cpt).  Device pointers.  kn_cen_h = 2 needs no exchange at all;
+ * kn_cen_h = 4 does the reference's lbc_lnk on the masked gradients (:126) and reproduces what its loop bounds do at the
+ * first interior row / column (:128-137 read ztu(0,jj,jk) and the never-assigned zwy(:,1,:), taken as 0 -- DESIGN.md).    */
+int nemo_tra_adv_cen_dev(nemo_fct_handle h, int kt, int kit000, const char *cdtype, const double *pun, const double *pvn,
+                         const double *pwn, const double *ptn, double *pta, int kjpt, int kn_cen_h, int kn_cen_v);
+int nemo_group_tra_adv_cen_dev(nemo_fct_handle *hs, int n, int kt, int kit000, const char *cdtype,
+                               const double *const *pun, const double *const *pvn, const double *const *pwn,
+                               const double *const *ptn, double *const *pta, int kjpt, int kn_cen_h, int kn_cen_v);
+
+/* ---- l_trd / l_hst / l_ptr hooks of tra_adv_fct (traadv_fct.F90:96-112, 172-176, 299-316) ------------------------------- */
+/* With three non-NULL DEVICE arrays (jpi,jpj,jpk,kjpt) every following nemo_tra_adv_fct[_dev] call also returns the total
+ * advective fluxes the reference hands to trd_tra / dia_ar5_hst / dia_ptr_hst: ztrdx, ztrdy (= zptry) = upstream + limited
+ * anti-diffusive flux on (1:jpim1, 1:jpjm1, 1:jpk) (column jpi / row jpj are undefined in the reference and left
+ * untouched), ztrdz on the whole (jpi,jpj,jpk).  The step then runs the reference pass structure (schedule 0), where the
+ * limited fluxes exist in memory.  Three NULLs switch the hooks off.  The consumers themselves (trd_tra, dia_*) stay on
+ * the host side of the boundary.                                                                                          */
+int nemo_fct_set_trend_diag(nemo_fct_handle h, double *ztrdx, double *ztrdy, double *ztrdz);
+
 /* ---- tra_nxt / trc_nxt: lateral boundary conditions on the after field, Asselin filter, swap ---------------------------- */
 /* Module variables read by tra_nxt_vvl (tranxt.F90:262-343; sbc_oce, sbcrnf, sbcisf, traqsr, phycst).  All pointers are
  * DEVICE pointers; a NULL 2-D flux array stands for zeros.  The arrays behind an enabled switch must be non-NULL.          */

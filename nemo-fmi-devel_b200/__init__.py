@@ -103,6 +103,9 @@ def lib():
         "nemo_tra_adv_mus": [vp, i, i, C.c_char_p, d] + [vp] * 5 + [i],
         "nemo_tra_adv_mus_dev": [vp, i, i, C.c_char_p, d] + [vp] * 5 + [i],
         "nemo_group_tra_adv_mus_dev": [C.POINTER(vp), i, i, i, C.c_char_p, d] + [C.POINTER(vp)] * 5 + [i],
+        "nemo_tra_adv_cen_dev": [vp, i, i, C.c_char_p] + [vp] * 5 + [i, i, i],
+        "nemo_group_tra_adv_cen_dev": [C.POINTER(vp), i, i, i, C.c_char_p] + [C.POINTER(vp)] * 5 + [i, i, i],
+        "nemo_fct_set_trend_diag": [vp, vp, vp, vp],
         "nemo_tra_nxt_dev": [vp, i, i, i, d, C.c_char_p, vp, vp, vp, vp, vp, vp, i],
         "nemo_group_tra_nxt_dev": [C.POINTER(vp), i, i, i, i, d, C.c_char_p] + [C.POINTER(vp)] * 6 + [i],
         "nemo_lbc_lnk_multi": [vp, C.c_char_p, i, C.POINTER(vp), C.c_char_p, dp, i, i, d],
@@ -130,7 +133,8 @@ ABI_SYMBOLS = (
     "nemo_fct_comm_init nemo_fct_comm_init_local nemo_tra_adv_fct nemo_tra_adv_fct_dev nemo_group_tra_adv_fct_dev "
     "nemo_interp_4th_cpt nemo_interp_4th_cpt_dev nemo_tra_adv_transports_dev nemo_tra_adv_dev nemo_trc_adv_dev nemo_lbc_lnk_multi "
     "nemo_fct_set_mus_metrics nemo_fct_set_e3uvw nemo_fct_set_mus_upstream nemo_tra_adv_mus nemo_tra_adv_mus_dev "
-    "nemo_group_tra_adv_mus_dev nemo_tra_nxt_dev nemo_group_tra_nxt_dev "
+    "nemo_group_tra_adv_mus_dev nemo_tra_nxt_dev nemo_group_tra_nxt_dev nemo_tra_adv_cen_dev nemo_group_tra_adv_cen_dev "
+    "nemo_fct_set_trend_diag "
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
     "nemo_fct_profile_read").split()
@@ -387,6 +391,29 @@ class FctContext:
         fn = lib().nemo_tra_adv_mus_dev if dev else lib().nemo_tra_adv_mus
         _check(fn(self._h, kt, kit000, cdtype.encode(), float(p2dt), _ptr(pun), _ptr(pvn), _ptr(pwn), _ptr(ptb), _ptr(pta), kjpt))
 
+    def tra_adv_cen(self, kt, kit000, cdtype, pun, pvn, pwn, ptn, pta, kjpt, kn_cen_h, kn_cen_v):
+        """tra_adv_cen( kt, kit000, cdtype, pun, pvn, pwn, ptn, pta, kjpt, kn_cen_h, kn_cen_v ) (traadv_cen.F90:46-47);
+        device tensors only."""
+        s3, s4 = self.dom.shape3, (kjpt,) + self.dom.shape3
+        for a, shp in ((pun, s3), (pvn, s3), (pwn, s3), (ptn, s4), (pta, s4)):
+            if not _is_dev(a) or tuple(a.shape) != shp:
+                raise ValueError(f"tra_adv_cen: device tensor of shape {shp} expected, got {tuple(a.shape)}")
+            _f64(a, "tra_adv_cen")
+        _check(lib().nemo_tra_adv_cen_dev(self._h, kt, kit000, cdtype.encode(), _ptr(pun), _ptr(pvn), _ptr(pwn), _ptr(ptn),
+                                          _ptr(pta), kjpt, kn_cen_h, kn_cen_v))
+
+    def set_trend_diag(self, ztrdx=None, ztrdy=None, ztrdz=None):
+        """l_trd / l_hst / l_ptr hooks of tra_adv_fct (traadv_fct.F90:96-112): device tensors (kjpt,jpk,jpj,jpi) that
+        receive ztrdx, ztrdy (= zptry), ztrdz at every following tra_adv_fct call; no arguments = hooks off."""
+        arrs = (ztrdx, ztrdy, ztrdz)
+        if any(a is not None for a in arrs):
+            for a in arrs:
+                if a is None or not _is_dev(a):
+                    raise ValueError("set_trend_diag: three device tensors or none")
+                _f64(a, "set_trend_diag")
+        self._keep["diag"] = arrs
+        _check(lib().nemo_fct_set_trend_diag(self._h, *[None if a is None else _ptr(a) for a in arrs]))
+
     def tra_nxt(self, kt, nit000, l_euler, rdt, cdtype, forcing, ptb, ptn, pta, kjpt, sbc_tc=None, sbc_tc_b=None):
         """tra_nxt( kt ) (tranxt.F90:65) for cdtype 'TRA' / trc_nxt( kt ) (trcnxt.F90:56) for 'TRC', module state passed
         explicitly; device tensors only.  forcing: :class:`NxtForcing` (may be None for an Euler step)."""
@@ -459,6 +486,12 @@ class LocalGroup:
         _check(lib().nemo_group_tra_adv_mus_dev(self._hs, self.n, kt, kit000, cdtype.encode(), float(p2dt),
                                                 self._tab(pun), self._tab(pvn), self._tab(pwn), self._tab(ptb),
                                                 self._tab(pta), kjpt))
+
+    def tra_adv_cen(self, kt, kit000, cdtype, pun, pvn, pwn, ptn, pta, kjpt, kn_cen_h, kn_cen_v):
+        for lst in (pun, pvn, pwn, ptn, pta):
+            assert len(lst) == self.n and all(_is_dev(a) for a in lst)
+        _check(lib().nemo_group_tra_adv_cen_dev(self._hs, self.n, kt, kit000, cdtype.encode(), self._tab(pun), self._tab(pvn),
+                                                self._tab(pwn), self._tab(ptn), self._tab(pta), kjpt, kn_cen_h, kn_cen_v))
 
     def tra_nxt(self, kt, nit000, l_euler, rdt, cdtype, forcing, ptb, ptn, pta, kjpt, sbc_tc=None, sbc_tc_b=None):
         """forcing: list over ranks of NxtForcing (or None for an Euler step)"""

@@ -1107,6 +1107,40 @@ void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s)
     note_launch();
 }
 
+// trend-diagnostic hook: ztrd = upstream flux + limited anti-diffusive flux (traadv_fct.F90:172-176, 299-303)
+__global__ void __launch_bounds__(kThreads) k_fct_diag(const FctArgs a, double *trdx, double *trdy, double *trdz)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)a.jpij) return;
+    const int jj = (int)(p / a.jpi) + 1, ji = (int)(p % a.jpi) + 1;
+    const size_t toff = (size_t)blockIdx.z * a.n3;
+    const double *ptb = a.ptb + toff, *zwx = a.zwx + toff, *zwy = a.zwy + toff, *zwz = a.zwz + toff;
+    const size_t c2 = (size_t)p;
+    const int mik = a.ln_isfcav ? a.mikt[c2] : 1;
+    const bool hm = ji <= a.jpi - 1 && jj <= a.jpj - 1;                  // the h- range of P1 (:123-135)
+    for (int k = 1; k <= a.jpk; ++k) {
+        const size_t o = c2 + (size_t)(k - 1) * a.jpij;
+        trdz[toff + o] = upstream_w(a, ptb, c2, k, mik) + zwz[o];
+        if (hm) {
+            double ux = 0.0, uy = 0.0;                                   // zwx(:,:,jpk) = zwy(:,:,jpk) = 0 (:115)
+            if (k <= a.jpk - 1) {
+                const double u = a.pun[o], v = a.pvn[o], t = ptb[o];
+                ux = 0.5 * ((u + fabs(u)) * t + (u - fabs(u)) * ptb[o + 1]);
+                uy = 0.5 * ((v + fabs(v)) * t + (v - fabs(v)) * ptb[o + a.jpi]);
+            }
+            trdx[toff + o] = ux + zwx[o];
+            trdy[toff + o] = uy + zwy[o];
+        }
+    }
+}
+
+void launch_fct_diag(const FctArgs &a, double *trdx, double *trdy, double *trdz, cudaStream_t s)
+{
+    const dim3 g((unsigned)((a.jpij + kThreads - 1) / kThreads), 1, (unsigned)a.kjpt);
+    k_fct_diag<<<g, kThreads, 0, s>>>(a, trdx, trdy, trdz);
+    note_launch();
+}
+
 void launch_fct_betas(const FctArgs &a, cudaStream_t s) { k_fct_betas<<<column_grid(a), kThreads, 0, s>>>(a); note_launch(); }
 void launch_fct_limit(const FctArgs &a, cudaStream_t s) { k_fct_limit<<<column_grid(a), kThreads, 0, s>>>(a); note_launch(); }
 void launch_fct_final(const FctArgs &a, cudaStream_t s) { k_fct_final<<<column_grid(a), kThreads, 0, s>>>(a); note_launch(); }

@@ -101,6 +101,25 @@ void launch_mus_inner(const MusArgs &a, cudaStream_t s);    // everything, excha
 void launch_mus_xind(int jpi, int jpj, int jpk, const double *rnfmsk, const double *rnfmsk_z, const double *tmask, double *xind,
                      cudaStream_t s);                        // :99-113
 
+// ---- tra_adv_cen                                                            traadv_cen.F90:46-204 ----
+struct CenArgs {
+    Region reg;
+    int jpi, jpj, jpk;
+    size_t jpij, n3;
+    const double *wmask, *e3t_n, *r1_e1e2t;
+    const int *mikt;
+    const double *pun, *pvn, *pwn, *ptn;
+    double *pta;
+    const double *ztu, *ztv, *ztw;         // exchanged masked gradients (order 4), compact interpolation (vertical order 4)
+    int kjpt, kn_cen_h, kn_cen_v, ln_linssh, ln_isfcav, nkchunk;
+};
+void launch_cen(const CenArgs &a, cudaStream_t s);
+
+// l_trd / l_hst / l_ptr hooks of tra_adv_fct (traadv_fct.F90:172-176, 299-303): total advective fluxes = upstream fluxes
+// (recomputed from ptb and the transports) + the limited anti-diffusive fluxes left in zwx, zwy, zwz by the
+// reference-structured schedule.  trdx / trdy on (1:jpim1, 1:jpjm1, 1:jpk), trdz on (1:jpi, 1:jpj, 1:jpk).
+void launch_fct_diag(const FctArgs &a, double *trdx, double *trdy, double *trdz, cudaStream_t s);
+
 // ---- tra_nxt_fix / tra_nxt_vvl / Euler swap                                 tranxt.F90:148-153, 190-380 ----
 struct NxtArgs {
     int jpi, jpj, jpk, kjpt;

@@ -128,6 +128,7 @@ struct nemo_fct_ctx {
     DevBuf<double> r1_e1e2u, r1_e1e2v, e3uvw_own[3], xind;
     const double *e3uvw[3] = {nullptr, nullptr, nullptr};
     bool have_mus_metrics = false, msc_ups = false;
+    double *diag[3] = {nullptr, nullptr, nullptr};                     // l_trd / l_hst / l_ptr hooks: ztrdx, ztrdy, ztrdz (device, borrowed)
     double r2dt = 0.0;                                                 // tracer time step of tra_adv (traadv.F90:95-97), persists across calls
     bool have_zl = false;
     int masks_from_t = 0;                                              // umask/vmask/wmask verified to be tmask products
@@ -158,11 +159,11 @@ typedef nemo_fct_ctx Ctx;
 // per-kernel timing with CUDA events on the launching stream
 // ------------------------------------------------------------------------------------------------------------
 enum ProfId { P_LAPLACIAN = 0, P_CPT, P_LOW_ANTIDIFF, P_BETAS, P_LIMIT, P_FINAL, P_LOW_INNER, P_NONOSC_FINAL, P_PACK, P_MOVE, P_UNPACK,
-              P_MUS_GRAD, P_MUS_HFLUX, P_MUS_TREND, P_MUS_INNER, P_NXT, P_COUNT };
+              P_MUS_GRAD, P_MUS_HFLUX, P_MUS_TREND, P_MUS_INNER, P_NXT, P_CEN, P_COUNT };
 static_assert(P_COUNT <= 24, "prof_ms / prof_calls too small");
 static const char *kProfName[P_COUNT] = {"fct_laplacian", "interp_4th_cpt", "fct_low_antidiff", "fct_betas", "fct_limit",
                                          "fct_final", "fct_low_antidiff_inner", "fct_nonosc_final", "lbc_pack", "lbc_move_nccl", "lbc_fill_unpack",
-                                         "mus_grad", "mus_hflux", "mus_trend", "mus_inner", "tra_nxt"};
+                                         "mus_grad", "mus_hflux", "mus_trend", "mus_inner", "tra_nxt", "tra_adv_cen"};
 struct ProfScope {
     nemo_fct_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int id;
     static cudaEvent_t get(nemo_fct_ctx *c) {
@@ -481,6 +482,11 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     // schedule 1 needs room for the fused inner region on every subdomain
     bool fused = g[0]->schedule >= 1;
     for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < 20 || g[m]->dom.jpj < 20) fused = false;
+    // the trend-diagnostic hooks need the limited fluxes in memory on the whole subdomain: reference pass structure
+    bool diag = false;
+    for (int m = 0; m < ng; ++m) if (g[m]->diag[0]) diag = true;
+    for (int m = 0; m < ng; ++m) if (diag && !g[m]->diag[0]) return fail("tra_adv_fct: trend diagnostics must be set on every subdomain of the communicator or on none");
+    if (diag) fused = false;
 
     if (!fused) {
         // ---- schedule 0: the reference pass structure, one kernel per pass group, exchanges X1..X4 -------------
@@ -496,6 +502,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         EACH(P_LIMIT, launch_fct_limit(fa[m], c->stream));
         if (exch({&Ctx::zwx, &Ctx::zwy}, "UV", {-1.0, -1.0})) return 1;                            // X4 (:426)
         EACH(P_FINAL, launch_fct_final(fa[m], c->stream));
+        if (diag) EACH(P_FINAL, launch_fct_diag(fa[m], c->diag[0], c->diag[1], c->diag[2], c->stream));   // :172-176, :299-303
         CU(cudaGetLastError());
         return 0;
     }
@@ -706,6 +713,56 @@ static int run_mus(std::vector<Ctx *> &g, const std::vector<MusCall> &args, doub
     CU(cudaEventRecord(g[0]->ev_t, side));
     to_main();
     CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_t, 0));
+#undef EACH
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// centred scheme over a set of in-process subdomains (traadv_cen.F90:46-204)
+// ------------------------------------------------------------------------------------------------------------
+struct CenCall { const double *pun, *pvn, *pwn, *ptn; double *pta; };
+
+static int run_cen(std::vector<Ctx *> &g, const std::vector<CenCall> &args, int kjpt, int h, int v)
+{
+    const int ng = (int)g.size();
+    if (kjpt < 1) return fail("tra_adv_cen: kjpt = %d", kjpt);
+    if (h != 2 && h != 4) return fail("tra_adv_cen: wrong value for nn_cen_h = %d", h);             // ctl_stop of :143
+    if (v != 2 && v != 4) return fail("tra_adv_cen: wrong value for nn_cen_v = %d", v);
+    std::vector<CenArgs> ca(ng);
+    std::vector<MusArgs> gr(ng);
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m];
+        if (!c->have_dom) return fail("tra_adv_cen: nemo_fct_set_domain_arrays has not been called");
+        if (!c->e3t[1]) return fail("tra_adv_cen: nemo_fct_set_e3t has not been called");
+        if (c->dom.jpk < 3) return fail("tra_adv_cen: jpk must be >= 3");
+        if (ensure_work(c, kjpt, 2, v)) return 1;
+        CenArgs &a = ca[m];
+        a.jpi = c->dom.jpi; a.jpj = c->dom.jpj; a.jpk = c->dom.jpk; a.jpij = c->jpij; a.n3 = c->n3;
+        a.wmask = c->wmask.p; a.e3t_n = c->e3t[1]; a.r1_e1e2t = c->r1_e1e2t.p; a.mikt = c->mikt.p;
+        a.pun = args[m].pun; a.pvn = args[m].pvn; a.pwn = args[m].pwn; a.ptn = args[m].ptn; a.pta = args[m].pta;
+        a.ztu = c->zwx.p; a.ztv = c->zwy.p; a.ztw = c->ztw.p;
+        a.kjpt = kjpt; a.kn_cen_h = h; a.kn_cen_v = v; a.ln_linssh = c->ln_linssh; a.ln_isfcav = c->ln_isfcav;
+        a.nkchunk = pick_nkchunk(c, kjpt);
+        a.reg = Region(); a.reg.add(2, a.jpi - 1, 2, a.jpj - 1);
+        MusArgs &q = gr[m];                                                // masked gradients ztu, ztv on (2:jpim1, 2:jpjm1)  :119-125
+        memset(&q, 0, sizeof q);
+        q.reg = a.reg; q.jpi = a.jpi; q.jpj = a.jpj; q.jpk = a.jpk; q.jpij = a.jpij; q.n3 = a.n3;
+        q.umask = c->umask.p; q.vmask = c->vmask.p; q.ptb = a.ptn; q.zwx = c->zwx.p; q.zwy = c->zwy.p; q.kjpt = kjpt; q.nkchunk = a.nkchunk;
+    }
+#define EACH(id, stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); ProfScope ps(c, id); stmt; }
+    if (h == 4) {
+        EACH(P_MUS_GRAD, launch_mus_grad(gr[m], c->stream));
+        LnkCall call; call.nfld = 2; call.nat = "UV"; call.sgn = {-1.0, -1.0}; call.has_pval = 0; call.pval = 0.0;
+        call.nlev = g[0]->dom.jpk * kjpt;
+        call.ptab.resize(ng);
+        for (int m = 0; m < ng; ++m) call.ptab[m] = {g[m]->zwx.p, g[m]->zwy.p};
+        if (lbc_exchange(g, call)) return 1;                                                       // :126
+    }
+    if (v == 4)
+        EACH(P_CPT, launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p, c->ln_isfcav,
+                                          c->cpt_zwt.p, c->cpt_simple.p, c->cpt_utab.p, ca[m].ptn, c->ztw.p, c->stream));
+    EACH(P_CEN, launch_cen(ca[m], c->stream));
 #undef EACH
     CU(cudaGetLastError());
     return 0;
@@ -1274,6 +1331,38 @@ int nemo_tra_adv_mus(nemo_fct_handle h, int kt, int kit000, const char *cdtype, 
     CU(cudaMemcpyAsync(pta, h->s_pta.p, n4 * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return 0;
+}
+
+int nemo_fct_set_trend_diag(nemo_fct_handle h, double *ztrdx, double *ztrdy, double *ztrdz)
+{
+    if (!h) return fail("NULL handle");
+    const int nn = (ztrdx ? 1 : 0) + (ztrdy ? 1 : 0) + (ztrdz ? 1 : 0);
+    if (nn != 0 && nn != 3) return fail("nemo_fct_set_trend_diag: give the three arrays or three NULLs");
+    h->diag[0] = ztrdx; h->diag[1] = ztrdy; h->diag[2] = ztrdz;
+    return 0;
+}
+
+int nemo_tra_adv_cen_dev(nemo_fct_handle h, int kt, int kit000, const char *cdtype, const double *pun, const double *pvn,
+                         const double *pwn, const double *ptn, double *pta, int kjpt, int kn_cen_h, int kn_cen_v)
+{
+    (void)kt; (void)kit000; (void)cdtype;
+    if (need_single(h, "nemo_tra_adv_cen_dev")) return 1;
+    if (!pun || !pvn || !pwn || !ptn || !pta) return fail("tra_adv_cen: NULL array");
+    std::vector<Ctx *> g = {h};
+    return run_cen(g, {CenCall{pun, pvn, pwn, ptn, pta}}, kjpt, kn_cen_h, kn_cen_v);
+}
+
+int nemo_group_tra_adv_cen_dev(nemo_fct_handle *hs, int n, int kt, int kit000, const char *cdtype,
+                               const double *const *pun, const double *const *pvn, const double *const *pwn,
+                               const double *const *ptn, double *const *pta, int kjpt, int kn_cen_h, int kn_cen_v)
+{
+    (void)kt; (void)kit000; (void)cdtype;
+    if (!hs || n < 1) return fail("bad arguments");
+    std::vector<Ctx *> g(hs, hs + n);
+    if ((int)g[0]->group.size() != n) return fail("nemo_group_tra_adv_cen_dev: call nemo_fct_comm_init_local first");
+    std::vector<CenCall> a(n);
+    for (int m = 0; m < n; ++m) a[m] = CenCall{pun[m], pvn[m], pwn[m], ptn[m], pta[m]};
+    return run_cen(g, a, kjpt, kn_cen_h, kn_cen_v);
 }
 
 int nemo_tra_nxt_dev(nemo_fct_handle h, int kt, int nit000, int l_euler, double rdt, const char *cdtype,

@@ -72,6 +72,25 @@ void oce_world_dom_msk(oce_world *w, const int **k_top, const int **k_bot, doubl
     oce_world_run(w, msk_thr, &a);
 }
 
+/* l_trd / l_hst / l_ptr hooks of tra_adv_fct: (jpi,jpj,jpk,kjpt) output arrays, or NULLs to switch them off */
+void oce_dom_set_diag(oce_dom *d, double *trdx, double *trdy, double *trdz)
+{
+    d->diag_trdx = trdx; d->diag_trdy = trdy; d->diag_trdz = trdz;
+}
+
+typedef struct { const double **pun, **pvn, **pwn, **ptn; double **pta; int kjpt, h, v; } cen_arg;
+static void cen_thr(oce_dom *d, void *p)
+{
+    cen_arg *a = (cen_arg *)p; int r = d->nproc;
+    tra_adv_cen(d, 1, 1, "TRA", a->pun[r], a->pvn[r], a->pwn[r], a->ptn[r], a->pta[r], a->kjpt, a->h, a->v);
+}
+void oce_world_tra_adv_cen(oce_world *w, const double **pun, const double **pvn, const double **pwn,
+                           const double **ptn, double **pta, int kjpt, int kn_cen_h, int kn_cen_v)
+{
+    cen_arg a = { pun, pvn, pwn, ptn, pta, kjpt, kn_cen_h, kn_cen_v };
+    oce_world_run(w, cen_thr, &a);
+}
+
 void oce_dom_set_mus_fields(oce_dom *d, const double *r1_e1e2u, const double *r1_e1e2v, const double *e3u_n,
                             const double *e3v_n, const double *e3w_n)
 {

@@ -10,6 +10,7 @@
  *   mpp_nfd (multi-rank north fold)         src/OCE/LBC/mpp_nfd_generic.h90:48-302 (+ lbc_nfd_nogather_generic.h90)
  *   mpp_init / mpp_basic_decomposition      src/OCE/LBC/mppini.F90:110-692, 695-798, 1180-1240
  *   dom_msk (masks)                         src/OCE/DOM/dommsk.F90:135-238
+ *   tra_adv_cen (centred 2nd / 4th order)   src/OCE/TRA/traadv_cen.F90:46-204
  *   tra_adv_mus (MUSCL)                     src/OCE/TRA/traadv_mus.F90:55-273
  *   tra_nxt / tra_nxt_fix / tra_nxt_vvl     src/OCE/TRA/tranxt.F90:65-380 (+ trc_nxt swap, src/TOP/TRP/trcnxt.F90:56-183)
  *   SIGN / DDPDD / glob_sum                 src/OCE/lib_fortran.F90:300-351, lib_fortran_generic.h90:32-65
@@ -71,6 +72,9 @@ typedef struct oce_dom {
     /* extra module arrays read by tra_adv_mus (dom_oce.F90:118, 132-136); NULL until set */
     const double *r1_e1e2u, *r1_e1e2v;                 /* (jpi,jpj)     */
     const double *e3u_n, *e3v_n, *e3w_n;               /* (jpi,jpj,jpk) */
+    /* l_trd / l_hst / l_ptr hooks of tra_adv_fct (traadv_fct.F90:104-112, 172-176, 299-316): total advective fluxes
+     * ztrdx, ztrdy (= zptry), ztrdz per tracer, (jpi,jpj,jpk,kjpt); NULL = hooks off */
+    double *diag_trdx, *diag_trdy, *diag_trdz;
 } oce_dom;
 
 /* Module variables read by tra_nxt_vvl (tranxt.F90:262-343): sbc_oce, sbcrnf, sbcisf, traqsr, phycst.
@@ -129,6 +133,11 @@ void nonosc(oce_dom *d, const double *pbef, double *paa, double *pbb, double *pc
             double p2dt, int jn);
 void interp_4th_cpt(const oce_dom *d, const double *pt_in, double *pt_out);
 void oracle_poison_workspace(int on);  /* fill automatic arrays with NaN before use (catches undefined reads) */
+int  oracle_poison_enabled(void);
+
+/* ---- traadv_cen.c ---- */
+void tra_adv_cen(oce_dom *d, int kt, int kit000, const char *cdtype, const double *pun, const double *pvn,
+                 const double *pwn, const double *ptn, double *pta, int kjpt, int kn_cen_h, int kn_cen_v);  /* traadv_cen.F90:46-204 */
 
 /* ---- traadv_mus.c ---- */
 void tra_adv_mus_xind(const oce_dom *d, int ld_msc_ups, const double *rnfmsk, const double *rnfmsk_z, double *xind);

@@ -57,6 +57,8 @@ def lib():
         L.sign_nosignedzero.argtypes = [C.c_double, C.c_double]
         L.tra_adv_transports.argtypes = [C.c_void_p] * 11
         L.oce_dom_set_mus_fields.argtypes = [C.c_void_p] * 6
+        L.oce_dom_set_diag.argtypes = [C.c_void_p] * 4
+        L.oce_world_tra_adv_cen.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5 + [C.c_int] * 3
         L.tra_adv_mus_xind.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oce_world_tra_adv_mus.argtypes = [C.c_void_p, C.c_double] + [C.POINTER(C.c_void_p)] * 5 + [C.c_int, C.POINTER(C.c_void_p)]
         L.oce_world_tra_nxt.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_char_p]
@@ -118,6 +120,11 @@ class Dom:
         assert mikt.dtype == np.int32 and mbkt.dtype == np.int32
         self._keep["fields"] = arrs
         lib().oce_dom_set_fields(self.h, *[_ptr(a) for a in arrs], int(ln_linssh), int(ln_isfcav))
+
+    def set_diag(self, trdx=None, trdy=None, trdz=None):
+        """l_trd / l_hst / l_ptr hooks of tra_adv_fct: (kjpt,jpk,jpj,jpi) arrays receiving ztrdx, ztrdy (= zptry), ztrdz"""
+        self._keep["diag"] = (trdx, trdy, trdz)
+        lib().oce_dom_set_diag(self.h, *[None if a is None else _ptr(a) for a in (trdx, trdy, trdz)])
 
     def set_mus_fields(self, r1_e1e2u, r1_e1e2v, e3u_n, e3v_n, e3w_n):
         arrs = [r1_e1e2u, r1_e1e2v, e3u_n, e3v_n, e3w_n]
@@ -187,6 +194,11 @@ class World:
         L = lib()
         L.oce_world_tra_adv_fct(self.h, p2dt, _ptr_table(pun), _ptr_table(pvn), _ptr_table(pwn), _ptr_table(ptb),
                                 _ptr_table(ptn), _ptr_table(pta), kjpt, kn_fct_h, kn_fct_v)
+
+    def tra_adv_cen(self, pun, pvn, pwn, ptn, pta, kjpt, kn_cen_h, kn_cen_v):
+        """tra_adv_cen on every subdomain; pta updated in place."""
+        lib().oce_world_tra_adv_cen(self.h, _ptr_table(pun), _ptr_table(pvn), _ptr_table(pwn), _ptr_table(ptn),
+                                    _ptr_table(pta), kjpt, kn_cen_h, kn_cen_v)
 
     def tra_adv_mus(self, p2dt, pun, pvn, pwn, ptb, pta, kjpt, xind):
         """tra_adv_mus on every subdomain; pta updated in place; xind: list over ranks."""

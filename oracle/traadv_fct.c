@@ -4,8 +4,9 @@
  * interp_4th_cpt :517-616).  Same loop bounds, same operation order, same automatic work arrays living
  * across the tracer loop.  PARITY UNPINNED by reference golden vectors (none exist); see nemo_oracle.h.
  *
- * Out of first scope (as in the reference these are optional hooks, off by default): l_trd / l_hst / l_ptr
- * diagnostics (:96-112, :172-176, :299-316) and kn_fct_h = 41 (:223-250, "coding attempt, need to be tested").
+ * The l_trd / l_hst / l_ptr hooks (:96-112, :172-176, :299-316) are restated up to the point where the reference hands
+ * ztrdx / ztrdy / ztrdz (zptry = ztrdy) to trd_tra, dia_ar5_hst and dia_ptr_hst: d->diag_trd* receive those arrays.
+ * Not restated: kn_fct_h = 41 (:223-250, "coding attempt, need to be tested").
  */
 #include "nemo_oracle.h"
 #include <math.h>
@@ -15,6 +16,7 @@
 
 static int g_poison = 0;
 void oracle_poison_workspace(int on) { g_poison = on; }
+int  oracle_poison_enabled(void) { return g_poison; }
 
 /* automatic array (jpi,jpj,jpk): undefined on entry in Fortran; optionally NaN-poisoned here */
 static double *auto3d(const oce_dom *d)
@@ -113,6 +115,13 @@ void tra_adv_fct(oce_dom *d, int kt, int kit000, const char *cdtype, double p2dt
                                           / e3t_a[I3(ji, jj, jk)] * tmask[I3(ji, jj, jk)];
                 }
 
+        /* trend diagnostics / poleward transports: contribution of the upstream fluxes  (:172-176, l_trd .OR. l_hst, l_ptr) */
+        if (d->diag_trdx) {
+            double *tx = d->diag_trdx + (size_t)(jn - 1) * n3, *ty = d->diag_trdy + (size_t)(jn - 1) * n3;
+            double *tz = d->diag_trdz + (size_t)(jn - 1) * n3;
+            for (size_t n = 0; n < n3; ++n) { tx[n] = zwx[n]; ty[n] = zwy[n]; tz[n] = zwz[n]; }
+        }
+
         /* anti-diffusive flux : high order minus low order  (:180-251) */
         switch (kn_fct_h) {
         case 2:                                                                 /* :182-190 */
@@ -209,6 +218,12 @@ void tra_adv_fct(oce_dom *d, int kt, int kit000, const char *cdtype, double p2dt
                            + zwy[I3(ji, jj, jk)] - zwy[I3(ji, jj - 1, jk)]
                            + zwz[I3(ji, jj, jk)] - zwz[I3(ji, jj, jk + 1)])
                           * r1_e1e2t[I2(ji, jj)] / e3t_n[I3(ji, jj, jk)];
+        /* add the (limited) anti-diffusive fluxes to the upstream ones  (:299-303, :313) */
+        if (d->diag_trdx) {
+            double *tx = d->diag_trdx + (size_t)(jn - 1) * n3, *ty = d->diag_trdy + (size_t)(jn - 1) * n3;
+            double *tz = d->diag_trdz + (size_t)(jn - 1) * n3;
+            for (size_t n = 0; n < n3; ++n) { tx[n] = tx[n] + zwx[n]; ty[n] = ty[n] + zwy[n]; tz[n] = tz[n] + zwz[n]; }
+        }
     }
 
     free(zwi); free(zwx); free(zwy); free(zwz);

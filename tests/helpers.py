@@ -256,3 +256,47 @@ def device_mus(N, gf, mx, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, ln_lins
     for c in ctxs:
         c.close()
     return glob, out
+
+
+# ---- tra_adv_cen helpers ---------------------------------------------------------------------------------------------
+def oracle_cen(O, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_linssh=False, ln_isfcav=False, poison=False):
+    w = O.World(jpiglo, jpjglo, jpk, jperio, jpni, jpnj)
+    loc = {k: w.scatter(gf[k]) for k in DOM_KEYS + ("pun", "pvn", "pwn", "ptn", "pta")}
+    for r, d in enumerate(w.doms):
+        d.set_fields(*[loc[k][r] for k in DOM_KEYS], ln_linssh=ln_linssh, ln_isfcav=ln_isfcav)
+    O.lib().oracle_poison_workspace(int(poison))
+    w.tra_adv_cen(loc["pun"], loc["pvn"], loc["pwn"], loc["ptn"], loc["pta"], kjpt, h, v)
+    O.lib().oracle_poison_workspace(0)
+    glob = w.gather(loc["pta"], gf["pta"].copy())
+    w.close()
+    return glob, loc["pta"]
+
+
+def device_cen(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_linssh=False, ln_isfcav=False):
+    from oracle import oracle as O
+    w = O.World(jpiglo, jpjglo, jpk, jperio, jpni, jpnj)
+    loc = {k: w.scatter(gf[k]) for k in DOM_KEYS + ("pun", "pvn", "pwn", "ptn", "pta")}
+    n = jpni * jpnj
+    dev = torch.device("cuda:0")
+    if n == 1:
+        ctxs = [N.FctContext(N.mpp_init(jpiglo, jpjglo, jpk, jperio, 1, 1, 1), 0)]
+    else:
+        grp = N.LocalGroup(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, 0)
+        ctxs = grp.ctx
+    for r, c in enumerate(ctxs):
+        c.set_domain_arrays(loc["tmask"][r], loc["umask"][r], loc["vmask"][r], loc["wmask"][r], loc["e1e2t"][r],
+                            loc["r1_e1e2t"][r], loc["mikt"][r], loc["mbkt"][r], ln_linssh, ln_isfcav)
+        c.set_e3t(loc["e3t_b"][r], loc["e3t_n"][r], loc["e3t_a"][r])
+    t = {k: [torch.from_numpy(a).to(dev) for a in loc[k]] for k in ("pun", "pvn", "pwn", "ptn", "pta")}
+    if n == 1:
+        ctxs[0].tra_adv_cen(1, 1, "TRA", t["pun"][0], t["pvn"][0], t["pwn"][0], t["ptn"][0], t["pta"][0], kjpt, h, v)
+        ctxs[0].synchronize()
+    else:
+        grp.tra_adv_cen(1, 1, "TRA", t["pun"], t["pvn"], t["pwn"], t["ptn"], t["pta"], kjpt, h, v)
+        grp.synchronize()
+    out = [a.cpu().numpy() for a in t["pta"]]
+    glob = w.gather(out, gf["pta"].copy())
+    w.close()
+    for c in ctxs:
+        c.close()
+    return glob, out
