@@ -35,6 +35,7 @@ MODULE traadv_fct
    PUBLIC   tra_adv_fct        ! called by traadv.F90 and trcadv.F90
    PUBLIC   interp_4th_cpt     ! called by traadv_cen.F90
    PUBLIC   tra_adv_fct_gpu_init   ! called once from nemo_init, after dom_init (nemogcm.F90:417)
+   PUBLIC   nhandle, gpu_stop      ! shared with the other device-path modules (traadv_mus_gpu.F90)
 
    !                                     ! struct nemo_fct_domain (include/nemo_fct.h), same field order
    TYPE, BIND(C) ::   nemo_fct_domain
