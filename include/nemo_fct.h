@@ -15,6 +15,10 @@
  *   interp_4th_cpt        src/OCE/TRA/traadv_fct.F90:517-527      ->  nemo_interp_4th_cpt[_dev]
  *   tra_adv transports    src/OCE/TRA/traadv.F90:100-124          ->  nemo_tra_adv_transports_dev
  *   tra_adv / trc_adv     src/OCE/TRA/traadv.F90:77, src/TOP/TRP/trcadv.F90:70 -> nemo_tra_adv_dev / nemo_trc_adv_dev
+ *   tra_adv_mus           src/OCE/TRA/traadv_mus.F90:55-79        ->  nemo_tra_adv_mus[_dev] (+ nemo_fct_set_mus_*, nemo_fct_set_e3uvw)
+ *   tra_adv_cen           src/OCE/TRA/traadv_cen.F90:46-77        ->  nemo_tra_adv_cen_dev
+ *   tra_nxt / trc_nxt     src/OCE/TRA/tranxt.F90:65-380, src/TOP/TRP/trcnxt.F90:56-183 -> nemo_tra_nxt_dev
+ *   l_trd/l_hst/l_ptr     src/OCE/TRA/traadv_fct.F90:96-112,172-176,299-316 -> nemo_fct_set_trend_diag
  *   lbc_lnk_multi         src/OCE/LBC/lbc_lnk_multi_generic.h90:16-29 -> nemo_lbc_lnk_multi[_dev]
  *   mynode / MPI_Init     src/OCE/LBC/lib_mpp.F90:197-331         ->  nemo_fct_comm_unique_id / nemo_fct_comm_init
  *   ctl_stop              src/OCE/LBC/lib_mpp.F90:1868-1907       ->  non-zero return + nemo_fct_last_error
