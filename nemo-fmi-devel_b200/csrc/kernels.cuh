@@ -95,7 +95,7 @@ struct MusArgs {
     int kjpt, ln_linssh, ln_isfcav, nkchunk;
 };
 void launch_mus_grad(const MusArgs &a, cudaStream_t s);     // first guess of the slopes         :134-141
-void launch_mus_hflux(const MusArgs &a, cudaStream_t s);    // slopes, limitation, fluxes        :145-191
+void launch_mus_hflux(const MusArgs &a, cudaStream_t s, bool from_ptb = false);   // slopes, limitation, fluxes :145-191
 void launch_mus_trend(const MusArgs &a, cudaStream_t s);    // horizontal trend + vertical part  :194-272
 void launch_mus_inner(const MusArgs &a, cudaStream_t s);    // everything, exchange-free columns
 void launch_mus_xind(int jpi, int jpj, int jpk, const double *rnfmsk, const double *rnfmsk_z, const double *tmask, double *xind,

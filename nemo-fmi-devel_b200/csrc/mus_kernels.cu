@@ -5,6 +5,8 @@
 // then vertically, with four automatic work arrays) become
 //   * reference-structured path: k_mus_grad -> lbc_lnk(U,-1 / V,-1) -> k_mus_hflux -> lbc_lnk -> k_mus_trend,
 //     three column kernels with slopes and limited slopes kept in registers, all tracers batched in one launch;
+//   * default path: on the columns whose slopes need no exchanged value k_mus_hflux forms the first-guess differences
+//     in place from ptb (no zwx / zwy arrays, first exchange only for the one-cell frame, on a side stream);
 //   * fused inner path: k_mus_inner computes the whole trend of the columns whose 5-point-wide stencil touches no halo
 //     cell straight from ptb (nothing but pta is written, no exchange is needed there); the reference-structured
 //     kernels then only run on the two-cell frame around it.
@@ -91,7 +93,10 @@ __global__ void __launch_bounds__(kThreads) k_mus_grad(const MusArgs a)
 // slopes, limitation and MUSCL horizontal fluxes on a.reg (interior columns)        traadv_mus.F90:145-191
 // reads the exchanged first-guess differences zwx, zwy; writes the fluxes to fx, fy
 // ------------------------------------------------------------------------------------------------------------
-template <bool XI>
+// FROM_T: the first-guess differences are formed in place from ptb (same expression as k_mus_grad) instead of being read
+// from the exchanged zwx / zwy arrays -- valid for the columns whose ji-1..ji+1 / jj-1..jj+1 differences are not halo or
+// fold-rewritten cells, i.e. (3:jpi-2, 3:jpj-2) minus one more row under a north fold.
+template <bool XI, bool FROM_T>
 __global__ void __launch_bounds__(kThreads) k_mus_hflux(const MusArgs a)
 {
     int ji, jj, ka, kb;
@@ -105,11 +110,18 @@ __global__ void __launch_bounds__(kThreads) k_mus_hflux(const MusArgs a)
     const double r1u = a.r1_e1e2u[c2], r1v = a.r1_e1e2v[c2], p2dt = a.p2dt;
     for (int k = ka; k <= kb; ++k) {
         const size_t o = c2 + (size_t)(k - 1) * a.jpij;
-        const double gx_w = zwx[o - 1], gx_c = zwx[o], gx_e = zwx[o + 1];
-        const double gy_s = zwy[o - jpi], gy_c = zwy[o], gy_n = zwy[o + jpi];
+        const double t_c = ptb[o], t_e = ptb[o + 1], t_n = ptb[o + jpi];
+        double gx_w, gx_c, gx_e, gy_s, gy_c, gy_n;
+        if (FROM_T) {
+            const double t_w = ptb[o - 1], t_ee = ptb[o + 2], t_s = ptb[o - jpi], t_nn = ptb[o + 2 * jpi];
+            gx_w = a.umask[o - 1] * (t_c - t_w); gx_c = a.umask[o] * (t_e - t_c); gx_e = a.umask[o + 1] * (t_ee - t_e);
+            gy_s = a.vmask[o - jpi] * (t_c - t_s); gy_c = a.vmask[o] * (t_n - t_c); gy_n = a.vmask[o + jpi] * (t_nn - t_n);
+        } else {
+            gx_w = zwx[o - 1]; gx_c = zwx[o]; gx_e = zwx[o + 1];
+            gy_s = zwy[o - jpi]; gy_c = zwy[o]; gy_n = zwy[o + jpi];
+        }
         const double sx_c = mus_slope(gx_c, gx_w), sx_e = mus_slope(gx_e, gx_c);
         const double sy_c = mus_slope(gy_c, gy_s), sy_n = mus_slope(gy_n, gy_c);
-        const double t_c = ptb[o], t_e = ptb[o + 1], t_n = ptb[o + jpi];
         const double xi = XI ? a.xind[o] : 1.0;
         const double u = a.pun[o], v = a.pvn[o];
         fx[o] = mus_flux<false>(u, 0.5 * u * p2dt * r1u / a.e3u_n[o], t_e, sx_e, t_c, sx_c, xi, XI);
@@ -285,11 +297,16 @@ void launch_mus_grad(const MusArgs &a, cudaStream_t s)
     if (a.reg.ncol() <= 0) return;
     k_mus_grad<<<column_grid(a), kThreads, 0, s>>>(a); note_launch();
 }
-void launch_mus_hflux(const MusArgs &a, cudaStream_t s)
+void launch_mus_hflux(const MusArgs &a, cudaStream_t s, bool from_ptb)
 {
     if (a.reg.ncol() <= 0) return;
-    if (a.xind) k_mus_hflux<true><<<column_grid(a), kThreads, 0, s>>>(a);
-    else        k_mus_hflux<false><<<column_grid(a), kThreads, 0, s>>>(a);
+    if (from_ptb) {
+        if (a.xind) k_mus_hflux<true, true><<<column_grid(a), kThreads, 0, s>>>(a);
+        else        k_mus_hflux<false, true><<<column_grid(a), kThreads, 0, s>>>(a);
+    } else {
+        if (a.xind) k_mus_hflux<true, false><<<column_grid(a), kThreads, 0, s>>>(a);
+        else        k_mus_hflux<false, false><<<column_grid(a), kThreads, 0, s>>>(a);
+    }
     note_launch();
 }
 void launch_mus_trend(const MusArgs &a, cudaStream_t s)

@@ -649,14 +649,59 @@ static int run_mus(std::vector<Ctx *> &g, const std::vector<MusCall> &args, doub
         return lbc_exchange(g, call);
     };
 #define EACH(id, stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); ProfScope ps(c, id); stmt; }
-    // schedule 0: reference structure; 1: fused inner kernel + frame; >= 2 (default): fused only where there is a real
-    // neighbour to wait for -- the inner kernel recomputes the west/south fluxes of every column (measured on B200:
-    // 10.4 ms against 9.2 ms for the three reference-structured kernels at 1442x1207x75, 2 tracers), which only pays
-    // when it hides the two exchanges.
-    bool fused = g[0]->schedule == 1 || (g[0]->schedule >= 2 && (g[0]->nccl_nranks > 1 || ng > 1));
-    for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < 20 || g[m]->dom.jpj < 20) fused = false;
+    // schedule 0: reference structure (three kernels on the whole interior, two exchanges on the main stream);
+    //          1: fully fused inner kernel + two-cell frame (no array but pta is written on the inner columns, but the
+    //             west / south fluxes of every column are computed twice: 10.4 ms against 9.2 ms for schedule 0 at
+    //             1442x1207x75, 2 tracers -- kept for study);
+    //       >= 2: (default) first-guess differences formed in place from ptb on the columns that need no exchanged value
+    //             (no k_mus_grad sweep, no zwx / zwy round trip: -14 GB of DRAM traffic per step); the one-cell frame goes
+    //             through k_mus_grad + the first exchange on the side stream, hidden behind the inner flux kernel.
+    bool fused = g[0]->schedule == 1;
+    bool semi = g[0]->schedule >= 2;
+    for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < 20 || g[m]->dom.jpj < 20) fused = semi = false;
 
     std::vector<MusArgs> grad(ma), hfl(ma), trd(ma), inner(ma);
+    if (semi) {
+        for (int m = 0; m < ng; ++m) {
+            Ctx *c = g[m];
+            const int jpi = c->dom.jpi, jpj = c->dom.jpj, f = c->dom.npolj != 0 ? 1 : 0;
+            try { CUTHROW(cudaSetDevice(c->device)); ensure_side(c); }
+            catch (const std::exception &e) { return fail("tra_adv_mus: side stream: %s", e.what()); }
+            auto band = [&](int i_lo, int wW, int wE, int j_lo, int wS, int wN) {
+                Region r;
+                r.add(i_lo, wW, j_lo, jpj - 1);
+                r.add(jpi - wE, jpi - 1, j_lo, jpj - 1);
+                r.add(wW + 1, jpi - wE - 1, j_lo, wS);
+                r.add(wW + 1, jpi - wE - 1, jpj - wN, jpj - 1);
+                return r;
+            };
+            inner[m].reg.add(3, jpi - 2, 3, jpj - 2 - f);                   // fluxes straight from ptb
+            hfl[m].reg = band(2, 2, 1, 2, 2, 1 + f);                        // the rest of the interior: exchanged differences
+            grad[m].reg = band(1, 3, 2, 1, 3, 3 + f);                       // what those columns and the first exchange read
+            trd[m].reg.add(2, jpi - 1, 2, jpj - 1);
+            for (MusArgs *x : {&grad[m], &hfl[m]}) x->nkchunk = std::max(1, std::min(8, (c->dom.jpk - 1) / 8));
+        }
+        cudaStream_t side = g[0]->side_stream;
+        std::vector<cudaStream_t> mainst(ng);
+        for (int m = 0; m < ng; ++m) mainst[m] = g[m]->stream;
+        auto to_side = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = side; };
+        auto to_main = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = mainst[m]; };
+        struct Restore { std::function<void()> f; ~Restore() { f(); } } restore{to_main};
+        CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
+        EACH(P_MUS_HFLUX, launch_mus_hflux(inner[m], c->stream, true));
+        to_side();
+        CU(cudaStreamWaitEvent(side, g[0]->ev_a, 0));
+        EACH(P_MUS_GRAD, launch_mus_grad(grad[m], c->stream));
+        if (exch({&Ctx::zwx, &Ctx::zwy})) return 1;                         // :143, frame only
+        EACH(P_MUS_GRAD, launch_mus_hflux(hfl[m], c->stream, false));
+        CU(cudaEventRecord(g[0]->ev_t, side));
+        to_main();
+        CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_t, 0));
+        if (exch({&Ctx::zwi, &Ctx::zwz})) return 1;                         // :192
+        EACH(P_MUS_TREND, launch_mus_trend(trd[m], c->stream));
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (!fused) {
         for (int m = 0; m < ng; ++m) {
             const int jpi = ma[m].jpi, jpj = ma[m].jpj;

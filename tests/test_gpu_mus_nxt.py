@@ -21,7 +21,7 @@ def _mus_case(jpiglo, jpjglo, jperio, kjpt, seed, **kw):
 
 
 @pytest.mark.parametrize("jperio", [0, 1, 2, 3, 4, 5, 6, 7])
-@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("schedule", [0, 1, 2])
 def test_mus_parity_all_boundaries(jperio, schedule):
     """single subdomain, every lateral boundary type, both schedules: identical to the oracle, whole array
     (interior = result, halos and level jpk = untouched input)."""
@@ -35,7 +35,7 @@ def test_mus_parity_all_boundaries(jperio, schedule):
 
 @pytest.mark.parametrize("ln_linssh,ln_isfcav,ld_msc_ups", [(True, False, False), (True, True, False), (False, False, True),
                                                             (True, True, True)])
-@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("schedule", [0, 1, 2])
 def test_mus_parity_options(ln_linssh, ln_isfcav, ld_msc_ups, schedule):
     jpiglo, jpjglo, jperio, kjpt = 40, 36, 4, 2
     gf, mx = _mus_case(jpiglo, jpjglo, jperio, kjpt, seed=7, ln_linssh=ln_linssh, ln_isfcav=ln_isfcav)
@@ -47,7 +47,7 @@ def test_mus_parity_options(ln_linssh, ln_isfcav, ld_msc_ups, schedule):
 
 
 @pytest.mark.parametrize("jperio,jpni,jpnj", [(0, 2, 2), (1, 3, 1), (4, 2, 2), (6, 2, 2), (4, 1, 2)])
-@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("schedule", [0, 1, 2])
 def test_mus_decomposed_in_process(jperio, jpni, jpnj, schedule):
     """jpni x jpnj subdomains on one GPU: every rank's local array equals the oracle's rank (halo exchanges through the
     compiled plans), and the assembled interior equals the mono-domain oracle."""
