@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kThreads) k_mus_hflux(const MusArgs a)
     const int jpi = a.jpi;
     const size_t c2 = (size_t)(jj - 1) * jpi + (ji - 1);
     const double r1u = a.r1_e1e2u[c2], r1v = a.r1_e1e2v[c2], p2dt = a.p2dt;
+#pragma unroll 2
     for (int k = ka; k <= kb; ++k) {
         const size_t o = c2 + (size_t)(k - 1) * a.jpij;
         const double t_c = ptb[o], t_e = ptb[o + 1], t_n = ptb[o + jpi];
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(kThreads) k_mus_trend(const MusArgs a)
         const double s_m = col.slope(ka - 1, g_m, g_c);
         f_top = col.face(ka, t_m, s_m, t_c, s_c);
     }
+#pragma unroll 2
     for (int k = ka; k <= kb; ++k) {
         const size_t o = c2 + (size_t)(k - 1) * jpij;
         const double t_pp = col.t(k + 2);
