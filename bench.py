@@ -320,6 +320,8 @@ def main():
         "fct_nonosc_final": a3 * ((6 + 1) * kjpt) + a3 * 2,                            # r ptb zwi zwx zwy zwz pta; w pta; r tmask e3t_n
         "mus_inner": a3 * (3 * kjpt) + a3 * 11,                                        # r ptb pta; w pta; r pun pvn pwn e3u e3v e3w e3t tmask umask vmask wmask
         "tra_nxt": a3 * (5 * kjpt) + a3 * 3,
+        "mus_hflux": a3 * (3 * kjpt) + a3 * 6,                                         # r ptb; w fx fy; r pun pvn e3u e3v umask vmask
+        "mus_trend": a3 * (5 * kjpt) + a3 * 5,                                         # r fx fy pta ptb; w pta; r tmask pwn e3w wmask e3t
     }
     if not fused:
         kbytes.update({
@@ -347,7 +349,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as tf:
-            ent = json.load(tf).get("%s:schedule%d" % (args.workload, sched))
+            key = "%s:schedule%d" % (args.workload, sched) if args.scheme == "fct" else "%s:%s:schedule%d" % (args.workload, args.scheme, sched)
+            ent = json.load(tf).get(key)
         if ent and world == 1:
             traffic = int(sum(ent["kernels"].values()))
             for name in kern:
