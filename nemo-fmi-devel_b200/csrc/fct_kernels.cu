@@ -989,6 +989,20 @@ inline dim3 column_grid(const FctArgs &a)
 
 }  // namespace
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so it
+// is remembered per device: contexts of several GPUs may live in one process.
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+static void allow_dynamic_smem(Kernel kernel, size_t smem, bool (&done)[kMaxDevices])
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool known = dev >= 0 && dev < kMaxDevices;
+    if (known && done[dev]) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (known) done[dev] = true;
+}
+
 void launch_fct_laplacian(const FctArgs &a, cudaStream_t s)
 {
     k_fct_laplacian<<<column_grid(a), kThreads, 0, s>>>(a); note_launch();
@@ -1060,7 +1074,7 @@ bool launch_fct_low_antidiff_tma(const FctArgs &a, cudaStream_t s)
     const size_t smem = (size_t)TSTAGES * kTileStageBytes + 64;
     const dim3 g((unsigned)(((rc.i1 - rc.i0 + 1 + TTX - 1) / TTX) * a.kjpt), (unsigned)((rc.j1 - rc.j0 + 1 + TTY - 1) / TTY), (unsigned)a.nkchunk);
     const bool ft = a.masks_from_t != 0;
-#define LAT(H, V, F) do { static bool set = false; if (!set) { cudaFuncSetAttribute(k_fct_low_antidiff_tma<H, V, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; } \
+#define LAT(H, V, F) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_low_antidiff_tma<H, V, F>, smem, done); \
                           k_fct_low_antidiff_tma<H, V, F><<<g, TTX * TTY, smem, s>>>(a, tm, rc); } while (0)
 #define LAT2(H, V) do { if (ft) LAT(H, V, true); else LAT(H, V, false); } while (0)
     if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LAT2(2, 2);
@@ -1084,9 +1098,9 @@ bool launch_fct_nonosc_final_tma(const FctArgs &a, cudaStream_t s)
                     make_tile_map(&tm.m[NQ_TM], a.tmask, a.jpi, a.jpj, n3, NX, NY) && make_tile_map(&tm.m[NQ_PCC], a.zwz, a.jpi, a.jpj, n4, NX, NY) &&
                     make_tile_map(&tm.m[NQ_PAA], a.zwx, a.jpi, a.jpj, n4, NX, NY) && make_tile_map(&tm.m[NQ_PBB], a.zwy, a.jpi, a.jpj, n4, NX, NY);
     if (!ok) return false;
-    static bool attr_set = false;
+    static bool done[kMaxDevices] = {};
     const size_t smem = (size_t)2 * kNqStageBytes + 6 * kNqBoxBytes + 64;
-    if (!attr_set) { cudaFuncSetAttribute(k_fct_nonosc_final_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    allow_dynamic_smem(k_fct_nonosc_final_tma, smem, done);
     const int ox = NX - 2 * NHALO, oy = NY - 2 * NHALO;
     const dim3 g((unsigned)((ni + ox - 1) / ox), (unsigned)((nj + oy - 1) / oy), (unsigned)a.kjpt);
     k_fct_nonosc_final_tma<<<g, NX * NY, smem, s>>>(a, tm);
@@ -1096,9 +1110,9 @@ bool launch_fct_nonosc_final_tma(const FctArgs &a, cudaStream_t s)
 
 void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s)
 {
-    static bool attr_set = false;
+    static bool done[kMaxDevices] = {};
     const size_t smem = (size_t)(3 * 4 + 2 * 2) * NY * NX * sizeof(double);
-    if (!attr_set) { cudaFuncSetAttribute(k_fct_nonosc_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    allow_dynamic_smem(k_fct_nonosc_final, smem, done);
     const int ox = NX - 2 * NHALO, oy = NY - 2 * NHALO;
     const int ni = a.out.i1 - a.out.i0 + 1, nj = a.out.j1 - a.out.j0 + 1;
     if (ni <= 0 || nj <= 0) return;

@@ -559,7 +559,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     // on the main stream (what matters at N > 1, where each exchange costs an NCCL round trip).
     // Without a real neighbour (single subdomain) the exchanges are local copies and the split only costs (thin bands
     // coalesce badly): keep K1 whole there.
-    bool split = g[0]->nccl_nranks > 1 || ng > 1 || getenv("NEMO_FCT_FORCE_SPLIT") != nullptr;
+    bool split = g[0]->nccl_nranks > 1 || ng > 1;
     std::vector<FctArgs> k1b(k1), k1c(k1);
     for (int m = 0; m < ng; ++m) {
         const Rect r1 = k1[m].reg.r[0];
