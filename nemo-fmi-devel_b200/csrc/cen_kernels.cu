@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kThreads) k_cen(const CenArgs a)
 
 }  // namespace
 
+#ifndef NEMO_EMU_KERNELS_ONLY          // the launcher (CUDA launch syntax) is left out of the host emulation build of tests/emu
 void launch_cen(const CenArgs &a, cudaStream_t s)
 {
     if (a.reg.ncol() <= 0) return;
@@ -99,5 +100,6 @@ void launch_cen(const CenArgs &a, cudaStream_t s)
     else                                         k_cen<4, 4><<<g, kThreads, 0, s>>>(a);
     note_launch();
 }
+#endif  // NEMO_EMU_KERNELS_ONLY
 
 }  // namespace nemo

@@ -287,13 +287,16 @@ __global__ void __launch_bounds__(kThreads) k_mus_xind(int jpi, int jpj, int jpk
     }
 }
 
+#ifndef NEMO_EMU_KERNELS_ONLY          // launchers (CUDA launch syntax) are left out of the host emulation build of tests/emu
 inline dim3 column_grid(const MusArgs &a)
 {
     return dim3((unsigned)((a.reg.ncol() + kThreads - 1) / kThreads), (unsigned)a.nkchunk, (unsigned)a.kjpt);
 }
+#endif
 
 }  // namespace
 
+#ifndef NEMO_EMU_KERNELS_ONLY
 void launch_mus_grad(const MusArgs &a, cudaStream_t s)
 {
     if (a.reg.ncol() <= 0) return;
@@ -332,5 +335,6 @@ void launch_mus_xind(int jpi, int jpj, int jpk, const double *rnfmsk, const doub
     k_mus_xind<<<(unsigned)((jpij + kThreads - 1) / kThreads), kThreads, 0, s>>>(jpi, jpj, jpk, rnfmsk, rnfmsk_z, tmask, xind);
     note_launch();
 }
+#endif  // NEMO_EMU_KERNELS_ONLY
 
 }  // namespace nemo

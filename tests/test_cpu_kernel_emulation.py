@@ -1,0 +1,119 @@
+"""The MUSCL and centred-scheme column kernels, compiled for the HOST from the very same source (tests/emu), against the
+oracle -- bit for bit.  Covers what the GPU suite does not reach at its small jpk: the jk loop split in chunks across
+blockIdx.y (chunk-start recomputation of the vertical slopes / fluxes), which production sizes (jpk = 75) use."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import helpers as H
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+JPK = 19
+
+
+@pytest.fixture(scope="module")
+def emu():
+    d = os.path.join(HERE, "emu")
+    subprocess.check_call(["make", "-C", d, "libemu.so"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(d, "libemu.so"))
+    L.emu_mus.restype = C.c_int
+    L.emu_cen.restype = C.c_int
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _rect(*r):
+    return (C.c_int * 4)(*r)
+
+
+def _mus(L, which, rect, nk, gf, mx, xind, pta, zwx, zwy, fx, fy, lin, isf, kjpt, ptb=None):
+    jpk, jpj, jpi = gf["tmask"].shape
+    rc = L.emu_mus(which, jpi, jpj, jpk, kjpt, _rect(*rect), nk, C.c_double(gf["p2dt"]), int(lin), int(isf),
+                   _p(gf["tmask"]), _p(gf["umask"]), _p(gf["vmask"]), _p(gf["wmask"]), _p(gf["e3t_n"]), _p(gf["r1_e1e2t"]),
+                   _p(mx["r1_e1e2u"]), _p(mx["r1_e1e2v"]), _p(mx["e3u_n"]), _p(mx["e3v_n"]), _p(mx["e3w_n"]), _p(xind),
+                   _p(gf["mikt"]), _p(gf["pun"]), _p(gf["pvn"]), _p(gf["pwn"]), _p(gf["ptb"] if ptb is None else ptb), _p(pta),
+                   _p(zwx), _p(zwy), _p(fx), _p(fy))
+    assert rc == 0
+
+
+def _lbc_uv(jpiglo, jpjglo, jperio, a, b):
+    w = O.World(jpiglo, jpjglo, JPK, jperio, 1, 1)
+    w.lbc_lnk([[a.reshape(-1, a.shape[-2], a.shape[-1])], [b.reshape(-1, b.shape[-2], b.shape[-1])]], "UV", [-1.0, -1.0])
+    w.close()
+
+
+@pytest.mark.parametrize("nk", [1, 2, 3, 5])
+@pytest.mark.parametrize("jperio,lin,isf,ups", [(0, False, False, False), (4, True, True, True), (6, True, False, False)])
+def test_mus_kernels_with_jk_chunks(emu, nk, jperio, lin, isf, ups):
+    G, GJ, kjpt = 30, 26, 2
+    gf = H.random_fields(O, G, GJ, JPK, jperio, kjpt, seed=60 + jperio, ln_linssh=lin, ln_isfcav=isf)
+    mx = H.mus_extra_fields(O, gf, G, GJ, JPK, jperio, seed=60 + jperio, runoff=True)
+    ref, _ = H.oracle_mus(O, gf, mx, G, GJ, JPK, jperio, 1, 1, kjpt, ln_linssh=lin, ln_isfcav=isf, ld_msc_ups=ups)
+    xind = None
+    if ups:
+        w = O.World(G, GJ, JPK, jperio, 1, 1)
+        w.doms[0].set_fields(*[gf[k] for k in H.DOM_KEYS])
+        xind = w.doms[0].mus_xind(True, mx["rnfmsk"], mx["rnfmsk_z"])
+        w.close()
+    jpi, jpj = G, GJ
+    f = 1 if jperio in (3, 4, 5, 6) else 0
+    shp = gf["ptb"].shape
+    # ---- reference structure: grad -> lbc -> hflux -> lbc -> trend ----
+    pta = gf["pta"].copy()
+    zwx, zwy, fx, fy = (np.zeros(shp) for _ in range(4))
+    _mus(emu, 0, (1, jpi - 1, 1, jpj - 1), nk, gf, mx, xind, pta, zwx, zwy, fx, fy, lin, isf, kjpt)
+    _lbc_uv(G, GJ, jperio, zwx, zwy)
+    _mus(emu, 1, (2, jpi - 1, 2, jpj - 1), nk, gf, mx, xind, pta, zwx, zwy, fx, fy, lin, isf, kjpt)
+    _lbc_uv(G, GJ, jperio, fx, fy)
+    _mus(emu, 3, (2, jpi - 1, 2, jpj - 1), nk, gf, mx, xind, pta, zwx, zwy, fx, fy, lin, isf, kjpt)
+    assert np.array_equal(pta, ref)
+    # ---- default structure: differences in place from ptb on the inner columns, exchanged ones on the frame ----
+    pta2 = gf["pta"].copy()
+    fx2, fy2 = np.zeros(shp), np.zeros(shp)
+    _mus(emu, 2, (3, jpi - 2, 3, jpj - 2 - f), nk, gf, mx, xind, pta2, zwx, zwy, fx2, fy2, lin, isf, kjpt)
+    for rect in ((2, 2, 2, jpj - 1), (jpi - 1, jpi - 1, 2, jpj - 1), (3, jpi - 2, 2, 2), (3, jpi - 2, jpj - 1 - f, jpj - 1)):
+        _mus(emu, 1, rect, nk, gf, mx, xind, pta2, zwx, zwy, fx2, fy2, lin, isf, kjpt)
+    _lbc_uv(G, GJ, jperio, fx2, fy2)
+    assert np.array_equal(fx2, fx) and np.array_equal(fy2, fy)
+    # ---- fully fused inner kernel on the columns that need no exchanged value ----
+    pta3 = gf["pta"].copy()
+    _mus(emu, 4, (4, jpi - 2, 4, jpj - 2 - f), nk, gf, mx, xind, pta3, zwx, zwy, fx, fy, lin, isf, kjpt)
+    sl = (slice(None), slice(None), slice(3, jpj - 2 - f), slice(3, jpi - 2))
+    assert np.array_equal(pta3[sl], ref[sl])
+
+
+@pytest.mark.parametrize("nk", [1, 3, 4])
+@pytest.mark.parametrize("h,v", [(2, 2), (2, 4), (4, 2), (4, 4)])
+@pytest.mark.parametrize("jperio,lin,isf", [(1, False, False), (4, True, True)])
+def test_cen_kernel_with_jk_chunks(emu, nk, h, v, jperio, lin, isf):
+    G, GJ, kjpt = 28, 24, 2
+    gf = H.random_fields(O, G, GJ, JPK, jperio, kjpt, seed=80 + jperio, ln_linssh=lin, ln_isfcav=isf)
+    ref, _ = H.oracle_cen(O, gf, G, GJ, JPK, jperio, 1, 1, kjpt, h, v, ln_linssh=lin, ln_isfcav=isf)
+    jpi, jpj = G, GJ
+    shp = gf["ptn"].shape
+    ztu, ztv, ztw = np.zeros(shp), np.zeros(shp), np.zeros(shp)
+    if h == 4:      # masked gradients by the MUSCL first-guess kernel on (2:jpim1, 2:jpjm1), then lbc_lnk (traadv_cen.F90:119-126)
+        dummy = {k: gf["r1_e1e2t"] for k in ("r1_e1e2u", "r1_e1e2v")}
+        dummy.update({k: gf["e3t_n"] for k in ("e3u_n", "e3v_n", "e3w_n")})
+        _mus(emu, 0, (2, jpi - 1, 2, jpj - 1), nk, gf, dummy, None, gf["pta"].copy(), ztu, ztv, ztu, ztv, lin, isf, kjpt, ptb=gf["ptn"])
+        _lbc_uv(G, GJ, jperio, ztu, ztv)
+    if v == 4:
+        w = O.World(G, GJ, JPK, jperio, 1, 1)
+        d = w.doms[0]
+        d.set_fields(*[gf[k] for k in H.DOM_KEYS], ln_linssh=lin, ln_isfcav=isf)
+        for jn in range(kjpt):
+            O.lib().interp_4th_cpt(d.h, gf["ptn"][jn].ctypes.data_as(C.c_void_p), ztw[jn].ctypes.data_as(C.c_void_p))
+        w.close()
+    pta = gf["pta"].copy()
+    rc = emu.emu_cen(h, v, jpi, jpj, JPK, kjpt, _rect(2, jpi - 1, 2, jpj - 1), nk, int(lin), int(isf), _p(gf["wmask"]), _p(gf["e3t_n"]),
+                     _p(gf["r1_e1e2t"]), _p(gf["mikt"]), _p(gf["pun"]), _p(gf["pvn"]), _p(gf["pwn"]), _p(gf["ptn"]), _p(pta),
+                     _p(ztu), _p(ztv), _p(ztw))
+    assert rc == 0
+    assert np.array_equal(pta, ref)
