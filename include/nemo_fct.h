@@ -162,9 +162,12 @@ int nemo_fct_set_e3uvw(nemo_fct_handle h, const double *e3u_n, const double *e3v
 int nemo_fct_set_mus_upstream(nemo_fct_handle h, int ld_msc_ups, const double *rnfmsk, const double *rnfmsk_z);
 /* CALL tra_adv_mus( kt, kit000, cdtype, p2dt, pun, pvn, pwn, ptb, pta, kjpt, ld_msc_ups ) -- ld_msc_ups is the state set by
  * nemo_fct_set_mus_upstream.  Only pta(2:jpim1, 2:jpjm1, 1:jpkm1, :) is modified.  Collective like tra_adv_fct (2 exchanges).
- * Schedules (nemo_fct_set_schedule): 0 = three reference-structured kernels on the whole interior; 1 = one fused kernel on
- * the exchange-free inner columns + the reference-structured kernels on the two-cell frame, overlapped on a side stream;
- * >= 2 (default) = 1 when the subdomain has real neighbours (the overlap hides the exchanges), else 0 (fewer instructions). */
+ * Schedules (nemo_fct_set_schedule), identical results bit for bit: 0 = three reference-structured kernels on the whole
+ * interior, both exchanges on the main stream; 1 = one fused kernel on the exchange-free inner columns + the
+ * reference-structured kernels on the two-cell frame, overlapped on a side stream (measured slower: kept for study);
+ * >= 2 (default) = the flux kernel forms the first-guess differences in place from ptb on the columns that need no
+ * exchanged value, so the first exchange only serves the one-cell frame (side stream); second exchange and trend kernel as 0.
+ * Subdomains smaller than 20 x 20 always use 0.                                                                           */
 int nemo_tra_adv_mus(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
                      const double *pvn, const double *pwn, const double *ptb, double *pta, int kjpt);
 int nemo_tra_adv_mus_dev(nemo_fct_handle h, int kt, int kit000, const char *cdtype, double p2dt, const double *pun,
