@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kThreads) k_nxt_euler(const NxtArgs a, int als
 
 }  // namespace
 
+#ifndef NEMO_EMU_KERNELS_ONLY          // launchers (CUDA launch syntax) are left out of the host emulation build of tests/emu
 void launch_nxt_fix(const NxtArgs &a, cudaStream_t s)
 {
     const dim3 g((unsigned)((a.jpi - 2 + kThreads - 1) / kThreads), (unsigned)(a.jpj - 2), (unsigned)(a.jpk - 1));
@@ -109,5 +110,6 @@ void launch_nxt_euler(const NxtArgs &a, int also_before, cudaStream_t s)
     const size_t per = a.jpij * (size_t)(a.jpk - 1);
     k_nxt_euler<<<(unsigned)((per + kThreads - 1) / kThreads), kThreads, 0, s>>>(a, also_before); note_launch();
 }
+#endif  // NEMO_EMU_KERNELS_ONLY
 
 }  // namespace nemo

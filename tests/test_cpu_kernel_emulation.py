@@ -117,3 +117,47 @@ def test_cen_kernel_with_jk_chunks(emu, nk, h, v, jperio, lin, isf):
                      _p(ztu), _p(ztv), _p(ztw))
     assert rc == 0
     assert np.array_equal(pta, ref)
+
+
+@pytest.mark.parametrize("mode,flags", [("fix", {}), ("vvl", {}), ("vvl", dict(ln_traqsr=1, ln_rnf=1, ln_isf=1)),
+                                        ("vvl", dict(ln_rnf_depth=1, ln_rnf=1)), ("euler_tra", {}), ("euler_trc", {})])
+def test_nxt_kernels(emu, mode, flags):
+    """k_nxt_fix / k_nxt_vvl (every forcing switch) / k_nxt_euler against the oracle's tra_nxt on a closed mono-domain, where
+    the lbc_lnk of tra_nxt only zeroes the halo: compared on the interior"""
+    G, GJ, kjpt, jperio = 24, 20, 3, 0
+    isf = bool(flags.get("ln_isf"))
+    lin = mode == "fix"
+    rng = np.random.default_rng(77)
+    gf = H.random_fields(O, G, GJ, JPK, jperio, kjpt, seed=91, ln_linssh=lin, ln_isfcav=isf)
+    f2 = {k: np.ascontiguousarray(rng.standard_normal((GJ, G)) * 1e-4) for k in ("emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf")}
+    f2["h_rnf"] = 10.0 + 50.0 * rng.random((GJ, G)); f2["r1_hisf_tbl"] = 1.0 / (20.0 + 10.0 * rng.random((GJ, G))); f2["ralpha"] = rng.random((GJ, G))
+    fn = {k: rng.standard_normal((kjpt, GJ, G)) * 1e-5 for k in ("sbc", "sbc_b", "rnf_tsc", "rnf_tsc_b", "risf_tsc", "risf_tsc_b")}
+    q3 = {k: rng.standard_normal((JPK, GJ, G)) * 1e-5 for k in ("qsr_hc", "qsr_hc_b")}
+    mikt, mbkt = gf["mikt"], gf["mbkt"]
+    ints = {"nk_rnf": np.minimum(mikt + 2, np.maximum(mbkt, 1)).astype(np.int32), "misfkt": mikt.astype(np.int32).copy(),
+            "misfkb": np.minimum(mikt + 1, np.maximum(mbkt, 1)).astype(np.int32)}
+    atfp, rdt, r1_rau0, nksr = 0.1, 900.0, 1.0 / 1026.0, 5
+    # ---- oracle ----
+    w = O.World(G, GJ, JPK, jperio, 1, 1)
+    w.doms[0].set_fields(*[gf[k] for k in H.DOM_KEYS], ln_linssh=lin, ln_isfcav=isf)
+    tb, tn, ta = gf["ptb"].copy(), gf["ptn"].copy(), gf["pta"].copy()
+    forc = O.NxtForcing(atfp=atfp, r1_rau0=r1_rau0, nksr=nksr, **flags, **f2, **q3, **ints,
+                        rnf_tsc=fn["rnf_tsc"], rnf_tsc_b=fn["rnf_tsc_b"], risf_tsc=fn["risf_tsc"], risf_tsc_b=fn["risf_tsc_b"])
+    cdtype = "TRC" if mode == "euler_trc" else "TRA"
+    w.tra_nxt(4, 1, mode.startswith("euler"), rdt, cdtype, [forc], [tb], [tn], [ta], kjpt, [fn["sbc"]], [fn["sbc_b"]])
+    w.close()
+    # ---- emulated kernels ----
+    eb, en, ea = gf["ptb"].copy(), gf["ptn"].copy(), gf["pta"].copy()
+    iflags = (C.c_int * 5)(int(flags.get("ln_traqsr", 0)), int(flags.get("ln_rnf", 0)), int(flags.get("ln_isf", 0)),
+                           int(flags.get("ln_rnf_depth", 0)), nksr)
+    tab = (C.c_void_p * 6)(*[f2[k].ctypes.data for k in ("emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf")])
+    m = {"fix": 0, "vvl": 1, "euler_tra": 2, "euler_trc": 2}[mode]
+    rc = emu.emu_nxt(m, int(mode == "euler_trc"), G, GJ, JPK, kjpt, C.c_double(atfp), C.c_double(atfp * rdt), C.c_double(atfp * rdt * r1_rau0),
+                     iflags, _p(gf["e3t_b"]), _p(gf["e3t_n"]), _p(gf["e3t_a"]), _p(mikt), _p(eb), _p(en), _p(ea), _p(fn["sbc"]), _p(fn["sbc_b"]),
+                     tab, _p(q3["qsr_hc"]), _p(q3["qsr_hc_b"]), _p(ints["nk_rnf"]), _p(f2["h_rnf"]), _p(fn["rnf_tsc"]), _p(fn["rnf_tsc_b"]),
+                     _p(ints["misfkt"]), _p(ints["misfkb"]), _p(fn["risf_tsc"]), _p(fn["risf_tsc_b"]), _p(f2["r1_hisf_tbl"]), _p(f2["ralpha"]))
+    assert rc == 0
+    inner = (slice(None), slice(0, JPK - 1), slice(1, -1), slice(1, -1))
+    for got, ref, name in ((eb, tb, "ptb"), (en, tn, "ptn"), (ea, ta, "pta")):
+        assert np.array_equal(got[inner], ref[inner]), name
+    assert not np.array_equal(en[inner], gf["ptn"][inner])
