@@ -1,0 +1,37 @@
+// Emulation of ONE thread block of a cooperative kernel (shared memory + __syncthreads): one host thread per CUDA thread,
+// std::barrier for __syncthreads(), a per-block host buffer for the dynamic shared memory.  TEST INFRASTRUCTURE ONLY.
+#pragma once
+#include "emu_common.h"
+
+#include <barrier>
+#include <memory>
+#include <thread>
+#include <vector>
+
+static thread_local std::barrier<> *emu_block_barrier = nullptr;
+static thread_local unsigned char *emu_block_smem = nullptr;
+#define __syncthreads() emu_block_barrier->arrive_and_wait()
+#define NEMO_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emu_block_smem)
+
+// run kernel(args...) for every block of a (gx, gy) grid with nthreads threads per block and smem_bytes of shared memory
+template <typename K, typename... A>
+static void emu_run_blocks(int gx, int gy, int nthreads, size_t smem_bytes, K kernel, const A &...args)
+{
+    std::vector<unsigned char> smem(smem_bytes);
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            std::barrier<> bar(nthreads);
+            std::vector<std::thread> th;
+            th.reserve(nthreads);
+            for (int t = 0; t < nthreads; ++t)
+                th.emplace_back([&, t, bx, by]() {
+                    blockIdx = {(unsigned)bx, (unsigned)by, 0};
+                    threadIdx = {(unsigned)t, 0, 0};
+                    blockDim = {(unsigned)nthreads, 1, 1};
+                    emu_block_barrier = &bar;
+                    emu_block_smem = smem.data();
+                    kernel(args...);
+                });
+            for (auto &x : th) x.join();
+        }
+}

@@ -27,7 +27,9 @@ def sign_half(x):
     return 0.5 + np.where(x >= 0.0, 0.5, -0.5)
 
 
-def tra_adv_fct(f, kjpt, kn_fct_h, jperio, ln_linssh=False):
+def tra_adv_fct(f, kjpt, kn_fct_h, jperio, ln_linssh=False, capture=None):
+    """capture: optional list that receives, per tracer, what the limiter + final trend start from (after X2, :280):
+    dict(zwi, zwx, zwy, zwz, pta) -- used to test the fused limiter kernel in isolation"""
     tmask, umask, vmask, wmask = f["tmask"], f["umask"], f["vmask"], f["wmask"]
     e3t_b, e3t_n, e3t_a, r1, e12 = f["e3t_b"], f["e3t_n"], f["e3t_a"], f["r1_e1e2t"][None], f["e1e2t"][None]
     pun, pvn, pwn, p2dt = f["pun"], f["pvn"], f["pwn"], f["p2dt"]
@@ -71,6 +73,8 @@ def tra_adv_fct(f, kjpt, kn_fct_h, jperio, ln_linssh=False):
         if ln_linssh:
             zwz[0] = 0.0
         lbc(zwi, "T", 1.0, jperio); lbc(zwx, "U", -1.0, jperio); lbc(zwy, "V", -1.0, jperio); lbc(zwz, "W", 1.0, jperio)
+        if capture is not None:
+            capture.append(dict(zwi=zwi.copy(), zwx=zwx.copy(), zwy=zwy.copy(), zwz=zwz.copy(), pta=pta.copy()))
         nonosc(ptb, zwx, zwy, zwz, zwi, p2dt, tmask, e3t_n, e12, jperio)
         # final trend (:288-297)
         pta[I] = pta[I] - ((zwx[:-1, 1:-1, 1:-1] - zwx[:-1, 1:-1, :-2]) + zwy[:-1, 1:-1, 1:-1] - zwy[:-1, :-2, 1:-1]

@@ -161,3 +161,35 @@ def test_nxt_kernels(emu, mode, flags):
     for got, ref, name in ((eb, tb, "ptb"), (en, tn, "ptn"), (ea, ta, "pta")):
         assert np.array_equal(got[inner], ref[inner]), name
     assert not np.array_equal(en[inner], gf["ptn"][inner])
+
+
+def _nonosc_case(jperio, h, seed):
+    import np_fct
+    G, GJ, K, kjpt = 46, 38, 9, 2
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=seed)
+    cap = []
+    final = np_fct.tra_adv_fct(gf, kjpt, h, jperio, capture=cap)
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, 2)
+    assert np.array_equal(final, ref)                       # the numpy statement is the oracle, bit for bit
+    return G, GJ, K, kjpt, gf, cap, final
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("jperio,h", [(0, 2), (1, 4)])
+def test_fused_limiter_kernel_emulated(emu, variant, jperio, h):
+    """k_fct_nonosc_final (512 cooperating threads per block, shared memory, one barrier per level) compiled for the host
+    from nonosc_final.cuh and run one host thread per CUDA thread: from the fields after X2 it must reproduce the final pta
+    of the oracle on its output rectangle.  variant 2 = the not-yet-measured kernel of csrc/dev/nonosc_final_v2.cuh."""
+    G, GJ, K, kjpt, gf, cap, final = _nonosc_case(jperio, h, 400 + jperio)
+    stack = lambda k: np.ascontiguousarray(np.stack([c[k] for c in cap]))
+    zwi, zwx, zwy, zwz, pta = (stack(k) for k in ("zwi", "zwx", "zwy", "zwz", "pta"))
+    out = (5, G - 4, 4, GJ - 4)
+    emu.emu_nonosc_final.restype = C.c_int
+    rc = emu.emu_nonosc_final(variant, G, GJ, K, kjpt, _rect(*out), C.c_double(gf["p2dt"]), _p(gf["tmask"]), _p(gf["e3t_n"]),
+                              _p(gf["e1e2t"]), _p(gf["r1_e1e2t"]), _p(gf["ptb"]), _p(zwi), _p(zwx), _p(zwy), _p(zwz), _p(pta))
+    if variant == 2 and rc == 1:
+        pytest.skip("csrc/dev/nonosc_final_v2.cuh not present")
+    assert rc == 0
+    sl = (slice(None), slice(0, K - 1), slice(out[2] - 1, out[3]), slice(out[0] - 1, out[1]))
+    assert np.array_equal(pta[sl], final[sl])
+    assert not np.array_equal(pta[sl], stack("pta")[sl])
