@@ -4,15 +4,12 @@
 
 namespace nemo { namespace {
 #include "../../nemo-fmi-devel_b200/csrc/nonosc_final.cuh"
-#ifdef NEMO_EMU_WITH_V2
-#include "../../nemo-fmi-devel_b200/csrc/dev/nonosc_final_v2.cuh"
-#endif
 } }
 
 extern "C" {
 
-// variant 1 = k_fct_nonosc_final (the product kernel), 2 = the dev variant.  out = i0, i1, j0, j1 (1-based output rectangle)
-int emu_nonosc_final(int variant, int jpi, int jpj, int jpk, int kjpt, const int *out, double p2dt, const double *tmask,
+// out = i0, i1, j0, j1 (1-based output rectangle)
+int emu_nonosc_final(int jpi, int jpj, int jpk, int kjpt, const int *out, double p2dt, const double *tmask,
                      const double *e3t_n, const double *e1e2t, const double *r1_e1e2t, const double *ptb, const double *zwi,
                      const double *zwx, const double *zwy, const double *zwz, double *pta)
 {
@@ -29,17 +26,8 @@ int emu_nonosc_final(int variant, int jpi, int jpj, int jpk, int kjpt, const int
     const int ni = out[1] - out[0] + 1, nj = out[3] - out[2] + 1;
     if (ni <= 0 || nj <= 0) return 0;
     const int gx = ((ni + ox - 1) / ox) * kjpt, gy = (nj + oy - 1) / oy;           // the grid of launch_fct_nonosc_final
-    if (variant == 1) {
-        emu_run_blocks(gx, gy, NX * NY, (size_t)(3 * 4 + 2 * 2) * NY * NX * sizeof(double), k_fct_nonosc_final, a);
-        return 0;
-    }
-#ifdef NEMO_EMU_WITH_V2
-    if (variant == 2) {
-        emu_run_blocks(gx, gy, NX * NY, (size_t)kNonoscV2SmemDoubles * sizeof(double), k_fct_nonosc_final_v2, a);
-        return 0;
-    }
-#endif
-    return 1;
+    emu_run_blocks(gx, gy, NX * NY, (size_t)(3 * 4 + 2 * 2) * NY * NX * sizeof(double), k_fct_nonosc_final, a);
+    return 0;
 }
 
 }  // extern "C"

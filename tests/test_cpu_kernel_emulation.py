@@ -174,21 +174,18 @@ def _nonosc_case(jperio, h, seed):
     return G, GJ, K, kjpt, gf, cap, final
 
 
-@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("jperio,h", [(0, 2), (1, 4)])
-def test_fused_limiter_kernel_emulated(emu, variant, jperio, h):
+def test_fused_limiter_kernel_emulated(emu, jperio, h):
     """k_fct_nonosc_final (512 cooperating threads per block, shared memory, one barrier per level) compiled for the host
     from nonosc_final.cuh and run one host thread per CUDA thread: from the fields after X2 it must reproduce the final pta
-    of the oracle on its output rectangle.  variant 2 = the not-yet-measured kernel of csrc/dev/nonosc_final_v2.cuh."""
+    of the oracle on its output rectangle."""
     G, GJ, K, kjpt, gf, cap, final = _nonosc_case(jperio, h, 400 + jperio)
     stack = lambda k: np.ascontiguousarray(np.stack([c[k] for c in cap]))
     zwi, zwx, zwy, zwz, pta = (stack(k) for k in ("zwi", "zwx", "zwy", "zwz", "pta"))
     out = (5, G - 4, 4, GJ - 4)
     emu.emu_nonosc_final.restype = C.c_int
-    rc = emu.emu_nonosc_final(variant, G, GJ, K, kjpt, _rect(*out), C.c_double(gf["p2dt"]), _p(gf["tmask"]), _p(gf["e3t_n"]),
+    rc = emu.emu_nonosc_final(G, GJ, K, kjpt, _rect(*out), C.c_double(gf["p2dt"]), _p(gf["tmask"]), _p(gf["e3t_n"]),
                               _p(gf["e1e2t"]), _p(gf["r1_e1e2t"]), _p(gf["ptb"]), _p(zwi), _p(zwx), _p(zwy), _p(zwz), _p(pta))
-    if variant == 2 and rc == 1:
-        pytest.skip("csrc/dev/nonosc_final_v2.cuh not present")
     assert rc == 0
     sl = (slice(None), slice(0, K - 1), slice(out[2] - 1, out[3]), slice(out[0] - 1, out[1]))
     assert np.array_equal(pta[sl], final[sl])
