@@ -25,4 +25,33 @@ for jperio, (h, v) in ((4, (4, 4)), (0, (2, 2))):
     got, _ = H.device_fct(N, gf, G, GJ, K, jperio, 2, 2, 2, h, v, schedule=2)
     print("jperio", jperio, "2x2 in-process group", bool(np.array_equal(got, ref)), flush=True)
     ok = ok and bool(np.array_equal(got, ref))
+# widened rows: MUSCL (all three structures, in-process group), centred scheme, tra_nxt
+import golden_cases as GC    # noqa: E402
+for jperio in (4, 0):
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=8)
+    mx = H.mus_extra_fields(O, gf, G, GJ, K, jperio, seed=8, runoff=True)
+    ref, _ = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, 1, 1, 2)
+    for schedule in (0, 1, 2):
+        _, loc = H.device_mus(N, gf, mx, G, GJ, K, jperio, 1, 1, 2, schedule=schedule)
+        same = bool(np.array_equal(loc[0], ref))
+        print("tra_adv_mus jperio", jperio, "schedule", schedule, "bit-identical" if same else "MISMATCH", flush=True)
+        ok = ok and same
+    got, _ = H.device_mus(N, gf, mx, G, GJ, K, jperio, 2, 2, 2, schedule=2)
+    inner = (slice(None), slice(0, K - 1), slice(1, -1), slice(1, -1))
+    same = bool(np.array_equal(got[inner], ref[inner]))
+    print("tra_adv_mus jperio", jperio, "2x2 in-process group", same, flush=True)
+    ok = ok and same
+    for (h, v) in ((2, 2), (4, 4)):
+        ref, _ = H.oracle_cen(O, gf, G, GJ, K, jperio, 1, 1, 2, h, v)
+        _, loc = H.device_cen(N, gf, G, GJ, K, jperio, 1, 1, 2, h, v)
+        same = bool(np.array_equal(loc[0], ref))
+        print("tra_adv_cen jperio", jperio, "h/v", h, v, "bit-identical" if same else "MISMATCH", flush=True)
+        ok = ok and same
+for name in ("nxt_vvl_jperio4", "nxt_fix_jperio1"):
+    gf, extra = GC.inputs(O, name)
+    ref = GC.run_oracle(O, name, gf, extra)
+    got = GC.run_device(N, name, gf, extra, 2)
+    same = all(bool(np.array_equal(got[k], ref[k])) for k in ref)
+    print("tra_nxt", name, "bit-identical" if same else "MISMATCH", flush=True)
+    ok = ok and same
 sys.exit(0 if ok else 1)
