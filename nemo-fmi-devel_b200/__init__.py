@@ -153,6 +153,8 @@ class NxtForcing(C.Structure):
         self.atfp, self.r1_rau0 = atfp, r1_rau0
         self._keep = {}
         for k, v in kw.items():
+            if v is None:
+                continue
             if hasattr(v, "data_ptr"):
                 if not v.is_cuda:
                     raise ValueError(f"NxtForcing.{k}: device tensors only")

@@ -91,6 +91,8 @@ class NxtForcing(C.Structure):
         self.atfp, self.r1_rau0 = atfp, r1_rau0
         self._keep = {}
         for k, v in kw.items():
+            if v is None:
+                continue
             if isinstance(v, np.ndarray):
                 self._keep[k] = v
                 setattr(self, k, v.ctypes.data)
