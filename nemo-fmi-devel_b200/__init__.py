@@ -8,6 +8,11 @@ reference's routine names, argument order and meaning so that tests read like ca
     interp_4th_cpt      src/OCE/TRA/traadv_fct.F90:517       -> :meth:`FctContext.interp_4th_cpt`
     lbc_lnk_multi       src/OCE/LBC/lbc_lnk_multi_generic.h90:16 -> :meth:`FctContext.lbc_lnk_multi`
     tra_adv transports  src/OCE/TRA/traadv.F90:100-124       -> :meth:`FctContext.tra_adv_transports`
+    tra_adv / trc_adv   src/OCE/TRA/traadv.F90:77, src/TOP/TRP/trcadv.F90:70 -> :meth:`FctContext.tra_adv`, :meth:`FctContext.trc_adv`
+    tra_adv_mus         src/OCE/TRA/traadv_mus.F90:55        -> :meth:`FctContext.tra_adv_mus`
+    tra_adv_cen         src/OCE/TRA/traadv_cen.F90:46        -> :meth:`FctContext.tra_adv_cen`
+    tra_nxt / trc_nxt   src/OCE/TRA/tranxt.F90:65, src/TOP/TRP/trcnxt.F90:56 -> :meth:`FctContext.tra_nxt`
+    l_trd/l_hst/l_ptr   src/OCE/TRA/traadv_fct.F90:96-112    -> :meth:`FctContext.set_trend_diag`
 
 Arrays are fp64 with the Fortran memory image ``a(jpi,jpj,jpk[,kjpt])``, i.e. C-order shape ``([kjpt,] jpk, jpj, jpi)``.
 numpy arrays are passed as HOST pointers (the library copies H2D/D2H, as a Fortran host would see it); CUDA
