@@ -78,3 +78,19 @@ def test_oracle_is_not_linked_into_the_product(N):
         assert sym not in exported
     ldd = subprocess.run(["ldd", N.LIB_PATH], capture_output=True, text=True).stdout
     assert "liboracle" not in ldd
+
+
+def test_header_is_plain_c_and_the_c_example_links(N, tmp_path):
+    """include/nemo_fct.h is C99 (a Fortran / C host binds it, no C++ or torch types), examples/fct_step.c builds against the
+    shared library with nothing but gcc, and on a machine without a GPU it stops at nemo_fct_create with a message."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "nemo_fct.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    exe = str(tmp_path / "fct_step")
+    libdir = os.path.dirname(N.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "fct_step.c"), "-L", libdir, "-lnemo_fct", "-Wl,-rpath," + libdir, "-o", exe])
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr, (r.returncode, r.stderr)
