@@ -2,8 +2,6 @@
 oracle -- bit for bit.  Covers what the GPU suite does not reach at its small jpk: the jk loop split in chunks across
 blockIdx.y (chunk-start recomputation of the vertical slopes / fluxes), which production sizes (jpk = 75) use."""
 import ctypes as C
-import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -11,36 +9,15 @@ import pytest
 from oracle import oracle as O
 import helpers as H
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+import emu_api
+from emu_api import p as _p, rect as _rect, mus as _mus
+
 JPK = 19
 
 
 @pytest.fixture(scope="module")
 def emu():
-    d = os.path.join(HERE, "emu")
-    subprocess.check_call(["make", "-C", d, "libemu.so"], stdout=subprocess.DEVNULL)
-    L = C.CDLL(os.path.join(d, "libemu.so"))
-    L.emu_mus.restype = C.c_int
-    L.emu_cen.restype = C.c_int
-    return L
-
-
-def _p(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
-
-
-def _rect(*r):
-    return (C.c_int * 4)(*r)
-
-
-def _mus(L, which, rect, nk, gf, mx, xind, pta, zwx, zwy, fx, fy, lin, isf, kjpt, ptb=None):
-    jpk, jpj, jpi = gf["tmask"].shape
-    rc = L.emu_mus(which, jpi, jpj, jpk, kjpt, _rect(*rect), nk, C.c_double(gf["p2dt"]), int(lin), int(isf),
-                   _p(gf["tmask"]), _p(gf["umask"]), _p(gf["vmask"]), _p(gf["wmask"]), _p(gf["e3t_n"]), _p(gf["r1_e1e2t"]),
-                   _p(mx["r1_e1e2u"]), _p(mx["r1_e1e2v"]), _p(mx["e3u_n"]), _p(mx["e3v_n"]), _p(mx["e3w_n"]), _p(xind),
-                   _p(gf["mikt"]), _p(gf["pun"]), _p(gf["pvn"]), _p(gf["pwn"]), _p(gf["ptb"] if ptb is None else ptb), _p(pta),
-                   _p(zwx), _p(zwy), _p(fx), _p(fy))
-    assert rc == 0
+    return emu_api.load()
 
 
 def _lbc_uv(jpiglo, jpjglo, jperio, a, b):
@@ -183,7 +160,6 @@ def test_fused_limiter_kernel_emulated(emu, jperio, h):
     stack = lambda k: np.ascontiguousarray(np.stack([c[k] for c in cap]))
     zwi, zwx, zwy, zwz, pta = (stack(k) for k in ("zwi", "zwx", "zwy", "zwz", "pta"))
     out = (5, G - 4, 4, GJ - 4)
-    emu.emu_nonosc_final.restype = C.c_int
     rc = emu.emu_nonosc_final(G, GJ, K, kjpt, _rect(*out), C.c_double(gf["p2dt"]), _p(gf["tmask"]), _p(gf["e3t_n"]),
                               _p(gf["e1e2t"]), _p(gf["r1_e1e2t"]), _p(gf["ptb"]), _p(zwi), _p(zwx), _p(zwy), _p(zwz), _p(pta))
     assert rc == 0
