@@ -24,7 +24,7 @@
 #define __launch_bounds__(...)
 
 struct EmuIdx { unsigned x, y, z; };
-static thread_local EmuIdx blockIdx, threadIdx, blockDim;      // thread_local: emu_block.h runs one host thread per CUDA thread
+static thread_local EmuIdx blockIdx, threadIdx, blockDim, gridDim;      // thread_local: emu_block.h runs one host thread per CUDA thread
 using std::min;
 #define NEMO_EMU_KERNELS_ONLY 1
 

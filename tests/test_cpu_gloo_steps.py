@@ -1,8 +1,8 @@
-"""N > 1 on the CPU for the widened rows: two processes (gloo, world_size 2, 127.0.0.1), each owning one subdomain, run a
-complete tra_adv_mus step and a complete tra_nxt with
+"""N > 1 on the CPU, whole steps: two processes (gloo, world_size 2, 127.0.0.1), each owning one subdomain, run a complete
+tra_adv_fct step (4th order + compact vertical, exchanges X1..X4), a complete tra_adv_mus step and a complete tra_nxt with
   * the product's column kernels compiled for the host from the same source (tests/emu), and
   * the product's compiled lbc_lnk plans executed over torch.distributed p2p (what pack / ncclSend / ncclRecv / unpack do),
-in the order run_mus / run_nxt launch them, and must reproduce the oracle's rank (threads as MPI ranks) bit for bit,
+in the order run_fct / run_mus / run_nxt launch them, and must reproduce the oracle's rank (threads as MPI ranks) bit for bit,
 including the halos and the north-fold rows."""
 import ctypes as C
 import os
@@ -45,6 +45,10 @@ def _worker(rank, world, port, cases, out):
             for a, nat, sgn in fields_nat_sgn:
                 _exchange(N, doms, rank, a, nat, sgn, nlev)
 
+        # ---- tra_adv_fct, reference pass structure with X1..X4 (run_fct, schedule 0): 4th order + compact vertical ----
+        refg, refl_fct, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, ni, nj, KJPT, 4, 4)
+        got, _ = emu_api.fct_step(L, loc, KJPT, 4, 4, False, False, 2, lbc)
+        ok = ok and bool(np.array_equal(got, refl_fct[rank]))
         # ---- tra_adv_mus, reference structure (run_mus, schedule 0) ----
         _, refl = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, ni, nj, KJPT)
         pta = loc["pta"].copy()
@@ -82,7 +86,7 @@ def _worker(rank, world, port, cases, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_muscl_step_and_tra_nxt_over_gloo():
+def test_two_rank_fct_muscl_and_tra_nxt_steps_over_gloo():
     import emu_api
     from test_cpu_gloo_exchange import _free_port
     emu_api.load()                                              # build libemu.so once, before the workers start

@@ -166,3 +166,53 @@ def test_fused_limiter_kernel_emulated(emu, jperio, h):
     sl = (slice(None), slice(0, K - 1), slice(out[2] - 1, out[3]), slice(out[0] - 1, out[1]))
     assert np.array_equal(pta[sl], final[sl])
     assert not np.array_equal(pta[sl], stack("pta")[sl])
+
+
+@pytest.mark.parametrize("nk", [1, 3])
+@pytest.mark.parametrize("h,v", [(2, 2), (4, 4), (4, 2), (2, 4)])
+@pytest.mark.parametrize("jperio,lin,isf", [(0, False, False), (4, True, True), (6, False, False)])
+def test_fct_column_kernels_reference_structure(emu, nk, h, v, jperio, lin, isf):
+    """the reference-structured FCT kernels (fct_column_kernels.cuh: laplacian, P1-P5, betas, limit, final, interp_4th_cpt with
+    its pivot table and simple-column classification, trend hook) in the order run_fct launches them, with the oracle's
+    lbc_lnk for X1..X4, jk loop chunked or not: whole-array equality with the oracle's tra_adv_fct and its hooks"""
+    G, GJ, kjpt = 30, 26, 2
+    gf = H.random_fields(O, G, GJ, JPK, jperio, kjpt, seed=700 + jperio, ln_linssh=lin, ln_isfcav=isf)
+    w = O.World(G, GJ, JPK, jperio, 1, 1)
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS], ln_linssh=lin, ln_isfcav=isf)
+    otrd = [np.full((kjpt,) + d.shape3, np.nan) for _ in range(3)]
+    d.set_diag(*otrd)
+    ref = gf["pta"].copy()
+    w.tra_adv_fct(gf["p2dt"], [gf["pun"]], [gf["pvn"]], [gf["pwn"]], [gf["ptb"]], [gf["ptn"]], [ref], kjpt, h, v)
+
+    def lbc(trip):
+        w.lbc_lnk([[a.reshape(-1, GJ, G)] for a, _, _ in trip], "".join(n for _, n, _ in trip), [s for _, _, s in trip])
+
+    pta, work = emu_api.fct_step(emu, gf, kjpt, h, v, lin, isf, nk, lbc, hooks=True)
+    w.close()
+    assert np.array_equal(pta, ref)
+    assert np.array_equal(work["trdx"][:, :, :-1, :-1], otrd[0][:, :, :-1, :-1])
+    assert np.array_equal(work["trdy"][:, :, :-1, :-1], otrd[1][:, :, :-1, :-1])
+    assert np.array_equal(work["trdz"], otrd[2])
+
+
+def test_interp_4th_cpt_simple_columns_and_general_path(emu):
+    """the 'simple column' shortcut (pivots and masks from mbkt and a jpk-entry table) must be taken on the full-depth
+    cavity-free columns only and give the same bits as the general path and as the oracle"""
+    G, GJ, jperio = 26, 22, 1
+    for isf in (False, True):
+        gf = H.random_fields(O, G, GJ, JPK, jperio, 2, seed=800, ln_isfcav=isf)
+        w = O.World(G, GJ, JPK, jperio, 1, 1)
+        d = w.doms[0]
+        d.set_fields(*[gf[k] for k in H.DOM_KEYS], ln_isfcav=isf)
+        ref = np.zeros_like(gf["ptn"])
+        for jn in range(2):
+            O.lib().interp_4th_cpt(d.h, gf["ptn"][jn].ctypes.data_as(C.c_void_p), ref[jn].ctypes.data_as(C.c_void_p))
+        w.close()
+        fast, slow = np.zeros_like(ref), np.zeros_like(ref)
+        nsimple = emu_api.interp_4th_cpt(emu, gf, gf["ptn"], fast, isf, use_simple=True)
+        assert emu_api.interp_4th_cpt(emu, gf, gf["ptn"], slow, isf, use_simple=False) == 0
+        ncol = (G - 2) * (GJ - 2)                                    # columns wet from level 1 down to mbkt qualify, cavities do not
+        assert (0 < nsimple < ncol) if isf else (0 < nsimple <= ncol), (nsimple, ncol)
+        inner = (slice(None), slice(1, JPK - 1), slice(1, -1), slice(1, -1))
+        assert np.array_equal(fast[inner], ref[inner]) and np.array_equal(slow[inner], ref[inner])
