@@ -23,6 +23,7 @@
 #include "../../include/nemo_fct.h"
 #include "kernels.cuh"
 #include "layout.hpp"
+#include "schedule.hpp"
 
 using namespace nemo;
 
@@ -481,7 +482,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
                                                  c->ln_isfcav, c->cpt_zwt.p, c->cpt_simple.p, c->cpt_utab.p, fa[m].ptn, c->ztw.p, c->stream))
     // schedule 1 needs room for the fused inner region on every subdomain
     bool fused = g[0]->schedule >= 1;
-    for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < 20 || g[m]->dom.jpj < 20) fused = false;
+    for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < kMinFusedSize || g[m]->dom.jpj < kMinFusedSize) fused = false;
     // the trend-diagnostic hooks need the limited fluxes in memory on the whole subdomain: reference pass structure
     bool diag = false;
     for (int m = 0; m < ng; ++m) if (g[m]->diag[0]) diag = true;
@@ -528,21 +529,9 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
             }
             ensure_side(c);
         } catch (const std::exception &e) { return fail("tra_adv_fct: schedule 1 set-up: %s", e.what()); }
-        auto band = [&](int wW, int wE, int wS, int wN) {
-            Region r;
-            r.add(2, 1 + wW, 2, jpj - 1);
-            r.add(jpi - wE, jpi - 1, 2, jpj - 1);
-            r.add(2 + wW, jpi - wE - 1, 2, 1 + wS);
-            r.add(2 + wW, jpi - wE - 1, jpj - wN, jpj - 1);
-            return r;
-        };
-        k1[m].reg = Region(); k1[m].reg.add(2, jpi - 2, 2, jpj - 2 - f);
-        k2[m].out = Rect{5, jpi - 4, 4, jpj - 4 - f};          // i0 odd: even TMA box origin
-        lowf[m].reg = Region(); lowf[m].reg.add(jpi - 1, jpi - 1, 2, jpj - 1); lowf[m].reg.add(2, jpi - 2, jpj - 1 - f, jpj - 1);
-        lap[m].reg = band(1, 1, 1, 2 + f);
-        fin[m].reg = band(3, 3, 2, 3 + f);
-        lim[m].reg = band(4, 4, 3, 4 + f);
-        bet[m].reg = band(5, 5, 4, 5 + f);
+        const FctFusedPlan fp = fct_fused_plan(jpi, jpj, f != 0, false);      // schedule.hpp
+        k1[m].reg = fp.k1; k2[m].out = fp.k2_out; lowf[m].reg = fp.lowf;
+        lap[m].reg = fp.lap; fin[m].reg = fp.fin; lim[m].reg = fp.lim; bet[m].reg = fp.bet;
         for (FctArgs *x : {&lim[m], &fin[m]}) { x->zlx = c->zlx.p; x->zly = c->zly.p; x->zlz = c->zlz.p; }
         // small launches: one jk chunk is enough for the bands
         for (FctArgs *x : {&lap[m], &lowf[m], &bet[m], &lim[m], &fin[m]}) x->nkchunk = std::max(1, std::min(8, (c->dom.jpk - 1) / 8));
@@ -561,18 +550,12 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     // coalesce badly): keep K1 whole there.
     bool split = g[0]->nccl_nranks > 1 || ng > 1;
     std::vector<FctArgs> k1b(k1), k1c(k1);
-    for (int m = 0; m < ng; ++m) {
-        const Rect r1 = k1[m].reg.r[0];
-        const int w = 8;
-        if (!split || r1.i1 - r1.i0 + 1 < 2 * w + 4 || r1.j1 - r1.j0 + 1 < 2 * w + 3) { split = false; break; }
-        k1b[m].reg = Region();
-        k1b[m].reg.add(r1.i0, r1.i0 + w - 1, r1.j0, r1.j1);                     // i0 = 2: the centre starts at an even column (TMA)
-        k1b[m].reg.add(r1.i1 - w + 1, r1.i1, r1.j0, r1.j1);
-        k1b[m].reg.add(r1.i0 + w, r1.i1 - w, r1.j0, r1.j0 + w - 2);
-        k1b[m].reg.add(r1.i0 + w, r1.i1 - w, r1.j1 - w + 1, r1.j1);
+    for (int m = 0; m < ng && split; ++m) {
+        const FctFusedPlan fp = fct_fused_plan(g[m]->dom.jpi, g[m]->dom.jpj, g[m]->dom.npolj != 0, true);
+        if (!fp.split) { split = false; break; }                                // all subdomains or none
+        k1b[m].reg = fp.k1_band;
         k1b[m].nkchunk = std::max(1, std::min(8, (g[m]->dom.jpk - 1) / 8));
-        k1c[m].reg = Region();
-        k1c[m].reg.add(r1.i0 + w, r1.i1 - w, r1.j0 + w - 1, r1.j1 - w);
+        k1c[m].reg = fp.k1_centre;
     }
     if (!split) k1c = k1;
 
@@ -658,7 +641,7 @@ static int run_mus(std::vector<Ctx *> &g, const std::vector<MusCall> &args, doub
     //             through k_mus_grad + the first exchange on the side stream, hidden behind the inner flux kernel.
     bool fused = g[0]->schedule == 1;
     bool semi = g[0]->schedule >= 2;
-    for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < 20 || g[m]->dom.jpj < 20) fused = semi = false;
+    for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < kMinFusedSize || g[m]->dom.jpj < kMinFusedSize) fused = semi = false;
 
     std::vector<MusArgs> grad(ma), hfl(ma), trd(ma), inner(ma);
     if (semi) {
@@ -667,18 +650,8 @@ static int run_mus(std::vector<Ctx *> &g, const std::vector<MusCall> &args, doub
             const int jpi = c->dom.jpi, jpj = c->dom.jpj, f = c->dom.npolj != 0 ? 1 : 0;
             try { CUTHROW(cudaSetDevice(c->device)); ensure_side(c); }
             catch (const std::exception &e) { return fail("tra_adv_mus: side stream: %s", e.what()); }
-            auto band = [&](int i_lo, int wW, int wE, int j_lo, int wS, int wN) {
-                Region r;
-                r.add(i_lo, wW, j_lo, jpj - 1);
-                r.add(jpi - wE, jpi - 1, j_lo, jpj - 1);
-                r.add(wW + 1, jpi - wE - 1, j_lo, wS);
-                r.add(wW + 1, jpi - wE - 1, jpj - wN, jpj - 1);
-                return r;
-            };
-            inner[m].reg.add(3, jpi - 2, 3, jpj - 2 - f);                   // fluxes straight from ptb
-            hfl[m].reg = band(2, 2, 1, 2, 2, 1 + f);                        // the rest of the interior: exchanged differences
-            grad[m].reg = band(1, 3, 2, 1, 3, 3 + f);                       // what those columns and the first exchange read
-            trd[m].reg.add(2, jpi - 1, 2, jpj - 1);
+            const MusPlan mp = mus_semi_plan(jpi, jpj, f != 0);              // schedule.hpp
+            inner[m].reg = mp.inner; hfl[m].reg = mp.hflux; grad[m].reg = mp.grad; trd[m].reg = mp.trend;
             for (MusArgs *x : {&grad[m], &hfl[m]}) x->nkchunk = std::max(1, std::min(8, (c->dom.jpk - 1) / 8));
         }
         cudaStream_t side = g[0]->side_stream;
@@ -725,18 +698,8 @@ static int run_mus(std::vector<Ctx *> &g, const std::vector<MusCall> &args, doub
         const int jpi = c->dom.jpi, jpj = c->dom.jpj, f = c->dom.npolj != 0 ? 1 : 0;
         try { CUTHROW(cudaSetDevice(c->device)); ensure_side(c); }
         catch (const std::exception &e) { return fail("tra_adv_mus: side stream: %s", e.what()); }
-        auto band = [&](int i_lo, int wW, int wE, int j_lo, int wS, int wN) {      // W: i_lo..wW, E: jpi-wE..jpi-1, S: j_lo..wS, N: jpj-wN..jpj-1
-            Region r;
-            r.add(i_lo, wW, j_lo, jpj - 1);
-            r.add(jpi - wE, jpi - 1, j_lo, jpj - 1);
-            r.add(wW + 1, jpi - wE - 1, j_lo, wS);
-            r.add(wW + 1, jpi - wE - 1, jpj - wN, jpj - 1);
-            return r;
-        };
-        inner[m].reg.add(4, jpi - 2, 4, jpj - 2 - f);
-        trd[m].reg = band(2, 3, 1, 2, 3, 1 + f);
-        hfl[m].reg = band(2, 4, 2, 2, 4, 3 + f);
-        grad[m].reg = band(1, 5, 3, 1, 5, 4 + f);
+        const MusPlan mp = mus_fused_plan(jpi, jpj, f != 0);                  // schedule.hpp
+        inner[m].reg = mp.inner; trd[m].reg = mp.trend; hfl[m].reg = mp.hflux; grad[m].reg = mp.grad;
         for (MusArgs *x : {&grad[m], &hfl[m], &trd[m]}) x->nkchunk = std::max(1, std::min(8, (c->dom.jpk - 1) / 8));
     }
     cudaStream_t side = g[0]->side_stream;

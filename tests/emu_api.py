@@ -40,12 +40,12 @@ def mus(L, which, rc, nk, gf, mx, xind, pta, zwx, zwy, fx, fy, lin, isf, kjpt, p
 
 
 FCT_ARRAYS = ("tmask umask vmask wmask e3t_b e3t_n e3t_a e1e2t r1_e1e2t pun pvn pwn ptb ptn pta "
-              "zwi zwx zwy zwz zltu zltv ztw zbetup zbetdo trdx trdy trdz").split()
+              "zwi zwx zwy zwz zltu zltv ztw zbetup zbetdo trdx trdy trdz zlx zly zlz").split()
 
 
-def fct(L, which, rc, nk, f, work, kjpt, h, v, lin, isf):
-    """which: 0 laplacian, 1 low_antidiff, 2 betas, 3 limit, 4 final, 5 trend hook.  f: module arrays + pun.. + pta (local);
-    work: dict of work arrays zwi.. (and trdx/trdy/trdz for the hook)"""
+def fct(L, which, rc, nk, f, work, kjpt, h, v, lin, isf, masks_from_t=False):
+    """which: 0 laplacian, 1 low_antidiff, 2 betas, 3 limit, 4 final, 5 trend hook, 6 fused inner P1-P5.  f: module arrays +
+    pun.. + pta (local); work: dict of work arrays zwi.. (trdx/trdy/trdz for the hook, zlx/zly/zlz for the fused frame)"""
     jpk, jpj, jpi = f["tmask"].shape
     tab = (C.c_void_p * len(FCT_ARRAYS))()
     for n, name in enumerate(FCT_ARRAYS):
@@ -53,8 +53,74 @@ def fct(L, which, rc, nk, f, work, kjpt, h, v, lin, isf):
         tab[n] = None if a is None else a.ctypes.data
     L.emu_fct.restype = C.c_int
     ret = L.emu_fct(which, jpi, jpj, jpk, kjpt, h, v, int(lin), int(isf), rect(*rc), nk, C.c_double(f["p2dt"]), tab,
-                    p(f["mikt"]), p(f["mbkt"]))
+                    p(f["mikt"]), p(f["mbkt"]), int(masks_from_t))
     assert ret == 0
+
+
+def _regions(buf, n):
+    out = []
+    for r in range(n):
+        b = buf[17 * r:17 * r + 17]
+        out.append([tuple(b[1 + 4 * q:5 + 4 * q]) for q in range(b[0])])
+    return out
+
+
+def fct_fused_plan(L, jpi, jpj, fold, want_split=False):
+    """schedule.hpp: dict of rectangle lists k1, k1_band, k1_centre, lowf, lap, bet, lim, fin + k2_out, split, min_size"""
+    buf = (C.c_int * (8 * 17 + 6))()
+    L.emu_fct_fused_plan(jpi, jpj, int(fold), int(want_split), buf)
+    d = dict(zip("k1 k1_band k1_centre lowf lap bet lim fin".split(), _regions(buf, 8)))
+    d["k2_out"] = tuple(buf[136:140]); d["split"] = bool(buf[140]); d["min_size"] = int(buf[141])
+    return d
+
+
+def mus_plan(L, which, jpi, jpj, fold):
+    """schedule.hpp: which = 0 default (differences in place on `inner`), 1 fully fused: dict inner, grad, hflux, trend"""
+    buf = (C.c_int * (4 * 17))()
+    L.emu_mus_plan(which, jpi, jpj, int(fold), buf)
+    return dict(zip("inner grad hflux trend".split(), _regions(buf, 4)))
+
+
+def nonosc_final(L, f, work, kjpt, out_rect):
+    """the fused limiter kernel (512 cooperating threads per block) on the output rectangle, in place on work['pta']"""
+    jpk, jpj, jpi = f["tmask"].shape
+    ret = L.emu_nonosc_final(jpi, jpj, jpk, kjpt, rect(*out_rect), C.c_double(f["p2dt"]), p(f["tmask"]), p(f["e3t_n"]), p(f["e1e2t"]),
+                             p(f["r1_e1e2t"]), p(f["ptb"]), p(work["zwi"]), p(work["zwx"]), p(work["zwy"]), p(work["zwz"]), p(work["pta"]))
+    assert ret == 0
+
+
+def fct_step_fused(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, masks_from_t, want_split=False):
+    """tra_adv_fct in the fused schedule (run_fct, schedules 1/2) on one subdomain: fused inner kernels on the regions of
+    schedule.hpp, reference-structured kernels on the frame bands with the exchanges X1..X4 through lbc()."""
+    import numpy as np
+    jpk, jpj, jpi = f["tmask"].shape
+    shp = (kjpt, jpk, jpj, jpi)
+    plan = fct_fused_plan(L, jpi, jpj, fold, want_split)
+    work = {k: np.zeros(shp) for k in ("zwi", "zwx", "zwy", "zwz", "zltu", "zltv", "ztw", "zbetup", "zbetdo", "zlx", "zly", "zlz")}
+    work["pta"] = f["pta"].copy()
+    frame = {k: v for k, v in work.items() if k not in ("zlx", "zly", "zlz")}        # kernels that must not see zlx..: NULL
+
+    def on(region, which, w, **kw):
+        for rc in plan[region]:
+            fct(L, which, rc, nk, f, w, kjpt, h, v, lin, isf, **kw)
+
+    if v == 4:
+        interp_4th_cpt(L, f, f["ptn"], work["ztw"], isf)
+    on("k1_centre", 6, frame, masks_from_t=masks_from_t)                             # main stream
+    if h == 4:
+        on("lap", 0, frame)
+        lbc([(work["zltu"], "T", 1.0), (work["zltv"], "T", 1.0)])                     # X1
+    on("lowf", 1, frame)
+    if plan["split"]:
+        on("k1_band", 6, frame, masks_from_t=masks_from_t)
+    lbc([(work["zwi"], "T", 1.0), (work["zwx"], "U", -1.0), (work["zwy"], "V", -1.0), (work["zwz"], "W", 1.0)])   # X2
+    on("bet", 2, frame)
+    lbc([(work["zbetup"], "T", 1.0), (work["zbetdo"], "T", 1.0)])                     # X3
+    on("lim", 3, work)                                                                # limited fluxes -> zlx, zly, zlz
+    lbc([(work["zlx"], "U", -1.0), (work["zly"], "V", -1.0)])                         # X4 on the limited copies
+    nonosc_final(L, f, work, kjpt, plan["k2_out"])                                    # main stream; reads the unlimited fluxes
+    on("fin", 4, work)
+    return work["pta"], plan
 
 
 def interp_4th_cpt(L, f, pt_in, pt_out, isf, use_simple=True):

@@ -216,3 +216,96 @@ def test_interp_4th_cpt_simple_columns_and_general_path(emu):
         assert (0 < nsimple < ncol) if isf else (0 < nsimple <= ncol), (nsimple, ncol)
         inner = (slice(None), slice(1, JPK - 1), slice(1, -1), slice(1, -1))
         assert np.array_equal(fast[inner], ref[inner]) and np.array_equal(slow[inner], ref[inner])
+
+
+@pytest.mark.parametrize("G,GJ", [(20, 20), (21, 20), (20, 23), (22, 20), (33, 21), (40, 38)])
+@pytest.mark.parametrize("jperio", [0, 1, 4, 6])
+def test_fct_fused_schedule_on_the_host(emu, G, GJ, jperio):
+    """The WHOLE fused schedule of run_fct (schedules 1/2) on the CPU: the column sets of csrc/schedule.hpp, the fused P1-P5
+    kernel (cp.async ring as plain copies), the fused limiter kernel (512 host threads per block), the reference-structured
+    kernels on the frame bands and X1..X4 -- from the minimum subdomain size (20 x 20) up, closed / cyclic / T- and F-pivot
+    fold, band split on and off, masks derived from tmask or read: whole-array equality with the oracle."""
+    kjpt, K = 2, 7
+    fold = jperio in (3, 4, 5, 6)
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=900 + G + GJ + jperio)
+    w = O.World(G, GJ, K, jperio, 1, 1)
+
+    def lbc(trip):
+        w.lbc_lnk([[a.reshape(-1, GJ, G)] for a, _, _ in trip], "".join(n for _, n, _ in trip), [s for _, _, s in trip])
+
+    for (h, v, from_t, split) in ((4, 4, True, False), (2, 2, False, True), (4, 2, True, True)):
+        ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v)
+        pta, plan = emu_api.fct_step_fused(emu, gf, kjpt, h, v, False, False, 1, lbc, fold, from_t, want_split=split)
+        assert plan["min_size"] == 20
+        assert np.array_equal(pta, ref), (h, v, from_t, split, plan["split"])
+    w.close()
+
+
+def test_fused_plans_cover_the_interior_exactly_once(emu):
+    """schedule.hpp: inner region + frame = the interior, no column twice, for every size from the minimum up"""
+    for fold in (False, True):
+        for jpi in range(20, 46):
+            for jpj in range(20, 44):
+                p = emu_api.fct_fused_plan(emu, jpi, jpj, fold, want_split=True)
+                cover = np.zeros((jpj + 1, jpi + 1), int)
+                for (i0, i1, j0, j1) in p["k1"] + p["lowf"]:
+                    cover[j0:j1 + 1, i0:i1 + 1] += 1
+                assert (cover[2:jpj, 2:jpi] == 1).all() and cover.sum() == (jpi - 2) * (jpj - 2), (jpi, jpj, fold)
+                if p["split"]:
+                    c2 = np.zeros_like(cover)
+                    for (i0, i1, j0, j1) in p["k1_band"] + p["k1_centre"]:
+                        c2[j0:j1 + 1, i0:i1 + 1] += 1
+                    c1 = np.zeros_like(cover)
+                    for (i0, i1, j0, j1) in p["k1"]:
+                        c1[j0:j1 + 1, i0:i1 + 1] += 1
+                    assert (c1 == c2).all(), (jpi, jpj, fold)
+                    assert p["k1_centre"][0][0] % 2 == 0                    # even first column: TMA box origin
+                # final trend: fused output rectangle + frame `fin` = the interior, exactly once
+                c3 = np.zeros_like(cover)
+                i0, i1, j0, j1 = p["k2_out"]
+                c3[j0:j1 + 1, i0:i1 + 1] += 1
+                for (i0, i1, j0, j1) in p["fin"]:
+                    c3[j0:j1 + 1, i0:i1 + 1] += 1
+                assert (c3[2:jpj, 2:jpi] == 1).all() and c3.sum() == (jpi - 2) * (jpj - 2), (jpi, jpj, fold)
+                for which in (0, 1):
+                    m = emu_api.mus_plan(emu, which, jpi, jpj, fold)
+                    c4 = np.zeros_like(cover)
+                    parts = m["inner"] + (m["hflux"] if which == 0 else m["trend"])
+                    for (i0, i1, j0, j1) in parts:
+                        c4[j0:j1 + 1, i0:i1 + 1] += 1
+                    assert (c4[2:jpj, 2:jpi] == 1).all() and c4.sum() == (jpi - 2) * (jpj - 2), (which, jpi, jpj, fold)
+
+
+@pytest.mark.parametrize("G,GJ", [(20, 20), (21, 22), (23, 20), (40, 38)])
+@pytest.mark.parametrize("jperio", [0, 1, 4, 6])
+def test_mus_schedules_on_the_host(emu, G, GJ, jperio):
+    """run_mus on the CPU with the column sets of schedule.hpp, from the minimum size up: the default structure (differences
+    in place from ptb on `inner`, exchanged ones on the frame) and the fully fused one, both equal to the oracle"""
+    kjpt, K = 2, 7
+    fold = jperio in (3, 4, 5, 6)
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=950 + G + GJ + jperio)
+    mx = H.mus_extra_fields(O, gf, G, GJ, K, jperio, seed=950 + jperio)
+    ref, _ = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, 1, 1, kjpt)
+    w = O.World(G, GJ, K, jperio, 1, 1)
+
+    def lbc(a, b):
+        w.lbc_lnk([[a.reshape(-1, GJ, G)], [b.reshape(-1, GJ, G)]], "UV", [-1.0, -1.0])
+
+    shp = gf["ptb"].shape
+    for which in (0, 1):
+        plan = emu_api.mus_plan(emu, which, G, GJ, fold)
+        pta = gf["pta"].copy()
+        zwx, zwy, fx, fy = (np.zeros(shp) for _ in range(4))
+
+        def on(region, kern):
+            for rc in plan[region]:
+                _mus(emu, kern, rc, 1, gf, mx, None, pta, zwx, zwy, fx, fy, False, False, kjpt)
+
+        on("inner", 2 if which == 0 else 4)          # fluxes from ptb / the whole trend
+        on("grad", 0)
+        lbc(zwx, zwy)
+        on("hflux", 1)
+        lbc(fx, fy)
+        on("trend", 3)
+        assert np.array_equal(pta, ref), which
+    w.close()
