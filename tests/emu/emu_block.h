@@ -4,6 +4,7 @@
 #include "emu_common.h"
 
 #include <barrier>
+#include <cstdint>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -12,26 +13,34 @@ static thread_local std::barrier<> *emu_block_barrier = nullptr;
 static thread_local unsigned char *emu_block_smem = nullptr;
 #define __syncthreads() emu_block_barrier->arrive_and_wait()
 #define NEMO_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emu_block_smem)
+#define NEMO_DYN_SMEM_ALIGNED(type, name, alignment) type *name = reinterpret_cast<type *>(emu_block_smem)
 
-// run kernel(args...) for every block of a (gx, gy) grid with nthreads threads per block and smem_bytes of shared memory
+// run kernel(args...) for every block of a (gx, gy, gz) grid with nthreads threads per block and smem_bytes of shared memory
 template <typename K, typename... A>
-static void emu_run_blocks(int gx, int gy, int nthreads, size_t smem_bytes, K kernel, const A &...args)
+static void emu_run_blocks3(int gx, int gy, int gz, int nthreads, size_t smem_bytes, K kernel, const A &...args)
 {
-    std::vector<unsigned char> smem(smem_bytes);
+    std::vector<unsigned char> smem(smem_bytes + 128);
+    unsigned char *base = smem.data() + (128 - reinterpret_cast<uintptr_t>(smem.data()) % 128) % 128;    // 128-byte aligned, like the device
+    for (int bz = 0; bz < gz; ++bz)
     for (int by = 0; by < gy; ++by)
         for (int bx = 0; bx < gx; ++bx) {
             std::barrier<> bar(nthreads);
             std::vector<std::thread> th;
             th.reserve(nthreads);
             for (int t = 0; t < nthreads; ++t)
-                th.emplace_back([&, t, bx, by]() {
-                    blockIdx = {(unsigned)bx, (unsigned)by, 0};
+                th.emplace_back([&, t, bx, by, bz]() {
+                    blockIdx = {(unsigned)bx, (unsigned)by, (unsigned)bz};
                     threadIdx = {(unsigned)t, 0, 0};
                     blockDim = {(unsigned)nthreads, 1, 1};
                     emu_block_barrier = &bar;
-                    emu_block_smem = smem.data();
+                    emu_block_smem = base;
                     kernel(args...);
                 });
             for (auto &x : th) x.join();
         }
+}
+template <typename K, typename... A>
+static void emu_run_blocks(int gx, int gy, int nthreads, size_t smem_bytes, K kernel, const A &...args)
+{
+    emu_run_blocks3(gx, gy, 1, nthreads, smem_bytes, kernel, args...);
 }

@@ -57,6 +57,19 @@ def fct(L, which, rc, nk, f, work, kjpt, h, v, lin, isf, masks_from_t=False):
     assert ret == 0
 
 
+def fct_tma(L, rc, nk, f, work, kjpt, h, v, lin, isf, masks_from_t):
+    """the TMA-tiled fused P1-P5 kernel on ONE rectangle.  Returns -1 where the product falls back to the cp.async kernel (odd
+    jpi or odd first column), else the number of violated hardware rules (negative / odd box origins): must be 0"""
+    jpk, jpj, jpi = f["tmask"].shape
+    tab = (C.c_void_p * len(FCT_ARRAYS))()
+    for n, name in enumerate(FCT_ARRAYS):
+        a = work.get(name) if name in work else f.get(name)
+        tab[n] = None if a is None else a.ctypes.data
+    L.emu_fct_low_antidiff_tma.restype = C.c_int
+    return L.emu_fct_low_antidiff_tma(jpi, jpj, jpk, kjpt, h, v, int(lin), int(isf), rect(*rc), nk, C.c_double(f["p2dt"]), tab,
+                                      p(f["mikt"]), p(f["mbkt"]), int(masks_from_t))
+
+
 def _regions(buf, n):
     out = []
     for r in range(n):
@@ -89,7 +102,7 @@ def nonosc_final(L, f, work, kjpt, out_rect):
     assert ret == 0
 
 
-def fct_step_fused(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, masks_from_t, want_split=False):
+def fct_step_fused(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, masks_from_t, want_split=False, tma=False):
     """tra_adv_fct in the fused schedule (run_fct, schedules 1/2) on one subdomain: fused inner kernels on the regions of
     schedule.hpp, reference-structured kernels on the frame bands with the exchanges X1..X4 through lbc()."""
     import numpy as np
@@ -106,7 +119,14 @@ def fct_step_fused(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, masks_from_t, want
 
     if v == 4:
         interp_4th_cpt(L, f, f["ptn"], work["ztw"], isf)
-    on("k1_centre", 6, frame, masks_from_t=masks_from_t)                             # main stream
+    used_tma = False
+    if tma and len(plan["k1_centre"]) == 1:                                          # schedule 2: TMA tiles where possible
+        rc_tma = fct_tma(L, plan["k1_centre"][0], nk, f, frame, kjpt, h, v, lin, isf, masks_from_t)
+        assert rc_tma <= 0, "TMA box origin rule violated %d times" % rc_tma
+        used_tma = rc_tma == 0
+    plan["used_tma"] = used_tma
+    if not used_tma:
+        on("k1_centre", 6, frame, masks_from_t=masks_from_t)                         # main stream
     if h == 4:
         on("lap", 0, frame)
         lbc([(work["zltu"], "T", 1.0), (work["zltv"], "T", 1.0)])                     # X1

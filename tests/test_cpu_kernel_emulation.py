@@ -309,3 +309,43 @@ def test_mus_schedules_on_the_host(emu, G, GJ, jperio):
         on("trend", 3)
         assert np.array_equal(pta, ref), which
     w.close()
+
+
+@pytest.mark.parametrize("G,GJ,jperio", [(20, 20, 0), (22, 21, 4), (34, 20, 1), (40, 29, 6), (52, 38, 4), (21, 24, 0), (66, 27, 1)])
+def test_fct_fused_schedule_with_tma_tiles_on_the_host(emu, G, GJ, jperio):
+    """schedule 2: the TMA-tiled P1-P5 kernel (256 host threads per block, mbarrier phases as atomic counters, bulk tensor
+    copies as box copies with zero fill on the high side) in the whole fused step.  Tile origins, box coordinates, shared-memory
+    indexing and ring reuse are exercised for one-tile and multi-tile rectangles with overhang, split and unsplit; the
+    emulation also CHECKS the hardware rules the kernel was designed around (box origins >= 0, even innermost coordinate);
+    odd jpi falls back to the cp.async kernel exactly like the launcher."""
+    kjpt, K = 2, 6
+    fold = jperio in (3, 4, 5, 6)
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=970 + G + GJ)
+    w = O.World(G, GJ, K, jperio, 1, 1)
+
+    def lbc(trip):
+        w.lbc_lnk([[a.reshape(-1, GJ, G)] for a, _, _ in trip], "".join(n for _, n, _ in trip), [s for _, _, s in trip])
+
+    for (h, v, from_t, split) in ((4, 4, True, False), (2, 2, False, False), (4, 4, True, True)):
+        ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v)
+        pta, plan = emu_api.fct_step_fused(emu, gf, kjpt, h, v, False, False, 1, lbc, fold, from_t, want_split=split, tma=True)
+        assert plan["used_tma"] == (G % 2 == 0), (G, plan)
+        assert np.array_equal(pta, ref), (h, v, from_t, split, plan["split"])
+    w.close()
+
+
+def test_fct_fused_schedule_tma_with_jk_chunks(emu):
+    """the same with the jk loop of every kernel split in 3 chunks (grid z of the TMA kernel, chunk-start state from global
+    memory), linear free surface with ice-shelf cavities"""
+    G, GJ, K, kjpt, jperio = 44, 30, 13, 2, 4
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=990, ln_linssh=True, ln_isfcav=True)
+    w = O.World(G, GJ, K, jperio, 1, 1)
+
+    def lbc(trip):
+        w.lbc_lnk([[a.reshape(-1, GJ, G)] for a, _, _ in trip], "".join(n for _, n, _ in trip), [s for _, _, s in trip])
+
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, 4, 4, ln_linssh=True, ln_isfcav=True)
+    pta, plan = emu_api.fct_step_fused(emu, gf, kjpt, 4, 4, True, True, 3, lbc, True, True, want_split=False, tma=True)
+    w.close()
+    assert plan["used_tma"]
+    assert np.array_equal(pta, ref)
