@@ -48,3 +48,43 @@ def test_device_reproduces_golden(name, schedule):
     N = importlib.import_module("nemo-fmi-devel_b200")
     gf, extra = _case(name)
     _check(name, GC.run_device(N, name, gf, extra, schedule))
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(GC.CASES) if GC.CASES[n][0] in ("fct", "mus")])
+def test_emulated_default_schedule_reproduces_golden(name):
+    """the default device schedule (fused, TMA tiles / differences in place) run on the CPU from the product's own kernel
+    sources and column sets (tests/emu) against the committed vectors: what the GPU case above will see, minus the GPU"""
+    import emu_api
+    L = emu_api.load()
+    kind, jperio, opt = GC.CASES[name]
+    gf, extra = _case(name)
+    lin, isf = opt.get("ln_linssh", False), opt.get("ln_isfcav", False)
+    fold = jperio in (3, 4, 5, 6)
+    w = O.World(GC.G, GC.GJ, GC.K, jperio, 1, 1)
+
+    def lbc(trip):
+        w.lbc_lnk([[a.reshape(-1, GC.GJ, GC.G)] for a, _, _ in trip], "".join(n for _, n, _ in trip), [s for _, _, s in trip])
+
+    if kind == "fct":
+        pta, plan = emu_api.fct_step_fused(L, gf, GC.KJPT, opt["h"], opt["v"], lin, isf, 1, lbc, fold, True, tma=True)
+        assert plan["used_tma"]
+    else:
+        xind = None
+        if opt.get("ld_msc_ups"):
+            w.doms[0].set_fields(*[gf[k] for k in ("tmask", "umask", "vmask", "wmask", "e3t_b", "e3t_n", "e3t_a", "e1e2t", "r1_e1e2t",
+                                                   "mikt", "mbkt")])
+            xind = w.doms[0].mus_xind(True, extra["rnfmsk"], extra["rnfmsk_z"])
+        plan = emu_api.mus_plan(L, 0, GC.G, GC.GJ, fold)
+        pta = gf["pta"].copy()
+        zwx, zwy, fx, fy = (np.zeros(pta.shape) for _ in range(4))
+        for region, kern in (("inner", 2), ("grad", 0)):
+            for rc in plan[region]:
+                emu_api.mus(L, kern, rc, 1, gf, extra, xind, pta, zwx, zwy, fx, fy, lin, isf, GC.KJPT)
+        lbc([(zwx, "U", -1.0), (zwy, "V", -1.0)])
+        for rc in plan["hflux"]:
+            emu_api.mus(L, 1, rc, 1, gf, extra, xind, pta, zwx, zwy, fx, fy, lin, isf, GC.KJPT)
+        lbc([(fx, "U", -1.0), (fy, "V", -1.0)])
+        for rc in plan["trend"]:
+            emu_api.mus(L, 3, rc, 1, gf, extra, xind, pta, zwx, zwy, fx, fy, lin, isf, GC.KJPT)
+    w.close()
+    _check(name, {"pta": pta})
