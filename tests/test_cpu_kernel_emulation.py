@@ -349,3 +349,44 @@ def test_fct_fused_schedule_tma_with_jk_chunks(emu):
     w.close()
     assert plan["used_tma"]
     assert np.array_equal(pta, ref)
+
+
+@pytest.mark.parametrize("K", [3, 4, 5])
+def test_fused_and_reference_schedules_at_tiny_jpk(emu, K):
+    """jpk = 3 is the smallest the ABI accepts: one level pair in the rings and pipelines"""
+    G, GJ, kjpt = 26, 22, 2
+    for jperio in (0, 4):
+        gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=5 + K)
+        w = O.World(G, GJ, K, jperio, 1, 1)
+
+        def lbc(trip):
+            w.lbc_lnk([[a.reshape(-1, GJ, G)] for a, _, _ in trip], "".join(n for _, n, _ in trip), [s for _, _, s in trip])
+
+        for (h, v) in ((2, 2), (4, 4)):
+            ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v)
+            fused, _ = emu_api.fct_step_fused(emu, gf, kjpt, h, v, False, False, 1, lbc, jperio == 4, True, tma=True)
+            plain, _ = emu_api.fct_step(emu, gf, kjpt, h, v, False, False, 1, lbc)
+            assert np.array_equal(fused, ref) and np.array_equal(plain, ref), (K, jperio, h, v)
+        w.close()
+
+
+def test_fused_schedule_random_shapes(emu):
+    """seeded sweep: random subdomain shapes, boundary types, orders, options, split / TMA choices"""
+    rng = np.random.default_rng(2024)
+    for it in range(10):
+        G, GJ = int(rng.integers(20, 72)), int(rng.integers(20, 52))
+        jperio = int(rng.choice([0, 1, 2, 3, 4, 5, 6, 7]))
+        K, kjpt = int(rng.integers(3, 9)), int(rng.integers(1, 4))
+        h, v = int(rng.choice([2, 4])), int(rng.choice([2, 4]))
+        lin = bool(rng.integers(0, 2)); isf = lin and bool(rng.integers(0, 2))
+        split, tma, from_t = bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=3000 + it, ln_linssh=lin, ln_isfcav=isf)
+        w = O.World(G, GJ, K, jperio, 1, 1)
+
+        def lbc(trip):
+            w.lbc_lnk([[a.reshape(-1, GJ, G)] for a, _, _ in trip], "".join(n for _, n, _ in trip), [s for _, _, s in trip])
+
+        ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v, ln_linssh=lin, ln_isfcav=isf)
+        pta, plan = emu_api.fct_step_fused(emu, gf, kjpt, h, v, lin, isf, 1, lbc, jperio in (3, 4, 5, 6), from_t, want_split=split, tma=tma)
+        w.close()
+        assert np.array_equal(pta, ref), (G, GJ, jperio, K, kjpt, h, v, lin, isf, split, tma, from_t)
