@@ -49,6 +49,10 @@ def _worker(rank, world, port, cases, out):
         refg, refl_fct, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, ni, nj, KJPT, 4, 4)
         got, _ = emu_api.fct_step(L, loc, KJPT, 4, 4, False, False, 2, lbc)
         ok = ok and bool(np.array_equal(got, refl_fct[rank]))
+        if jpi >= 20 and jpj >= 20:
+            # the fused schedule as run_fct launches it with real neighbours: band split, TMA tiles where jpi is even
+            got, plan = emu_api.fct_step_fused(L, loc, KJPT, 4, 4, False, False, 1, lbc, me.npolj != 0, True, want_split=True, tma=True)
+            ok = ok and bool(np.array_equal(got, refl_fct[rank]))
         # ---- tra_adv_mus, reference structure (run_mus, schedule 0) ----
         _, refl = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, ni, nj, KJPT)
         pta = loc["pta"].copy()
@@ -90,7 +94,7 @@ def test_two_rank_fct_muscl_and_tra_nxt_steps_over_gloo():
     import emu_api
     from test_cpu_gloo_exchange import _free_port
     emu_api.load()                                              # build libemu.so once, before the workers start
-    cases = [(30, 24, 0, 2, 1), (30, 24, 4, 2, 1), (30, 24, 6, 1, 2), (30, 24, 1, 2, 1)]
+    cases = [(30, 24, 0, 2, 1), (30, 24, 4, 2, 1), (30, 24, 6, 1, 2), (30, 24, 1, 2, 1), (44, 24, 4, 2, 1), (26, 42, 6, 1, 2)]
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
