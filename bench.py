@@ -217,7 +217,7 @@ def main():
     part = BF.best_partition(world)
     dom = N.mpp_init(G, GJ, K, jperio, part[0], part[1], rank + 1)
     ctx = N.FctContext(dom, local_rank)
-    sched = 2 if args.schedule is None else args.schedule
+    sched = 4 if args.schedule is None else args.schedule
     ctx.set_schedule(sched)
     if world > 1:
         idt = torch.zeros(N.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
@@ -317,6 +317,7 @@ def main():
     kbytes = {
         "interp_4th_cpt": a3 * (2 * kjpt) + a3 * 2,                                    # r ptn; w ztw; r wmask, zwt
         "fct_low_antidiff_inner": a3 * ((3 + 5 + (1 if v == 4 else 0)) * kjpt) + a3 * 7,   # r ptb ptn pta [ztw]; w pta zwi zwx zwy zwz; r pun pvn pwn e3t_b/n/a tmask
+        "fct_fused": a3 * ((3 + 1 + (1 if v == 4 else 0)) * kjpt) + a3 * 7,            # r ptb ptn pta [ztw]; w pta; r pun pvn pwn e3t_b/n/a tmask
         "fct_nonosc_final": a3 * ((6 + 1) * kjpt) + a3 * 2,                            # r ptb zwi zwx zwy zwz pta; w pta; r tmask e3t_n
         "mus_inner": a3 * (3 * kjpt) + a3 * 11,                                        # r ptb pta; w pta; r pun pvn pwn e3u e3v e3w e3t tmask umask vmask wmask
         "tra_nxt": a3 * (5 * kjpt) + a3 * 3,

@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff_inner(const FctAr
     const int ktop = a.ln_linssh ? (a.ln_isfcav ? a.mikt[c2] : 1) : 0;     // level whose top flux is pwn*ptb (:146-156)
     const double p2dt = a.p2dt;
     const double r1_6 = 1.0 / 6.0;
+    // schedule 4: the columns of a.out get their whole trend from k_fct_fused; this launch only feeds the frame chain there
+    const bool skip_pta = ji >= a.out.i0 && ji <= a.out.i1 && jj >= a.out.j0 && jj <= a.out.j1;
 
     auto slot = [&](int lev, int f) -> double * { return pf_smem + ((size_t)((lev % kPfStages) * F_LOW_COUNT + f) * kThreads + threadIdx.x); };
     auto issue = [&](int lev) {                          // own-column values of level `lev`
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff_inner(const FctAr
         const double upy_s = 0.5 * (zfp * tb_s + zfm * tb_c);
         const double upz_kp1 = upw(k + 1, w_p, tb_p, tb_c, wm_p);
         const double ztra = -(upx_c - upx_w + upy_c - upy_s + upz_k - upz_kp1) * r1;
-        pta[o] = ta_c + ztra / e3n * tm;
+        if (!skip_pta) pta[o] = ta_c + ztra / e3n * tm;
         zwi[o] = (e3b * tb_c + p2dt * ztra) / e3a * tm;
         if (H == 2) {
             zwx[o] = 0.5 * u_c * (tn_c + tn_e) - upx_c;

@@ -16,6 +16,7 @@
 #include <cudaTypedefs.h>
 
 #include <atomic>
+#include <cstring>
 
 namespace nemo {
 
@@ -73,6 +74,8 @@ __device__ __forceinline__ void mbar_init_fence()
 }
 
 #include "fct_tma_kernel.cuh"     // tile geometry, TileMaps, k_fct_low_antidiff_tma
+
+#include "fct_fused_kernel.cuh"   // k_fct_fused: P1-P8 in one kernel (schedule 4)
 
 // ---- TMA-fed variant of the fused nonosc + final kernel ---------------------------------------------------------
 // Same tile, same arithmetic; the six streamed arrays (ptb, zwi, tmask, zwz of level jk+1; zwx, zwy of level jk) arrive
@@ -317,6 +320,49 @@ bool launch_fct_nonosc_final_tma(const FctArgs &a, cudaStream_t s)
     k_fct_nonosc_final_tma<<<g, NX * NY, smem, s>>>(a, tm);
     note_launch();
     return true;
+}
+
+bool prepare_fct_fused(const FctArgs &a, TmaMapCache *cache)
+{
+    const int ni = a.out.i1 - a.out.i0 + 1, nj = a.out.j1 - a.out.j0 + 1;
+    if (ni <= 0 || nj <= 0) return false;
+    // 16-byte global strides, even box origins >= 0, masks as tmask products (the kernel derives umask/vmask/wmask)
+    if ((a.jpi & 1) || !(a.out.i0 & 1) || a.out.i0 - 1 - FHALO - 2 < 0 || a.out.j0 - 1 - FHALO - 1 < 0 || a.jpk < 3 || !a.masks_from_t) return false;
+    static_assert(sizeof(FusedMaps) == 11 * 128, "tensor-map cache size");
+    const void *key[12] = {a.ptb, a.ptn, a.tmask, a.pun, a.pvn, a.pta, a.kn_fct_v == 4 ? a.ztw : a.pta, a.pwn, a.e3t_b, a.e3t_n, a.e3t_a, nullptr};
+    const int dims[4] = {a.jpi, a.jpj, a.jpk, a.kjpt};
+    if (!cache->valid || memcmp(cache->key, key, sizeof key) || memcmp(cache->dims, dims, sizeof dims)) {
+        FusedMaps tm;
+        const long long n4 = (long long)a.jpk * a.kjpt, n3 = a.jpk;
+        const double *hb[FH_COUNT] = {a.ptb, a.ptn, a.tmask, a.pun, a.pvn};
+        const long long hn[FH_COUNT] = {n4, n4, n3, n3, n3};
+        const double *pb[FP_COUNT] = {a.pta, a.kn_fct_v == 4 ? a.ztw : a.pta, a.pwn, a.e3t_b, a.e3t_n, a.e3t_a};
+        const long long pn[FP_COUNT] = {n4, n4, n3, n3, n3, n3};
+        bool ok = true;
+        for (int q = 0; q < FH_COUNT && ok; ++q) ok = make_tile_map(&tm.h[q], hb[q], a.jpi, a.jpj, hn[q], FBW, FBH);
+        for (int q = 0; q < FP_COUNT && ok; ++q) ok = make_tile_map(&tm.p[q], pb[q], a.jpi, a.jpj, pn[q], FX, FY);
+        if (!ok) return false;
+        memcpy(cache->maps, &tm, sizeof tm);
+        memcpy(cache->key, key, sizeof key); memcpy(cache->dims, dims, sizeof dims);
+        cache->valid = true;
+    }
+    return true;
+}
+
+void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache)
+{
+    const int ni = a.out.i1 - a.out.i0 + 1, nj = a.out.j1 - a.out.j0 + 1;
+    FusedMaps tm;
+    memcpy(&tm, cache->maps, sizeof tm);
+    const dim3 g((unsigned)(((ni + FOX - 1) / FOX) * a.kjpt), (unsigned)((nj + FOY - 1) / FOY), (unsigned)a.nkchunk);
+#define LFU(H, V) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_fused<H, V>, kFusedSmemBytes, done); \
+                       k_fct_fused<H, V><<<g, FX * FY, kFusedSmemBytes, s>>>(a, tm); } while (0)
+    if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LFU(2, 2);
+    else if (a.kn_fct_h == 2)               LFU(2, 4);
+    else if (a.kn_fct_v == 2)               LFU(4, 2);
+    else                                    LFU(4, 4);
+#undef LFU
+    note_launch();
 }
 
 void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s)

@@ -65,6 +65,19 @@ void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s);
 // same, streamed arrays through a 2-stage TMA ring; false if TMA cannot be used
 bool launch_fct_nonosc_final_tma(const FctArgs &a, cudaStream_t s);
 
+// schedule 4, inner region: the whole step (P1-P8) in ONE kernel on the rectangle a.out -- no intermediate array in HBM.
+// The 11 tensor maps depend only on (pointers, shape): they are encoded once and kept in `cache` (one per context).
+struct TmaMapCache {
+    bool valid = false;
+    const void *key[12] = {};
+    int dims[4] = {};
+    alignas(64) unsigned char maps[11 * 128];
+};
+// prepare: false if the TMA path cannot be used (odd jpi, even out.i0, masks not derived from tmask, unaligned arrays, no
+// driver entry point) -- nothing has been launched then and the caller falls back to the three-kernel schedule
+bool prepare_fct_fused(const FctArgs &a, TmaMapCache *cache);
+void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache);
+
 // interp_4th_cpt                                                            traadv_fct.F90:517-616
 void launch_cpt_pivots(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt,
                        int ln_isfcav, double *zwt, cudaStream_t s);

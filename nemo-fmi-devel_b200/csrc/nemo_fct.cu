@@ -146,7 +146,8 @@ struct nemo_fct_ctx {
     std::vector<nemo_fct_ctx *> group;                                 // in-process communicator (incl. self)
     void *nccl_comm = nullptr; int nccl_nranks = 0;
     long long n_exchanges = 0, bytes_sent = 0;
-    int schedule = 2;                                                  // fused inner kernels with TMA tiles where possible
+    int schedule = 4;                                                  // 4: whole step fused in one kernel where possible; 2: three TMA-tiled kernels
+    TmaMapCache fused_maps;                                            // schedule 4: tensor maps of k_fct_fused, encoded once per (pointers, shape)
     // per-kernel CUDA-event timing (bench.py's roofline): off by default
     bool profiling = false;
     struct ProfRec { int id; cudaEvent_t a, b; };
@@ -160,11 +161,11 @@ typedef nemo_fct_ctx Ctx;
 // per-kernel timing with CUDA events on the launching stream
 // ------------------------------------------------------------------------------------------------------------
 enum ProfId { P_LAPLACIAN = 0, P_CPT, P_LOW_ANTIDIFF, P_BETAS, P_LIMIT, P_FINAL, P_LOW_INNER, P_NONOSC_FINAL, P_PACK, P_MOVE, P_UNPACK,
-              P_MUS_GRAD, P_MUS_HFLUX, P_MUS_TREND, P_MUS_INNER, P_NXT, P_CEN, P_COUNT };
+              P_MUS_GRAD, P_MUS_HFLUX, P_MUS_TREND, P_MUS_INNER, P_NXT, P_CEN, P_FUSED, P_COUNT };
 static_assert(P_COUNT <= 24, "prof_ms / prof_calls too small");
 static const char *kProfName[P_COUNT] = {"fct_laplacian", "interp_4th_cpt", "fct_low_antidiff", "fct_betas", "fct_limit",
                                          "fct_final", "fct_low_antidiff_inner", "fct_nonosc_final", "lbc_pack", "lbc_move_nccl", "lbc_fill_unpack",
-                                         "mus_grad", "mus_hflux", "mus_trend", "mus_inner", "tra_nxt", "tra_adv_cen"};
+                                         "mus_grad", "mus_hflux", "mus_trend", "mus_inner", "tra_nxt", "tra_adv_cen", "fct_fused"};
 struct ProfScope {
     nemo_fct_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int id;
     static cudaEvent_t get(nemo_fct_ctx *c) {
@@ -441,6 +442,16 @@ static int pick_nkchunk(const Ctx *c, int kjpt)
     return (int)n;
 }
 
+// k_fct_fused runs one 512-thread block per SM: split the jk loop when the tiles alone do not fill the machine twice
+static int pick_fused_nkchunk(const Ctx *c, int kjpt, const Rect &out)
+{
+    const long long tiles = (long long)((out.i1 - out.i0 + 28) / 28) * ((out.j1 - out.j0 + 12) / 12) * kjpt;
+    if (tiles <= 0) return 1;
+    long long n = (2 * 148 + tiles - 1) / tiles;
+    const int kmax = std::max(1, (c->dom.jpk - 1) / 12);               // >= 12 levels per chunk (each chunk recomputes 2+2 levels)
+    return (int)std::max(1LL, std::min<long long>(n, kmax));
+}
+
 static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, double p2dt, int kjpt, int h, int v)
 {
     const int ng = (int)g.size();
@@ -548,7 +559,15 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     // on the main stream (what matters at N > 1, where each exchange costs an NCCL round trip).
     // Without a real neighbour (single subdomain) the exchanges are local copies and the split only costs (thin bands
     // coalesce badly): keep K1 whole there.
-    bool split = g[0]->nccl_nranks > 1 || ng > 1;
+    // Schedule 4: the whole step of the inner rectangle K2 runs in ONE kernel (k_fct_fused) straight from the inputs; the
+    // band of K1 then only feeds the frame chain (it leaves pta alone inside K2's rectangle) and nothing on the main stream
+    // waits for the side stream except the end of the step.
+    bool one_kernel = g[0]->schedule >= 4;
+    for (int m = 0; m < ng && one_kernel; ++m) {
+        k2[m].nkchunk = pick_fused_nkchunk(g[m], kjpt, k2[m].out);
+        one_kernel = fct_fused_plan(g[m]->dom.jpi, g[m]->dom.jpj, g[m]->dom.npolj != 0, true).split && prepare_fct_fused(k2[m], &g[m]->fused_maps);
+    }
+    bool split = g[0]->nccl_nranks > 1 || ng > 1 || one_kernel;
     std::vector<FctArgs> k1b(k1), k1c(k1);
     for (int m = 0; m < ng && split; ++m) {
         const FctFusedPlan fp = fct_fused_plan(g[m]->dom.jpi, g[m]->dom.jpj, g[m]->dom.npolj != 0, true);
@@ -556,12 +575,14 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         k1b[m].reg = fp.k1_band;
         k1b[m].nkchunk = std::max(1, std::min(8, (g[m]->dom.jpk - 1) / 8));
         k1c[m].reg = fp.k1_centre;
+        if (one_kernel) k1b[m].out = fp.k2_out;
     }
     if (!split) k1c = k1;
 
     if (v == 4) CPT();                                                                             // ztw, whole interior
     CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
-    EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1c[m], c->stream))) launch_fct_low_antidiff_inner(k1c[m], c->stream));
+    if (one_kernel) { EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps)); }
+    else EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1c[m], c->stream))) launch_fct_low_antidiff_inner(k1c[m], c->stream));
     if (!split) CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
     // frame
     to_side();
@@ -585,8 +606,10 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     EACH(P_FINAL, launch_fct_final(fin[m], c->stream));
     CU(cudaEventRecord(g[0]->ev_t, side));
     to_main();
-    if (split) CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_k1, 0));                                 // K2 reads the band as well
-    EACH(P_NONOSC_FINAL, if (!(c->schedule >= 3 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
+    if (!one_kernel) {
+        if (split) CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_k1, 0));                             // K2 reads the band as well
+        EACH(P_NONOSC_FINAL, if (!(c->schedule == 3 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
+    }
     CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_t, 0));
 #undef EACH
 #undef CPT
@@ -995,7 +1018,7 @@ int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int n
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule)
 {
     if (!h) return fail("NULL handle");
-    if (schedule < 0 || schedule > 3) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
+    if (schedule < 0 || schedule > 4) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
     for (Ctx *o : h->group) o->schedule = schedule;
     return 0;
 }

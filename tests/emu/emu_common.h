@@ -26,6 +26,7 @@
 struct EmuIdx { unsigned x, y, z; };
 static thread_local EmuIdx blockIdx, threadIdx, blockDim, gridDim;      // thread_local: emu_block.h runs one host thread per CUDA thread
 using std::min;
+using std::max;
 #define NEMO_EMU_KERNELS_ONLY 1
 
 // walk the launch grid of a column kernel serially: blockIdx.x = column block, .y = jk chunk, .z = tracer

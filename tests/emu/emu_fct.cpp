@@ -17,6 +17,10 @@ template <int N> inline void cp_async_wait() {}
 
 extern "C" {
 
+// schedule 4: rectangle inside which the band launch of k_fct_low_antidiff_inner leaves pta alone (FctArgs::out); empty = none
+static int g_skip_rect[4] = {0, -1, 0, -1};
+void emu_fct_set_skip_rect(int i0, int i1, int j0, int j1) { g_skip_rect[0] = i0; g_skip_rect[1] = i1; g_skip_rect[2] = j0; g_skip_rect[3] = j1; }
+
 // which: 0 laplacian, 1 low_antidiff, 2 betas, 3 limit, 4 final, 5 trend-diagnostic hook, 6 low_antidiff_inner (fused P1-P5).
 // arrays: tmask umask vmask wmask e3t_b e3t_n e3t_a e1e2t r1_e1e2t | pun pvn pwn ptb ptn pta | zwi zwx zwy zwz zltu zltv ztw zbetup zbetdo
 //         | trdx trdy trdz (hook only) | zlx zly zlz (frame of the fused schedules: limited fluxes kept apart, else NULL)
@@ -27,6 +31,7 @@ int emu_fct(int which, int jpi, int jpj, int jpk, int kjpt, int h, int v, int ln
     FctArgs a;
     std::memset(&a, 0, sizeof a);
     a.reg = Region(); a.reg.add(rect[0], rect[1], rect[2], rect[3]);
+    a.out = Rect{g_skip_rect[0], g_skip_rect[1], g_skip_rect[2], g_skip_rect[3]};
     a.jpi = jpi; a.jpj = jpj; a.jpk = jpk; a.jpij = (size_t)jpi * jpj; a.n3 = a.jpij * jpk;
     a.tmask = arr[0]; a.umask = arr[1]; a.vmask = arr[2]; a.wmask = arr[3]; a.e3t_b = arr[4]; a.e3t_n = arr[5]; a.e3t_a = arr[6];
     a.e1e2t = arr[7]; a.r1_e1e2t = arr[8]; a.mikt = mikt; a.mbkt = mbkt;

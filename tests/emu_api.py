@@ -102,6 +102,58 @@ def nonosc_final(L, f, work, kjpt, out_rect):
     assert ret == 0
 
 
+def fct_fused(L, out, nk, f, work, kjpt, h, v, lin, isf, masks_from_t):
+    """the one-kernel step k_fct_fused on the output rectangle `out`, in place on work['pta'].  Returns -1 where the product
+    falls back to the three-kernel schedule, else the number of violated TMA box rules: must be 0"""
+    jpk, jpj, jpi = f["tmask"].shape
+    tab = (C.c_void_p * len(FCT_ARRAYS))()
+    for n, name in enumerate(FCT_ARRAYS):
+        a = work.get(name) if name in work else f.get(name)
+        tab[n] = None if a is None else a.ctypes.data
+    L.emu_fct_fused.restype = C.c_int
+    return L.emu_fct_fused(jpi, jpj, jpk, kjpt, h, v, int(lin), int(isf), rect(*out), nk, C.c_double(f["p2dt"]), tab,
+                           p(f["mikt"]), p(f["mbkt"]), int(masks_from_t))
+
+
+def fct_step_one_kernel(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, nk_fused=1):
+    """tra_adv_fct in schedule 4 (run_fct): k_fct_fused on K2's rectangle straight from the inputs; the band of K1 (which
+    leaves pta alone inside that rectangle) and the frame chain with X1..X4 as in the other fused schedules.  Returns
+    (pta, plan) or (None, plan) where the product falls back (no split possible, odd jpi)."""
+    import numpy as np
+    jpk, jpj, jpi = f["tmask"].shape
+    shp = (kjpt, jpk, jpj, jpi)
+    plan = fct_fused_plan(L, jpi, jpj, fold, True)
+    if not plan["split"] or jpi % 2:
+        return None, plan
+    work = {k: np.zeros(shp) for k in ("zwi", "zwx", "zwy", "zwz", "zltu", "zltv", "ztw", "zbetup", "zbetdo", "zlx", "zly", "zlz")}
+    work["pta"] = f["pta"].copy()
+    frame = {k: v for k, v in work.items() if k not in ("zlx", "zly", "zlz")}
+
+    def on(region, which, w, **kw):
+        for rc in plan[region]:
+            fct(L, which, rc, nk, f, w, kjpt, h, v, lin, isf, **kw)
+
+    if v == 4:
+        interp_4th_cpt(L, f, f["ptn"], work["ztw"], isf)
+    if h == 4:
+        on("lap", 0, frame)
+        lbc([(work["zltu"], "T", 1.0), (work["zltv"], "T", 1.0)])                     # X1
+    on("lowf", 1, frame)
+    L.emu_fct_set_skip_rect(*plan["k2_out"])
+    on("k1_band", 6, frame, masks_from_t=True)
+    L.emu_fct_set_skip_rect(0, -1, 0, -1)
+    lbc([(work["zwi"], "T", 1.0), (work["zwx"], "U", -1.0), (work["zwy"], "V", -1.0), (work["zwz"], "W", 1.0)])   # X2
+    on("bet", 2, frame)
+    lbc([(work["zbetup"], "T", 1.0), (work["zbetdo"], "T", 1.0)])                     # X3
+    on("lim", 3, work)
+    lbc([(work["zlx"], "U", -1.0), (work["zly"], "V", -1.0)])                         # X4 on the limited copies
+    on("fin", 4, work)
+    # the fused kernel is independent of all of the above (main stream): run it last to prove it reads inputs only
+    rc = fct_fused(L, plan["k2_out"], nk_fused, f, frame, kjpt, h, v, lin, isf, True)
+    assert rc == 0, "TMA box origin rule violated / kernel refused: %d" % rc
+    return work["pta"], plan
+
+
 def fct_step_fused(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, masks_from_t, want_split=False, tma=False):
     """tra_adv_fct in the fused schedule (run_fct, schedules 1/2) on one subdomain: fused inner kernels on the regions of
     schedule.hpp, reference-structured kernels on the frame bands with the exchanges X1..X4 through lbc()."""

@@ -103,9 +103,10 @@ def oracle_fct(O, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_li
 
 
 def device_fct(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_linssh=False, ln_isfcav=False,
-               host_path=False, schedule=0, nsteps=1):
+               host_path=False, schedule=0, nsteps=1, kernels=None):
     """Run the product on cuda:0 through the C ABI: single subdomain (jpni = jpnj = 1) or an in-process group of
-    jpni x jpnj subdomains on one GPU.  Returns (global pta, list of local pta)."""
+    jpni x jpnj subdomains on one GPU.  Returns (global pta, list of local pta).  kernels: list that receives the names of
+    the kernels subdomain 0 launched (per-kernel profiling of the library)"""
     from oracle import oracle as O   # only for scatter/gather bookkeeping of the test itself
     w = O.World(jpiglo, jpjglo, jpk, jperio, jpni, jpnj)
     loc = {k: w.scatter(gf[k]) for k in DOM_KEYS + ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
@@ -119,6 +120,8 @@ def device_fct(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_li
         grp = N.LocalGroup(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, 0)
         ctxs = grp.ctx
     ctxs[0].set_schedule(schedule)
+    if kernels is not None:
+        ctxs[0].set_profiling(True)
     for r, c in enumerate(ctxs):
         c.set_domain_arrays(loc["tmask"][r], loc["umask"][r], loc["vmask"][r], loc["wmask"][r], loc["e1e2t"][r],
                             loc["r1_e1e2t"][r], loc["mikt"][r], loc["mbkt"][r], ln_linssh, ln_isfcav)
@@ -141,6 +144,8 @@ def device_fct(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_li
                                 kjpt, h, v)
                 grp.synchronize()
         out = [a.cpu().numpy() for a in t["pta"]]
+    if kernels is not None:
+        kernels.extend(ctxs[0].profile().keys())
     glob = w.gather(out, gf["pta"].copy())
     w.close()
     for c in ctxs:
