@@ -235,6 +235,11 @@ const char *nemo_fct_last_error(void);
 int nemo_fct_abi_version(void);
 /* number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches)                */
 long long nemo_fct_launch_count(void);
+/* Self-test of the inlined IEEE division of the fused kernel (csrc/fct_fused_kernel.cuh: div_rn): n pseudo-random operand
+ * pairs per class (ordinary magnitudes, the FCT ranges 1e-15 .. 1e40, zeros, subnormals, huge, Inf/NaN) are divided on device
+ * `device` by div_rn and by the compiler's x / y; *nbad = number of pairs whose bit patterns differ (NaN payloads aside).
+ * Every REAL(wp) division of traadv_fct.F90 (:164, :166, :394-396, :294) goes through it.                              */
+int nemo_fct_selftest_division(int device, long long n, unsigned long long seed, long long *nbad);
 /* communication report in the spirit of mpp_report (lib_mpp.F90:1471-1587): exchanges and bytes sent so far       */
 int nemo_fct_comm_report(nemo_fct_handle h, long long *n_exchanges, long long *bytes_sent);
 /* Per-kernel device timing with CUDA events recorded on the launching stream around every launch of this context

@@ -121,6 +121,7 @@ def lib():
         "nemo_fct_set_profiling": [vp, i],
         "nemo_fct_profile_read": [vp, i, C.c_char_p, i, dp, C.POINTER(C.c_longlong)],
         "nemo_fct_abi_version": [],
+        "nemo_fct_selftest_division": [i, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)          # AttributeError here == a declared symbol is not exported
@@ -142,7 +143,7 @@ ABI_SYMBOLS = (
     "nemo_fct_set_trend_diag "
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
-    "nemo_fct_profile_read").split()
+    "nemo_fct_profile_read nemo_fct_selftest_division").split()
 
 
 class NxtForcing(C.Structure):
@@ -192,6 +193,14 @@ def _f64(a, what):
     if "float64" not in dt:
         raise TypeError(f"{what}: REAL(wp) arrays are float64, got {dt}")
     return a
+
+
+def selftest_division(n=1 << 22, seed=1, device=0):
+    """the fused kernel's inlined IEEE division against the compiler's x / y on n operand pairs per class; returns the number
+    of results whose bit patterns differ (must be 0)"""
+    nbad = C.c_longlong(-1)
+    _check(lib().nemo_fct_selftest_division(device, n, seed, C.byref(nbad)))
+    return int(nbad.value)
 
 
 def launch_count():

@@ -320,13 +320,15 @@ __global__ void __launch_bounds__(kThreads) k_interp_4th_cpt(int jpi, int jpj, i
                                                              const int *__restrict__ mikt, const int *__restrict__ mbkt,
                                                              const double *__restrict__ zwt, const unsigned char *__restrict__ simple,
                                                              const double *__restrict__ utab, const double *__restrict__ pt_in_all,
-                                                             double *__restrict__ pt_out_all)
+                                                             double *pt_out_all, const Region reg, double *scratch_all)
 {
     int ji, jj;
-    if (!interior_column(jpi, jpj, ji, jj)) return;
+    if (reg.n > 0 ? !region_column(reg, ji, jj) : !interior_column(jpi, jpj, ji, jj)) return;   // reg: only these columns (frame bands)
     const size_t jpij = (size_t)jpi * jpj, n3 = jpij * jpk, c2 = (size_t)(jj - 1) * jpi + (ji - 1);
     const double *__restrict__ pt_in = pt_in_all + (size_t)blockIdx.z * n3;
-    double *__restrict__ pt_out = pt_out_all + (size_t)blockIdx.z * n3;
+    double *pt_out = pt_out_all + (size_t)blockIdx.z * n3;
+    // the forward sweep is parked in `fw`: pt_out itself, or a scratch array when another stream may read pt_out meanwhile
+    double *fw = scratch_all ? scratch_all + (size_t)blockIdx.z * n3 : pt_out;
     const int ikt = mikt[c2] + 1, ikb = mbkt[c2];
     const int jpkm1 = jpk - 1;
     const bool smp = simple && simple[c2] != 0;
@@ -347,14 +349,14 @@ __global__ void __launch_bounds__(kThreads) k_interp_4th_cpt(int jpi, int jpj, i
         else                      { rhs = 3.0 * wm * (t_k + t_km1); wi = wm; }     // (:538-542)
         double z = rhs;
         if (k >= 3) z = rhs - wi / zwt_m * z_m;
-        pt_out[c2 + (size_t)(k - 1) * jpij] = z;
+        fw[c2 + (size_t)(k - 1) * jpij] = z;
         z_m = z; zwt_m = zw; t_km1 = t_k;
     }
     // back substitution (:603-614).  NB pt_out is read back here: the loads below are of levels this thread wrote.
     {
         double x = z_m / zwt_m;                                                    // level jpkm1: still in registers
         pt_out[c2 + (size_t)(jpkm1 - 1) * jpij] = x;
-        const double *rd = pt_out;
+        const double *rd = fw;
         double z_a = rd[c2 + (size_t)(clampk(jpk - 2) - 1) * jpij], z_b = rd[c2 + (size_t)(clampk(jpk - 3) - 1) * jpij];
         p_a = pivot(clampk(jpk - 2)); p_b = pivot(clampk(jpk - 3)); w_a = wmsk(clampk(jpk - 2)); w_b = wmsk(clampk(jpk - 3));
         for (int k = jpk - 2; k >= 2; --k) {

@@ -16,10 +16,24 @@
 //   C  level c = it-2 (output cols)   limits the six fluxes of the cell with the betas published one iteration earlier,
 //                                     applies the final divergence and stores pta
 // so ONE barrier per level orders every shared-memory reuse (zbup/zbdo and the betas are double-buffered by level parity,
-// fx/fy triple-buffered).  Inputs arrive as TMA boxes (cp.async.bulk.tensor.3d, one elected thread) in a 3-stage ring.
+// fx/fy triple-buffered).  The level loop has a steady-state body (all three stages active, every level test resolved at
+// compile time) between a generic prologue and epilogue.  Inputs arrive as TMA boxes (cp.async.bulk.tensor.3d, one elected thread) in a 3-stage ring.
 // Box origins must be >= 0 and even in ji (fp64: 16-byte aligned start, measured on B200): the extended tile starts at an
 // even 0-based column (out.i0 odd), the halo boxes two columns to its west.
+//
+// Arithmetic is the reference's, operation for operation (-fmad=false), with four rewrites that select the same VALUES
+// (they can differ from the CPU restatement only in the sign of a zero, which Fortran's MAX/MIN leave unspecified anyway):
+//  * tmask is verified to hold only 0 and 1, so zbup/zbdo = tmask ? MAX/MIN(pbef, paft) : -/+1e40 with ONE compare for both
+//    instead of 4 multiplies, 6 adds and two compares (:361-364);
+//  * MAX(0,f) / MIN(0,f) of the flux sums (:384-391) and SIGN(0.5,f) of the limiter (:408,414,421) test the sign bit;
+//  * the betas are published already capped, MIN(1,beta): every use is MIN(1, beta_here, beta_next) (:406-407), which then
+//    takes one MIN per face after selecting the two candidates by the sign of the flux;
+//  * the limited flux through the bottom face of level c is kept for the top face of level c+1.
 #pragma once
+
+#ifndef NEMO_NOINLINE
+#define NEMO_NOINLINE __noinline__
+#endif
 
 constexpr int FX = 32, FY = 16, FHALO = 2, FOX = FX - 2 * FHALO, FOY = FY - 2 * FHALO;
 constexpr int FBW = FX + 4, FBH = FY + 3;             // halo box: (pad, 1) west, 2 east; 1 south, 2 north
@@ -33,6 +47,66 @@ constexpr int kFPlanes = 2 + 2 + 3 + 3 + 2 + 2;       // zbup, zbdo (x2), fx, fy
 constexpr size_t kFusedSmemBytes = (size_t)FSTAGES * kFStageBytes + (size_t)kFPlanes * kFPlane * 8 + 64;
 
 struct FusedMaps { CUtensorMap h[FH_COUNT]; CUtensorMap p[FP_COUNT]; };
+
+__device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
+
+// one thread: all TMA boxes of level `lev` into stage lev % FSTAGES (kept out of line: called from every copy of the level loop).
+// The issuing thread sits in the LAST warp of the block: the first and last rows of the tile only run stage A, so the ~150
+// instructions of the descriptor sequence are hidden in that warp's slack instead of delaying a full-work warp at the barrier.
+template <int V>
+__device__ NEMO_NOINLINE void fused_issue_level(unsigned char *fu_smem, unsigned long long *full, const CUtensorMap *mh, const CUtensorMap *mp,
+                                                int lev, int ztracer, int X0, int Y0)
+{
+    unsigned char *st = fu_smem + (size_t)(lev % FSTAGES) * kFStageBytes;
+    unsigned long long *bar = &full[lev % FSTAGES];
+    mbar_expect_tx(bar, FH_COUNT * (FBW * FBH * 8) + (FP_COUNT - (V == 4 ? 0 : 1)) * kFPlainBytes);
+    const int z3 = lev - 1, z4 = ztracer + lev - 1;
+    tma_load_3d(st + FH_PTB * kFHaloBytes, &mh[FH_PTB], bar, X0 - 2, Y0 - 1, z4);
+    tma_load_3d(st + FH_PTN * kFHaloBytes, &mh[FH_PTN], bar, X0 - 2, Y0 - 1, z4);
+    tma_load_3d(st + FH_TM * kFHaloBytes, &mh[FH_TM], bar, X0 - 2, Y0 - 1, z3);
+    tma_load_3d(st + FH_PUN * kFHaloBytes, &mh[FH_PUN], bar, X0 - 2, Y0 - 1, z3);
+    tma_load_3d(st + FH_PVN * kFHaloBytes, &mh[FH_PVN], bar, X0 - 2, Y0 - 1, z3);
+    unsigned char *pl = st + FH_COUNT * kFHaloBytes;
+    tma_load_3d(pl + FP_PTA * kFPlainBytes, &mp[FP_PTA], bar, X0, Y0, z4);
+    if (V == 4) tma_load_3d(pl + FP_ZTW * kFPlainBytes, &mp[FP_ZTW], bar, X0, Y0, z4);
+    tma_load_3d(pl + FP_PWN * kFPlainBytes, &mp[FP_PWN], bar, X0, Y0, z3);
+    tma_load_3d(pl + FP_E3B * kFPlainBytes, &mp[FP_E3B], bar, X0, Y0, z3);
+    tma_load_3d(pl + FP_E3N * kFPlainBytes, &mp[FP_E3N], bar, X0, Y0, z3);
+    tma_load_3d(pl + FP_E3A * kFPlainBytes, &mp[FP_E3A], bar, X0, Y0, z3);
+}
+
+// IEEE-754 x / y (round to nearest).  This is the fast path of the compiler's own division, instruction for instruction
+// (MUFU.RCP64H seed with the low word set to 1, two Newton steps, quotient, one residual correction, the same two validity
+// tests on the high words), written inline so that it carries no call frame in the hot loop; when the tests fail (tiny / huge /
+// non-finite operands, zero numerator) the operands go to the ordinary division.  Split in two so that a divisor shared by
+// several quotients (a pivot of the compact scheme, say) is refined once: div_rn(x, y) == div_by(x, y, rcp_refined(y)).
+#ifndef NEMO_EMU_KERNELS_ONLY
+__device__ __forceinline__ double rcp_refined(double y)
+{
+    double seed;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(y));
+    double r = __hiloint2double(__double2hiint(seed), 1);
+    double e = fma(-y, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-y, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double div_by(double x, double y, double r)
+{
+    double q = x * r;
+    const double rem = fma(-y, q, x);
+    q = fma(r, rem, q);
+    const float xh = __int_as_float(__double2hiint(x)), yh = __int_as_float(__double2hiint(y)), qh = __int_as_float(__double2hiint(q));
+    const bool ok = !(fabsf(xh) < 6.5827683646048100446e-37f) && fabsf(fmaf(0.0f, yh, qh)) > 1.469367938527859385e-39f;
+    if (!ok) q = (x == 0.0 && y != 0.0 && fabs(y) <= 1.7976931348623157e308) ? x * y : x / y;     // +-0 / finite = +-0 without the slow path
+    return q;
+}
+#else
+inline double rcp_refined(double) { return 0.0; }
+inline double div_by(double x, double y, double) { return x / y; }
+#endif
+__device__ __forceinline__ double div_rn(double x, double y) { return div_by(x, y, rcp_refined(y)); }
 
 template <int H, int V>
 __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const __grid_constant__ FusedMaps maps)
@@ -56,7 +130,10 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
     const int lastlev = min(jpk, a_hi + 1);                             // last level whose boxes are loaded
     const int gi = X0 + tx + 1, gj = Y0 + ty + 1;                       // 1-based column of this thread
     const bool is_out = tx >= FHALO && tx < FX - FHALO && ty >= FHALO && ty < FY - FHALO && gi <= a.out.i1 && gj <= a.out.j1;
-    const bool is_beta = tx >= 1 && tx < FX - 1 && ty >= 1 && ty < FY - 1;
+    // Stages B and C are entered per ROW (warp-uniform): the lanes outside the ring / output columns compute on neighbouring
+    // cells' finite values and their results are never read (B) or never stored (C)
+    const bool row_beta = ty >= 1 && ty < FY - 1;
+    const bool row_out = ty >= FHALO && ty < FY - FHALO && gj <= a.out.j1;
     const int ci = min(gi, jpi), cj = min(gj, a.jpj);                   // tiles overhang the rectangle: keep addresses legal
     const size_t toff = (size_t)jn * a.n3;
     const size_t c2 = (size_t)(cj - 1) * jpi + (ci - 1);
@@ -64,38 +141,13 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
     const double r1 = a.r1_e1e2t[c2], e12 = a.e1e2t[c2];
     const int ktop = a.ln_linssh ? (a.ln_isfcav ? a.mikt[c2] : 1) : 0; // level whose top flux is pwn*ptb (:146-156)
     const double p2dt = a.p2dt;
-    const double r1_6 = 1.0 / 6.0, zrtrn = 1.e-15;
+    const double r1_6 = 1.0 / 6.0, zrtrn = 1.e-15, zbig = 1.e+40;
 
     const CUtensorMap *mh = maps.h, *mp = maps.p;                       // descriptor addresses stay in the parameter space
-    auto issue = [=](int lev) {                                         // one thread: all boxes of level `lev`
-        unsigned char *st = fu_smem + (size_t)(lev % FSTAGES) * kFStageBytes;
-        unsigned long long *bar = &full[lev % FSTAGES];
-        mbar_expect_tx(bar, FH_COUNT * (FBW * FBH * 8) + (FP_COUNT - (V == 4 ? 0 : 1)) * kFPlainBytes);
-        const int z3 = lev - 1, z4 = jn * jpk + lev - 1;
-        tma_load_3d(st + FH_PTB * kFHaloBytes, &mh[FH_PTB], bar, X0 - 2, Y0 - 1, z4);
-        tma_load_3d(st + FH_PTN * kFHaloBytes, &mh[FH_PTN], bar, X0 - 2, Y0 - 1, z4);
-        tma_load_3d(st + FH_TM * kFHaloBytes, &mh[FH_TM], bar, X0 - 2, Y0 - 1, z3);
-        tma_load_3d(st + FH_PUN * kFHaloBytes, &mh[FH_PUN], bar, X0 - 2, Y0 - 1, z3);
-        tma_load_3d(st + FH_PVN * kFHaloBytes, &mh[FH_PVN], bar, X0 - 2, Y0 - 1, z3);
-        unsigned char *pl = st + FH_COUNT * kFHaloBytes;
-        tma_load_3d(pl + FP_PTA * kFPlainBytes, &mp[FP_PTA], bar, X0, Y0, z4);
-        if (V == 4) tma_load_3d(pl + FP_ZTW * kFPlainBytes, &mp[FP_ZTW], bar, X0, Y0, z4);
-        tma_load_3d(pl + FP_PWN * kFPlainBytes, &mp[FP_PWN], bar, X0, Y0, z3);
-        tma_load_3d(pl + FP_E3B * kFPlainBytes, &mp[FP_E3B], bar, X0, Y0, z3);
-        tma_load_3d(pl + FP_E3N * kFPlainBytes, &mp[FP_E3N], bar, X0, Y0, z3);
-        tma_load_3d(pl + FP_E3A * kFPlainBytes, &mp[FP_E3A], bar, X0, Y0, z3);
-    };
-    auto upw = [&](int k, double w, double tb_k, double tb_km1, double wm) -> double {      // P2 + P2b (:137-156)
-        double v = 0.0;
-        if (k >= 2 && k <= jpk - 1) {
-            const double zfp_wk = w + fabs(w), zfm_wk = w - fabs(w);
-            v = 0.5 * (zfp_wk * tb_k + zfm_wk * tb_km1) * wm;
-        }
-        if (k == ktop) v = w * tb_k;
-        return v;
-    };
+    auto issue = [=](int lev) { fused_issue_level<V>(fu_smem, full, mh, mp, lev, jn * jpk, X0, Y0); };
+    const bool issuer = threadIdx.x == (FY - 1) * FX;                  // lane 0 of the last warp
 
-    if (threadIdx.x == 0) {
+    if (issuer) {
         for (int s = 0; s < FSTAGES; ++s) mbar_init(&full[s], 1);
         mbar_init_fence();
         issue(a_lo);
@@ -105,29 +157,38 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
     double tb_m = 0.0, tn_m = 0.0, tm_m = 0.0;          // ptb, ptn, tmask of level a-1
     if (a_lo >= 2) { const size_t om = c2 + (size_t)(a_lo - 2) * jpij; tb_m = a.ptb[toff + om]; tn_m = a.ptn[toff + om]; tm_m = a.tmask[om]; }
     double upz_k = 0.0;                                  // upstream vertical flux through the top of level a
-    bool first = true;
-    double up_b = 0.0, do_b = 0.0, up_bm = 0.0, do_bm = 0.0;            // zbup / zbdo at levels b, b-1
+    // (what a thread published for its own column -- zbup, zbdo, fx, fy, capped betas -- is read back from the shared planes at
+    // the later levels rather than carried: the kernel sits at the 128-register cap)
     double aft_b = 0.0, e3n_b = 1.0, e3n_c = 1.0, pta_b = 0.0, pta_c = 0.0;
-    double fx_b = 0.0, fy_b = 0.0, fz_b = 0.0, fx_c = 0.0, fy_c = 0.0, fz_c = 0.0;   // anti-diffusive fluxes at levels b, c
-    double bup_c = 0.0, bdo_c = 0.0, bup_cm = 0.0, bdo_cm = 0.0;       // betas at levels c, c-1
+    double fz_b = 0.0, fz_c = 0.0;                       // vertical anti-diffusive flux through the top of levels b, c
+    double cu_cm = 0.0, cd_cm = 0.0, cu_b_prev = 0.0, cd_b_prev = 0.0;   // capped betas of level c-1: only read at the first output level of a chunk (generic steps)
+    double lz_t = 0.0;                                   // limited flux through the top face of level c
     const int hc = (ty + 1) * FBW + (tx + 2), pc = ty * FX + tx;
     const int cell = ty * FX + tx;
+    // ring slots of the levels a, b, c (3-deep: TMA stages and fx/fy planes) and their parities (2-deep planes)
+    int ra = a_lo % 3, rb = (a_lo + 2) % 3, rc = (a_lo + 1) % 3;
 
-    for (int it = a_lo; it <= kb + 2; ++it) {
+    // one level step; ST = steady state: max(ka+3, 4) <= it <= min(kb+2, jpk-2): all three stages active on levels >= 2, level
+    // a+1 <= jpk-1, level c past the first output level
+    auto level_step = [&](auto st_tag, const int it) {
+        constexpr bool ST = decltype(st_tag)::value;
         __syncthreads();                                 // every thread is done with iteration it-1: its stage and planes are free
-        if (threadIdx.x == 0 && it + 2 <= lastlev) issue(it + 2);
+        if (issuer && it + 2 <= lastlev) issue(it + 2);
         const int lev_a = it, lev_b = it - 1, lev_c = it - 2;
+        const int pa = (lev_a & 1) * kFPlane, pb = kFPlane - pa;       // parity planes of levels a (= c = b-1) and b
+        const double up_bm = sU[pa + cell], do_bm = sD[pa + cell];     // own zbup / zbdo of level b-1, before stage A reuses the plane
 
         // ---- stage A: level a ----------------------------------------------------------------------------------
         double up_a = 0.0, do_a = 0.0, aft_a = 0.0, e3n_a = 1.0, pta_a = 0.0, fx_a = 0.0, fy_a = 0.0, fz_a = 0.0;
-        if (lev_a <= a_hi) {
-            mbar_wait(&full[lev_a % FSTAGES], ((lev_a - a_lo) / FSTAGES) & 1);
-            const double *sh = reinterpret_cast<const double *>(fu_smem + (size_t)(lev_a % FSTAGES) * kFStageBytes);
+        if (ST || lev_a <= a_hi) {
+            mbar_wait(&full[ra], ((lev_a - a_lo) / FSTAGES) & 1);
+            const double *sh = reinterpret_cast<const double *>(fu_smem + (size_t)ra * kFStageBytes);
             const double *s_tb = sh + FH_PTB * (kFHaloBytes / 8), *s_tm = sh + FH_TM * (kFHaloBytes / 8);
             const double tb_c = s_tb[hc], tm = s_tm[hc];
-            if (lev_a <= jpk - 1) {
-                mbar_wait(&full[(lev_a + 1) % FSTAGES], ((lev_a + 1 - a_lo) / FSTAGES) & 1);
-                const double *sh1 = reinterpret_cast<const double *>(fu_smem + (size_t)((lev_a + 1) % FSTAGES) * kFStageBytes);
+            if (ST || lev_a <= jpk - 1) {
+                const int ra1 = (ra == 2) ? 0 : ra + 1;
+                mbar_wait(&full[ra1], ((lev_a + 1 - a_lo) / FSTAGES) & 1);
+                const double *sh1 = reinterpret_cast<const double *>(fu_smem + (size_t)ra1 * kFStageBytes);
                 const double *sp = sh + FH_COUNT * (kFHaloBytes / 8), *sp1 = sh1 + FH_COUNT * (kFHaloBytes / 8);
                 const double *s_tn = sh + FH_PTN * (kFHaloBytes / 8), *s_u = sh + FH_PUN * (kFHaloBytes / 8), *s_v = sh + FH_PVN * (kFHaloBytes / 8);
                 const double tb_w = s_tb[hc - 1], tb_e = s_tb[hc + 1], tb_s = s_tb[hc - FBW], tb_n = s_tb[hc + FBW];
@@ -137,8 +198,18 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
                 const double e3b = sp[FP_E3B * kFPlane + pc], e3n = sp[FP_E3N * kFPlane + pc], e3a = sp[FP_E3A * kFPlane + pc];
                 const double tb_p = sh1[FH_PTB * (kFHaloBytes / 8) + hc], tm_p = sh1[FH_TM * (kFHaloBytes / 8) + hc];
                 const double w_p = sp1[FP_PWN * kFPlane + pc];
-                const double wm_c = (lev_a == 1) ? tm : tm * tm_m, wm_p = tm_p * tm;       // wmask (dommsk.F90:193)
-                if (first) upz_k = upw(lev_a, w_c, tb_c, tb_m, wm_c);
+                const double wm_c = (!ST && lev_a == 1) ? tm : tm * tm_m, wm_p = tm_p * tm;       // wmask (dommsk.F90:193)
+                // upstream vertical flux through the top face of level k (P2 + P2b, :137-156)
+                auto upw = [&](int k, double w, double tb_k, double tb_km1, double wm) -> double {
+                    double v = 0.0;
+                    if (ST || (k >= 2 && k <= jpk - 1)) {
+                        const double zfp_wk = w + fabs(w), zfm_wk = w - fabs(w);
+                        v = 0.5 * (zfp_wk * tb_k + zfm_wk * tb_km1) * wm;
+                    }
+                    if (k == ktop) v = w * tb_k;
+                    return v;
+                };
+                if (!ST && lev_a == a_lo) upz_k = upw(lev_a, w_c, tb_c, tb_m, wm_c);
                 double zfp, zfm;
                 zfp = u_c + fabs(u_c); zfm = u_c - fabs(u_c);
                 const double upx_c = 0.5 * (zfp * tb_c + zfm * tb_e);
@@ -150,8 +221,8 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
                 const double upy_s = 0.5 * (zfp * tb_s + zfm * tb_c);
                 const double upz_kp1 = upw(lev_a + 1, w_p, tb_p, tb_c, wm_p);
                 const double ztra = -(upx_c - upx_w + upy_c - upy_s + upz_k - upz_kp1) * r1;
-                if (is_out) pta_a = sp[FP_PTA * kFPlane + pc] + ztra / e3n * tm;           // first half of the trend (:165)
-                aft_a = (e3b * tb_c + p2dt * ztra) / e3a * tm;                            // zwi (:167)
+                if (row_out) pta_a = sp[FP_PTA * kFPlane + pc] + div_rn(ztra, e3n) * tm;           // first half of the trend (:165)
+                aft_a = div_rn(e3b * tb_c + p2dt * ztra, e3a) * tm;                            // zwi (:167)
                 if (H == 2) {
                     fx_a = 0.5 * u_c * (tn_c + tn_e) - upx_c;
                     fy_a = 0.5 * v_c * (tn_c + tn_n) - upy_c;
@@ -169,58 +240,82 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
                     fx_a = 0.5 * u_c * (zC2t_u + zltu_c - zltu_e) - upx_c;
                     fy_a = 0.5 * v_c * (zC2t_v + zltv_c - zltv_n) - upy_c;
                 }
-                if (lev_a >= 2) {
+                if (ST || lev_a >= 2) {
                     if (V == 2) fz_a = (w_c * 0.5 * (tn_c + tn_m) - upz_k) * wm_c;
                     else        fz_a = (w_c * sp[FP_ZTW * kFPlane + pc] - upz_k) * wm_c;
                 }
                 e3n_a = e3n;
                 upz_k = upz_kp1; tn_m = tn_c;
             }
-            first = false;
-            bup_bdo(tb_c, aft_a, tm, up_a, do_a);                                          // zbup, zbdo (:361-364); zwi(jpk) = 0
-            sU[(lev_a & 1) * kFPlane + cell] = up_a; sD[(lev_a & 1) * kFPlane + cell] = do_a;
-            sFx[(lev_a % 3) * kFPlane + cell] = fx_a; sFy[(lev_a % 3) * kFPlane + cell] = fy_a;
+            // zbup, zbdo (:361-364) with tmask in {0,1}; zwi(jpk) = 0
+            {
+                const bool gt = tb_c > aft_a, wet = __double2hiint(tm) != 0;
+                up_a = wet ? (gt ? tb_c : aft_a) : -zbig;
+                do_a = wet ? (gt ? aft_a : tb_c) : zbig;
+            }
+            sU[pa + cell] = up_a; sD[pa + cell] = do_a;
+            sFx[ra * kFPlane + cell] = fx_a; sFy[ra * kFPlane + cell] = fy_a;
             tb_m = tb_c; tm_m = tm;
         }
 
-        // ---- stage B: betas of level b (:366-399) ----------------------------------------------------------------
-        double bup_b = 0.0, bdo_b = 0.0;                                                  // zbetup(jpk) = zbetdo(jpk) = 0 (:356)
-        if (lev_b >= b_lo && lev_b <= b_hi && is_beta) {
-            const double *U = sU + (lev_b & 1) * kFPlane + cell, *D = sD + (lev_b & 1) * kFPlane + cell;
-            const double up_m1 = (lev_b == 1) ? up_b : up_bm, do_m1 = (lev_b == 1) ? do_b : do_bm;   // ikm1 = MAX(jk-1,1)
+        // ---- stage B: capped betas of level b (:366-399, MIN(1,.) of :406-407) ------------------------------------
+        double cu_b = 0.0, cd_b = 0.0;                                                    // zbetup(jpk) = zbetdo(jpk) = 0 (:356)
+        if ((ST || (lev_b >= b_lo && lev_b <= b_hi)) && row_beta) {
+            const double *U = sU + pb + cell, *D = sD + pb + cell;
+            const double up_b = U[0], do_b = D[0], fx_b = sFx[rb * kFPlane + cell], fy_b = sFy[rb * kFPlane + cell];
+            const double up_m1 = (!ST && lev_b == 1) ? up_b : up_bm, do_m1 = (!ST && lev_b == 1) ? do_b : do_bm;   // ikm1 = MAX(jk-1,1)
             const double zup = dmax(dmax(dmax(dmax(dmax(dmax(up_b, U[-1]), U[1]), U[-FX]), U[FX]), up_m1), up_a);
             const double zdo = dmin(dmin(dmin(dmin(dmin(dmin(do_b, D[-1]), D[1]), D[-FX]), D[FX]), do_m1), do_a);
-            const double paa_w = sFx[(lev_b % 3) * kFPlane + cell - 1], pbb_s = sFy[(lev_b % 3) * kFPlane + cell - FX];
-            const double zpos = dmax(0., paa_w) - dmin(0., fx_b) + dmax(0., pbb_s) - dmin(0., fy_b)
-                              + dmax(0., fz_a) - dmin(0., fz_b);
-            const double zneg = dmax(0., fx_b) - dmin(0., paa_w) + dmax(0., fy_b) - dmin(0., pbb_s)
-                              + dmax(0., fz_b) - dmin(0., fz_a);
-            const double zbt = e12 * e3n_b / p2dt;
-            bup_b = (zup - aft_b) / (zpos + zrtrn) * zbt;
-            bdo_b = (aft_b - zdo) / (zneg + zrtrn) * zbt;
+            const double paa_w = sFx[rb * kFPlane + cell - 1], pbb_s = sFy[rb * kFPlane + cell - FX];
+            // MAX(0,f) and MIN(0,f) by the sign bit: p = f or 0, n = 0 or f
+            const bool s1 = sign_clear(paa_w), s2 = sign_clear(fx_b), s3 = sign_clear(pbb_s), s4 = sign_clear(fy_b),
+                       s5 = sign_clear(fz_a), s6 = sign_clear(fz_b);
+            const double zpos = (s1 ? paa_w : 0.) - (s2 ? 0. : fx_b) + (s3 ? pbb_s : 0.) - (s4 ? 0. : fy_b)
+                              + (s5 ? fz_a : 0.) - (s6 ? 0. : fz_b);
+            const double zneg = (s2 ? fx_b : 0.) - (s1 ? 0. : paa_w) + (s4 ? fy_b : 0.) - (s3 ? 0. : pbb_s)
+                              + (s6 ? fz_b : 0.) - (s5 ? 0. : fz_a);
+            const double zbt = div_rn(e12 * e3n_b, p2dt);
+            cu_b = dmin(1.0, div_rn(zup - aft_b, zpos + zrtrn) * zbt);
+            cd_b = dmin(1.0, div_rn(aft_b - zdo, zneg + zrtrn) * zbt);
         }
-        if (lev_b >= 1) { sBu[(lev_b & 1) * kFPlane + cell] = bup_b; sBd[(lev_b & 1) * kFPlane + cell] = bdo_b; }
+        if (ST || lev_b >= 1) { sBu[pb + cell] = cu_b; sBd[pb + cell] = cd_b; }
 
         // ---- stage C: limited fluxes and final trend of level c (:404-425, :288-297) -------------------------------
-        if (lev_c >= ka && is_out) {
-            const double *Bu = sBu + (lev_c & 1) * kFPlane + cell, *Bd = sBd + (lev_c & 1) * kFPlane + cell;
-            const double bup_e = Bu[1], bdo_e = Bd[1], bup_w = Bu[-1], bdo_w = Bd[-1];
-            const double bup_n = Bu[FX], bdo_n = Bd[FX], bup_s = Bu[-FX], bdo_s = Bd[-FX];
-            const double paa_w = sFx[(lev_c % 3) * kFPlane + cell - 1], pbb_s = sFy[(lev_c % 3) * kFPlane + cell - FX];
-            const double lx_e = fx_c * limit_coef_sel(fx_c, bdo_c, bup_e, bup_c, bdo_e);
-            const double lx_w = paa_w * limit_coef_sel(paa_w, bdo_w, bup_c, bup_w, bdo_c);
-            const double ly_n = fy_c * limit_coef_sel(fy_c, bdo_c, bup_n, bup_c, bdo_n);
-            const double ly_s = pbb_s * limit_coef_sel(pbb_s, bdo_s, bup_c, bup_s, bdo_c);
-            // pcc(jk+1) is limited with betas(jk), betas(jk+1) (:419-422); pcc(:,:,1) is never limited
-            const double lz_t = (lev_c == 1) ? fz_c : fz_c * limit_coef_sel(fz_c, bdo_c, bup_cm, bup_c, bdo_cm);
-            const double lz_b = fz_b * limit_coef_sel(fz_b, bdo_b, bup_c, bup_b, bdo_c);
-            pta[c2 + (size_t)(lev_c - 1) * jpij] = pta_c - (lx_e - lx_w + ly_n - ly_s + lz_t - lz_b) * r1 / e3n_c;
+        if ((ST || lev_c >= ka) && row_out) {
+            const double *Bu = sBu + pa + cell, *Bd = sBd + pa + cell;
+            const double cu_c = Bu[0], cd_c = Bd[0], fx_c = sFx[rc * kFPlane + cell], fy_c = sFy[rc * kFPlane + cell];
+            const double cu_e = Bu[1], cd_e = Bd[1], cu_w = Bu[-1], cd_w = Bd[-1];
+            const double cu_n = Bu[FX], cd_n = Bd[FX], cu_s = Bu[-FX], cd_s = Bd[-FX];
+            const double paa_w = sFx[rc * kFPlane + cell - 1], pbb_s = sFy[rc * kFPlane + cell - FX];
+            // flux from `here` to `next`: f >= 0 -> MIN(1, zbetdo(here), zbetup(next)), else MIN(1, zbetup(here), zbetdo(next))
+            auto coef = [](double f, double cd_here, double cu_next, double cu_here, double cd_next) -> double {
+                const bool pos = sign_clear(f);
+                return dmin(pos ? cd_here : cu_here, pos ? cu_next : cd_next);
+            };
+            const double lx_e = fx_c * coef(fx_c, cd_c, cu_e, cu_c, cd_e);
+            const double lx_w = paa_w * coef(paa_w, cd_w, cu_c, cu_w, cd_c);
+            const double ly_n = fy_c * coef(fy_c, cd_c, cu_n, cu_c, cd_n);
+            const double ly_s = pbb_s * coef(pbb_s, cd_s, cu_c, cu_s, cd_c);
+            // pcc(jk+1) is limited with betas(jk), betas(jk+1) (:419-422); pcc(:,:,1) is never limited.  The top face of level c
+            // is the bottom face of c-1: kept from the previous step, except at the first output level of the chunk
+            if (!ST && lev_c == ka) lz_t = (lev_c == 1) ? fz_c : fz_c * coef(fz_c, cd_c, cu_cm, cu_c, cd_cm);
+            const double lz_b = fz_b * coef(fz_b, cd_b, cu_c, cu_b, cd_c);
+            const double res = pta_c - div_rn((lx_e - lx_w + ly_n - ly_s + lz_t - lz_b) * r1, e3n_c);
+            if (is_out) pta[c2 + (size_t)(lev_c - 1) * jpij] = res;
+            lz_t = lz_b;
         }
 
         // rotate the column registers: b -> c, a -> b
-        bup_cm = bup_c; bdo_cm = bdo_c; bup_c = bup_b; bdo_c = bdo_b;
-        fx_c = fx_b; fy_c = fy_b; fz_c = fz_b; fx_b = fx_a; fy_b = fy_a; fz_b = fz_a;
-        e3n_c = e3n_b; e3n_b = e3n_a; pta_c = pta_b; pta_b = pta_a;
-        up_bm = up_b; do_bm = do_b; up_b = up_a; do_b = do_a; aft_b = aft_a;
-    }
+        if (!ST) { cu_cm = cu_b_prev; cd_cm = cd_b_prev; cu_b_prev = cu_b; cd_b_prev = cd_b; }
+        fz_c = fz_b; fz_b = fz_a;
+        e3n_c = e3n_b; e3n_b = e3n_a; pta_c = pta_b; pta_b = pta_a; aft_b = aft_a;
+        rc = rb; rb = ra; ra = (ra == 2) ? 0 : ra + 1;
+    };
+
+    const int steady_lo = max(ka + 3, 4), steady_hi = min(kb + 2, jpk - 2);   // the first output level (c = ka) is generic
+    int it = a_lo;
+    for (; it <= kb + 2 && it < steady_lo; ++it) level_step(std::false_type{}, it);
+#pragma unroll 3
+    for (; it <= steady_hi; ++it) level_step(std::true_type{}, it);
+    for (; it <= kb + 2; ++it) level_step(std::false_type{}, it);
 }

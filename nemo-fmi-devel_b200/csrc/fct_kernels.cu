@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <type_traits>
 
 namespace nemo {
 
@@ -75,7 +76,8 @@ __device__ __forceinline__ void mbar_init_fence()
 
 #include "fct_tma_kernel.cuh"     // tile geometry, TileMaps, k_fct_low_antidiff_tma
 
-#include "fct_fused_kernel.cuh"   // k_fct_fused: P1-P8 in one kernel (schedule 4)
+#include "fct_fused_kernel.cuh"   // k_fct_fused: P1-P8 in one kernel (schedule 4); div_rn
+#include "cpt_tiled_kernel.cuh"   // k_interp_4th_cpt_tiled: TMA-fed Thomas solve with the forward sweep in shared memory
 
 // ---- TMA-fed variant of the fused nonosc + final kernel ---------------------------------------------------------
 // Same tile, same arithmetic; the six streamed arrays (ptb, zwi, tmask, zwz of level jk+1; zwx, zwy of level jk) arrive
@@ -195,6 +197,39 @@ __global__ void __launch_bounds__(NX * NY, 2) k_fct_nonosc_final_tma(const FctAr
     }
 }
 
+// ---- self-test of div_rn ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long &x)
+{
+    unsigned long long z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+// a double with random sign and mantissa and an exponent field drawn from [elo, ehi]
+__device__ __forceinline__ double random_double(unsigned long long &st, int elo, int ehi)
+{
+    const unsigned long long r = splitmix64(st), e = (unsigned long long)(elo + (int)(splitmix64(st) % (unsigned)(ehi - elo + 1)));
+    return __longlong_as_double((long long)((r & 0x800fffffffffffffull) | (e << 52)));
+}
+__global__ void k_div_selftest(long long n, unsigned long long seed, unsigned long long *nbad)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long st = seed + 0x1234567ull * (unsigned long long)i;
+    // exponent-field ranges: ordinary; the FCT ranges (1e-15 .. 1e40); near the fast-path limits; subnormal / zero; huge / Inf / NaN
+    const int cls[8][4] = {{900, 1150, 900, 1150}, {970, 1160, 970, 1160}, {1, 120, 900, 1100}, {0, 0, 1, 2046},
+                           {1, 2046, 0, 0}, {1960, 2047, 1, 2047}, {1, 2047, 1960, 2047}, {0, 2047, 0, 2047}};
+    unsigned long long bad = 0;
+    for (int c = 0; c < 8; ++c) {
+        double x = random_double(st, cls[c][0], cls[c][1]), y = random_double(st, cls[c][2], cls[c][3]);
+        if (c == 3 && (i & 3) == 0) x = (i & 4) ? 0.0 : -0.0;
+        if (c == 4 && (i & 3) == 0) y = (i & 4) ? 0.0 : -0.0;
+        const double q1 = div_rn(x, y), q2 = x / y;
+        const bool same = (q1 != q1 && q2 != q2) || __double_as_longlong(q1) == __double_as_longlong(q2);
+        bad += same ? 0 : 1;
+    }
+    if (bad) atomicAdd(nbad, bad);
+}
+
 inline dim3 column_grid(const FctArgs &a)
 {
     const long long ncol = a.reg.ncol();
@@ -217,6 +252,19 @@ static void allow_dynamic_smem(Kernel kernel, size_t smem, bool (&done)[kMaxDevi
     if (known) done[dev] = true;
 }
 
+long long division_selftest(long long n, unsigned long long seed, cudaStream_t s)
+{
+    unsigned long long *d = nullptr, h = 0;
+    if (cudaMalloc(&d, sizeof h) != cudaSuccess) return -1;
+    cudaMemsetAsync(d, 0, sizeof h, s);
+    k_div_selftest<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, seed, d);
+    note_launch();
+    const cudaError_t e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(d);
+    return (e == cudaSuccess && e2 == cudaSuccess) ? (long long)h : -1;
+}
+
 void launch_fct_laplacian(const FctArgs &a, cudaStream_t s)
 {
     k_fct_laplacian<<<column_grid(a), kThreads, 0, s>>>(a); note_launch();
@@ -235,7 +283,7 @@ void launch_fct_low_antidiff(const FctArgs &a, cudaStream_t s)
 void launch_fct_low_antidiff_inner(const FctArgs &a, cudaStream_t s)
 {
     const dim3 g = column_grid(a);
-    const bool ft = a.masks_from_t != 0;
+    const bool ft = (a.masks_from_t & 1) != 0;
     const size_t smem = (size_t)kPfStages * F_LOW_COUNT * kThreads * sizeof(double);   // 33 KB: below the 48 KB opt-in limit
 #define LAI(H, V) (ft ? k_fct_low_antidiff_inner<H, V, true><<<g, kThreads, smem, s>>>(a) : k_fct_low_antidiff_inner<H, V, false><<<g, kThreads, smem, s>>>(a))
     if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LAI(2, 2);
@@ -287,7 +335,7 @@ bool launch_fct_low_antidiff_tma(const FctArgs &a, cudaStream_t s)
     const Rect rc = a.reg.r[0];
     const size_t smem = (size_t)TSTAGES * kTileStageBytes + 64;
     const dim3 g((unsigned)(((rc.i1 - rc.i0 + 1 + TTX - 1) / TTX) * a.kjpt), (unsigned)((rc.j1 - rc.j0 + 1 + TTY - 1) / TTY), (unsigned)a.nkchunk);
-    const bool ft = a.masks_from_t != 0;
+    const bool ft = (a.masks_from_t & 1) != 0;
 #define LAT(H, V, F) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_low_antidiff_tma<H, V, F>, smem, done); \
                           k_fct_low_antidiff_tma<H, V, F><<<g, TTX * TTY, smem, s>>>(a, tm, rc); } while (0)
 #define LAT2(H, V) do { if (ft) LAT(H, V, true); else LAT(H, V, false); } while (0)
@@ -327,7 +375,7 @@ bool prepare_fct_fused(const FctArgs &a, TmaMapCache *cache)
     const int ni = a.out.i1 - a.out.i0 + 1, nj = a.out.j1 - a.out.j0 + 1;
     if (ni <= 0 || nj <= 0) return false;
     // 16-byte global strides, even box origins >= 0, masks as tmask products (the kernel derives umask/vmask/wmask)
-    if ((a.jpi & 1) || !(a.out.i0 & 1) || a.out.i0 - 1 - FHALO - 2 < 0 || a.out.j0 - 1 - FHALO - 1 < 0 || a.jpk < 3 || !a.masks_from_t) return false;
+    if ((a.jpi & 1) || !(a.out.i0 & 1) || a.out.i0 - 1 - FHALO - 2 < 0 || a.out.j0 - 1 - FHALO - 1 < 0 || a.jpk < 3 || (a.masks_from_t & 3) != 3) return false;
     static_assert(sizeof(FusedMaps) == 11 * 128, "tensor-map cache size");
     const void *key[12] = {a.ptb, a.ptn, a.tmask, a.pun, a.pvn, a.pta, a.kn_fct_v == 4 ? a.ztw : a.pta, a.pwn, a.e3t_b, a.e3t_n, a.e3t_a, nullptr};
     const int dims[4] = {a.jpi, a.jpj, a.jpk, a.kjpt};
@@ -408,12 +456,57 @@ void launch_cpt_classify(int jpi, int jpj, int jpk, const double *wmask, const i
 
 void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
                            int ln_isfcav, const double *zwt, const unsigned char *simple, const double *utab,
-                           const double *pt_in, double *pt_out, cudaStream_t s)
+                           const double *pt_in, double *pt_out, cudaStream_t s, TmaMapCache *cache)
 {
+    (void)ln_isfcav;
+    // tiled kernel: even jpi (16-byte global strides), 16-byte aligned input, the forward sweep of a tile fits in shared memory
+    const size_t smem = cpt_tiled_smem_bytes(jpk);
+    if (cache && !(jpi & 1) && jpk >= 3 && smem <= 200 * 1024 && utab && simple) {
+        const void *key[12] = {pt_in};
+        const int dims[4] = {jpi, jpj, jpk, nfld};
+        bool ok = cache->valid && !memcmp(cache->key, key, sizeof key) && !memcmp(cache->dims, dims, sizeof dims);
+        if (!ok) {
+            CptMap m;
+            auto enc = tensor_map_encoder();
+            if (enc && !(reinterpret_cast<uintptr_t>(pt_in) & 15u)) {
+                cuuint64_t gd[3] = {(cuuint64_t)jpi, (cuuint64_t)jpj, (cuuint64_t)jpk * nfld};
+                cuuint64_t gs[2] = {(cuuint64_t)jpi * 8, (cuuint64_t)jpi * jpj * 8};
+                cuuint32_t box[3] = {CTX, CTY, CKL};
+                cuuint32_t es[3] = {1, 1, 1};
+                ok = enc(&m.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(pt_in), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            if (ok) {
+                memcpy(cache->maps, &m, sizeof m);
+                memcpy(cache->key, key, sizeof key); memcpy(cache->dims, dims, sizeof dims);
+                cache->valid = true;
+            }
+        }
+        if (ok) {
+            CptMap m;
+            memcpy(&m, cache->maps, sizeof m);
+            static bool done[kMaxDevices] = {};
+            allow_dynamic_smem(k_interp_4th_cpt_tiled, 200 * 1024, done);
+            const dim3 g((unsigned)((jpi - 1 + CTX - 1) / CTX), (unsigned)((jpj - 2 + CTY - 1) / CTY), (unsigned)nfld);
+            k_interp_4th_cpt_tiled<<<g, CTX * CTY, smem, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_out, m);
+            note_launch();
+            return;
+        }
+    }
     const long long ncol = (long long)(jpi - 2) * (jpj - 2);
     const dim3 g((unsigned)((ncol + kThreads - 1) / kThreads), 1, (unsigned)nfld);
-    (void)ln_isfcav;
-    k_interp_4th_cpt<<<g, kThreads, 0, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_in, pt_out);
+    k_interp_4th_cpt<<<g, kThreads, 0, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_in, pt_out, Region(), nullptr);
+    note_launch();
+}
+
+void launch_interp_4th_cpt_region(const Region &reg, int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
+                                  const double *zwt, const unsigned char *simple, const double *utab, const double *pt_in, double *pt_out,
+                                  double *scratch, cudaStream_t s)
+{
+    const long long ncol = reg.ncol();
+    if (ncol <= 0) return;
+    const dim3 g((unsigned)((ncol + kThreads - 1) / kThreads), 1, (unsigned)nfld);
+    k_interp_4th_cpt<<<g, kThreads, 0, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_in, pt_out, reg, scratch);
     note_launch();
 }
 

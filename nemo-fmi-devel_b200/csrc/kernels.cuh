@@ -28,7 +28,7 @@ struct Region {
 struct FctArgs {
     Region reg;                            // columns this launch works on
     Rect out;                              // fused nonosc+final kernel: output rectangle
-    int masks_from_t;                      // umask/vmask/wmask are products of tmask (dommsk.F90:176-177,193): derive them
+    int masks_from_t;                      // bit 0: umask/vmask/wmask are products of tmask (dommsk.F90:176-177,193): derive them; bit 1: tmask in {+0, 1}
     double *zlx, *zly, *zlz;               // schedule 1: limited fluxes of the frame path (separate from zwx/zwy/zwz)
     int jpi, jpj, jpk;
     size_t jpij, n3;                       // jpi*jpj, jpi*jpj*jpk
@@ -86,7 +86,12 @@ void launch_cpt_classify(int jpi, int jpj, int jpk, const double *wmask, const i
                          const double *utab, unsigned char *simple, cudaStream_t s);
 void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
                            int ln_isfcav, const double *zwt, const unsigned char *simple, const double *utab,
-                           const double *pt_in, double *pt_out, cudaStream_t s);
+                           const double *pt_in, double *pt_out, cudaStream_t s, struct TmaMapCache *cache = nullptr);
+// the same on the columns of `reg` only (the frame bands of schedule 4), column kernel.  The forward sweep is parked in
+// `scratch` (same shape), never in pt_out: another stream may be reading pt_out on these columns (same final values)
+void launch_interp_4th_cpt_region(const Region &reg, int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
+                                  const double *zwt, const unsigned char *simple, const double *utab, const double *pt_in, double *pt_out,
+                                  double *scratch, cudaStream_t s);
 // tra_adv transports                                                        traadv.F90:100-124
 void launch_transports(int jpi, int jpj, int jpk, const double *e2u, const double *e1v, const double *e1e2t,
                        const double *e3u_n, const double *e3v_n, const double *un, const double *vn,
@@ -162,5 +167,7 @@ void launch_lbc_unpack(const UnpackJob *jobs_dev, int njobs, int maxcell, int nl
 void launch_lbc_fill(const FillJob *jobs_dev, int njobs, int maxcell, int nlev, size_t jpij, cudaStream_t s);
 
 long long kernel_launch_count();
+// div_rn (fct_fused_kernel.cuh) against x / y on n operand pairs per class; returns the number of differing results, < 0 on error
+long long division_selftest(long long n, unsigned long long seed, cudaStream_t s);
 
 }  // namespace nemo

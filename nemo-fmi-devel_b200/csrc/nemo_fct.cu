@@ -132,7 +132,7 @@ struct nemo_fct_ctx {
     double *diag[3] = {nullptr, nullptr, nullptr};                     // l_trd / l_hst / l_ptr hooks: ztrdx, ztrdy, ztrdz (device, borrowed)
     double r2dt = 0.0;                                                 // tracer time step of tra_adv (traadv.F90:95-97), persists across calls
     bool have_zl = false;
-    int masks_from_t = 0;                                              // umask/vmask/wmask verified to be tmask products
+    int masks_from_t = 0;                                              // bit 0: umask/vmask/wmask verified to be tmask products; bit 1: tmask holds only +0.0 / 1.0
     cudaStream_t side_stream = nullptr;                                // schedule 1: frame kernels + exchanges
     cudaEvent_t ev_a = nullptr, ev_k1 = nullptr, ev_t = nullptr;
     // host-variant staging
@@ -148,6 +148,7 @@ struct nemo_fct_ctx {
     long long n_exchanges = 0, bytes_sent = 0;
     int schedule = 4;                                                  // 4: whole step fused in one kernel where possible; 2: three TMA-tiled kernels
     TmaMapCache fused_maps;                                            // schedule 4: tensor maps of k_fct_fused, encoded once per (pointers, shape)
+    TmaMapCache cpt_maps[3];                                           // tensor map of k_interp_4th_cpt_tiled: tra_adv_fct, tra_adv_cen, interp_4th_cpt entry
     // per-kernel CUDA-event timing (bench.py's roofline): off by default
     bool profiling = false;
     struct ProfRec { int id; cudaEvent_t a, b; };
@@ -161,11 +162,11 @@ typedef nemo_fct_ctx Ctx;
 // per-kernel timing with CUDA events on the launching stream
 // ------------------------------------------------------------------------------------------------------------
 enum ProfId { P_LAPLACIAN = 0, P_CPT, P_LOW_ANTIDIFF, P_BETAS, P_LIMIT, P_FINAL, P_LOW_INNER, P_NONOSC_FINAL, P_PACK, P_MOVE, P_UNPACK,
-              P_MUS_GRAD, P_MUS_HFLUX, P_MUS_TREND, P_MUS_INNER, P_NXT, P_CEN, P_FUSED, P_COUNT };
+              P_MUS_GRAD, P_MUS_HFLUX, P_MUS_TREND, P_MUS_INNER, P_NXT, P_CEN, P_FUSED, P_CPT_BAND, P_COUNT };
 static_assert(P_COUNT <= 24, "prof_ms / prof_calls too small");
 static const char *kProfName[P_COUNT] = {"fct_laplacian", "interp_4th_cpt", "fct_low_antidiff", "fct_betas", "fct_limit",
                                          "fct_final", "fct_low_antidiff_inner", "fct_nonosc_final", "lbc_pack", "lbc_move_nccl", "lbc_fill_unpack",
-                                         "mus_grad", "mus_hflux", "mus_trend", "mus_inner", "tra_nxt", "tra_adv_cen", "fct_fused"};
+                                         "mus_grad", "mus_hflux", "mus_trend", "mus_inner", "tra_nxt", "tra_adv_cen", "fct_fused", "interp_4th_cpt_band"};
 struct ProfScope {
     nemo_fct_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int id;
     static cudaEvent_t get(nemo_fct_ctx *c) {
@@ -490,7 +491,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     };
 #define EACH(id, stmt) for (int m = 0; m < ng; ++m) { Ctx *c = g[m]; CU(cudaSetDevice(c->device)); ProfScope ps(c, id); stmt; }
 #define CPT() EACH(P_CPT, launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p, \
-                                                 c->ln_isfcav, c->cpt_zwt.p, c->cpt_simple.p, c->cpt_utab.p, fa[m].ptn, c->ztw.p, c->stream))
+                                                 c->ln_isfcav, c->cpt_zwt.p, c->cpt_simple.p, c->cpt_utab.p, fa[m].ptn, c->ztw.p, c->stream, c->schedule >= 4 ? &c->cpt_maps[0] : nullptr))
     // schedule 1 needs room for the fused inner region on every subdomain
     bool fused = g[0]->schedule >= 1;
     for (int m = 0; m < ng; ++m) if (g[m]->dom.jpi < kMinFusedSize || g[m]->dom.jpj < kMinFusedSize) fused = false;
@@ -579,14 +580,31 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     }
     if (!split) k1c = k1;
 
+    // Where the frame chain runs in schedule 4.  With real neighbours (NCCL ranks, in-process groups) it overlaps the main
+    // stream: each of its four exchanges costs a round trip.  On a lone subdomain the exchanges are local copies and the chain
+    // is ~0.8 ms of small latency-bound launches at ORCA025: overlapped, its blocks displace whole-SM blocks of k_fct_fused or
+    // fight the compact-scheme solve for DRAM and cost 1.0-1.3 ms (measured), so it simply runs first on the main stream.
+    // NEMO_FCT_FRAME_ORDER = 0 / 1 forces overlapped / serial (experiments).
+    static const int frame_env = getenv("NEMO_FCT_FRAME_ORDER") ? atoi(getenv("NEMO_FCT_FRAME_ORDER")) : -1;
+    const int frame_order = frame_env >= 0 ? frame_env : ((g[0]->nccl_nranks > 1 || ng > 1) ? 0 : 1);
+    // Schedule 4 overlaps the whole frame chain with the compact-scheme solve of the main stream (small blocks that leave room
+    // on every SM; k_fct_fused owns whole SMs and would be displaced block by block): the side stream starts before CPT and
+    // solves the frame's own columns itself.
+    const bool early_side = one_kernel && frame_order == 0;
+    if (early_side) CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
     if (v == 4) CPT();                                                                             // ztw, whole interior
-    CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
-    if (one_kernel) { EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps)); }
+    if (!early_side) CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
+    if (one_kernel && frame_order >= 1) side = mainst[0];                                          // frame chain first, same stream
+    if (one_kernel) { if (frame_order != 1) EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps)); }
     else EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1c[m], c->stream))) launch_fct_low_antidiff_inner(k1c[m], c->stream));
     if (!split) CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
     // frame
     to_side();
     CU(cudaStreamWaitEvent(side, g[0]->ev_a, 0));
+    if (early_side && v == 4)
+        EACH(P_CPT_BAND, launch_interp_4th_cpt_region(fct_fused_plan(c->dom.jpi, c->dom.jpj, c->dom.npolj != 0, true).cptb, c->dom.jpi, c->dom.jpj,
+                                                      c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p, c->cpt_zwt.p, c->cpt_simple.p,
+                                                      c->cpt_utab.p, fa[m].ptn, c->ztw.p, c->zwz.p, c->stream));   // forward sweep parked in zwz (rewritten by P1-P5 below)
     if (h == 4) {
         EACH(P_LAPLACIAN, launch_fct_laplacian(lap[m], c->stream));
         if (exch({&Ctx::zltu, &Ctx::zltv}, "TT", {1.0, 1.0})) return 1;                            // X1
@@ -606,6 +624,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     EACH(P_FINAL, launch_fct_final(fin[m], c->stream));
     CU(cudaEventRecord(g[0]->ev_t, side));
     to_main();
+    if (one_kernel && frame_order == 1) EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps));
     if (!one_kernel) {
         if (split) CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_k1, 0));                             // K2 reads the band as well
         EACH(P_NONOSC_FINAL, if (!(c->schedule == 3 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
@@ -792,7 +811,7 @@ static int run_cen(std::vector<Ctx *> &g, const std::vector<CenCall> &args, int 
     }
     if (v == 4)
         EACH(P_CPT, launch_interp_4th_cpt(c->dom.jpi, c->dom.jpj, c->dom.jpk, kjpt, c->wmask.p, c->mikt.p, c->mbkt.p, c->ln_isfcav,
-                                          c->cpt_zwt.p, c->cpt_simple.p, c->cpt_utab.p, ca[m].ptn, c->ztw.p, c->stream));
+                                          c->cpt_zwt.p, c->cpt_simple.p, c->cpt_utab.p, ca[m].ptn, c->ztw.p, c->stream, c->schedule >= 4 ? &c->cpt_maps[1] : nullptr));
     EACH(P_CEN, launch_cen(ca[m], c->stream));
 #undef EACH
     CU(cudaGetLastError());
@@ -875,6 +894,16 @@ extern "C" {
 const char *nemo_fct_last_error(void) { return g_err.c_str(); }
 int nemo_fct_abi_version(void) { return NEMO_FCT_ABI_VERSION; }
 long long nemo_fct_launch_count(void) { return kernel_launch_count(); }
+
+int nemo_fct_selftest_division(int device, long long n, unsigned long long seed, long long *nbad)
+{
+    if (!nbad || n < 1) return fail("nemo_fct_selftest_division: bad arguments");
+    CU(cudaSetDevice(device));
+    const long long r = division_selftest(n, seed, nullptr);
+    if (r < 0) return fail("nemo_fct_selftest_division: the self-test kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    *nbad = r;
+    return 0;
+}
 
 int nemo_mpp_init(int jpiglo, int jpjglo, int jpk, int jperio, int jpni, int jpnj, int narea, int key_mpp_mpi,
                   nemo_fct_domain *out)
@@ -1046,7 +1075,13 @@ int nemo_fct_set_domain_arrays(nemo_fct_handle h, const double *tmask, const dou
                         wmask[o + i] != (k == 0 ? tm : tm * tmask[o + i - h->jpij])) { ok = false; break; }
                 }
             }
-        h->masks_from_t = ok ? 1 : 0;
+        // ... and does tmask hold nothing but +0.0 and 1.0 (bit patterns)?  k_fct_fused selects on it instead of multiplying
+        bool binary = true;
+        for (size_t i = 0; i < h->n3 && binary; ++i) {
+            unsigned long long b; memcpy(&b, &tmask[i], 8);
+            binary = b == 0ull || b == 0x3ff0000000000000ull;
+        }
+        h->masks_from_t = (ok ? 1 : 0) | (binary ? 2 : 0);
     }
     try {
         CUTHROW(cudaStreamSynchronize(h->stream));
@@ -1204,7 +1239,7 @@ int nemo_interp_4th_cpt_dev(nemo_fct_handle h, const double *pt_in, double *pt_o
     if (h->dom.jpk < 3) return fail("interp_4th_cpt: jpk must be >= 3");
     CU(cudaSetDevice(h->device));
     launch_interp_4th_cpt(h->dom.jpi, h->dom.jpj, h->dom.jpk, 1, h->wmask.p, h->mikt.p, h->mbkt.p, h->ln_isfcav,
-                          h->cpt_zwt.p, h->cpt_simple.p, h->cpt_utab.p, pt_in, pt_out, h->stream);
+                          h->cpt_zwt.p, h->cpt_simple.p, h->cpt_utab.p, pt_in, pt_out, h->stream, h->schedule >= 4 ? &h->cpt_maps[2] : nullptr);
     CU(cudaGetLastError());
     return 0;
 }

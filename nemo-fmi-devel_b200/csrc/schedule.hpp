@@ -31,6 +31,7 @@ struct FctFusedPlan {
     Rect k2_out;               // nonosc + final inner kernel: output rectangle (5:jpi-4, 4:jpj-4-f), i0 odd (even TMA box origin)
     Region lowf;               // frame P1-P5: E column and N rows left out by k1
     Region lap, bet, lim, fin; // frame Laplacian, betas, limiter, final trend
+    Region cptb;               // schedule 4: columns whose ztw the frame chain reads (k1_band + lowf), solved on the side stream
 };
 
 inline FctFusedPlan fct_fused_plan(int jpi, int jpj, bool fold, bool want_split)
@@ -45,6 +46,7 @@ inline FctFusedPlan fct_fused_plan(int jpi, int jpj, bool fold, bool want_split)
     p.fin = frame_band(jpi, jpj, 3, 3, 2, 3 + f);
     p.lim = frame_band(jpi, jpj, 4, 4, 3, 4 + f);
     p.bet = frame_band(jpi, jpj, 5, 5, 4, 5 + f);
+    p.cptb = frame_band(jpi, jpj, 8, 9, 7, 9 + f);      // = k1_band + lowf exactly (their P1-P5 launches rewrite the zwz scratch)
     const Rect r1 = p.k1.r[0];
     const int w = 8;
     p.split = want_split && !(r1.i1 - r1.i0 + 1 < 2 * w + 4 || r1.j1 - r1.j0 + 1 < 2 * w + 3);

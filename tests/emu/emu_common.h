@@ -22,11 +22,15 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define NEMO_NOINLINE
 
 struct EmuIdx { unsigned x, y, z; };
 static thread_local EmuIdx blockIdx, threadIdx, blockDim, gridDim;      // thread_local: emu_block.h runs one host thread per CUDA thread
 using std::min;
 using std::max;
+#include <type_traits>
+// high word of a double (device intrinsic of the same name)
+static inline int __double2hiint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
 #define NEMO_EMU_KERNELS_ONLY 1
 
 // walk the launch grid of a column kernel serially: blockIdx.x = column block, .y = jk chunk, .z = tracer

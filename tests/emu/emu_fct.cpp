@@ -119,7 +119,7 @@ int emu_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, int ln_isfcav, const
         for (int bx = 0; bx < (ncol + 127) / 128; ++bx)
             for (int t = 0; t < 128; ++t) {
                 blockIdx = {(unsigned)bx, 0, (unsigned)bz}; threadIdx = {(unsigned)t, 0, 0};
-                k_interp_4th_cpt(jpi, jpj, jpk, wmask, mikt, mbkt, zwt.data(), simple.data(), utab.data(), pt_in, pt_out);
+                k_interp_4th_cpt(jpi, jpj, jpk, wmask, mikt, mbkt, zwt.data(), simple.data(), utab.data(), pt_in, pt_out, Region(), nullptr);
             }
     int nsimple = 0;
     for (unsigned char c : simple) nsimple += c;

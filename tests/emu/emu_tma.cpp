@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <thread>
 
 #include "../../nemo-fmi-devel_b200/csrc/kernels.cuh"

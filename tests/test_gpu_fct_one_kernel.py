@@ -80,3 +80,11 @@ def test_one_kernel_orca2_pisces_shape_26_tracers(N, O):
         for schedule in (4, 2, 0):
             got, _ = H.device_fct(N, gf, G, GJ, K, 4, 1, 1, kjpt, h, v, schedule=schedule)
             _check(got, ref, "C5 h%d v%d schedule %d" % (h, v, schedule))
+
+
+def test_inlined_division_is_the_ieee_division(N):
+    """div_rn of the fused kernel (the compiler's fast path written inline, fct_fused_kernel.cuh) == x / y bit for bit on
+    2^24 operand pairs in each of 8 classes: ordinary, the FCT ranges (1e-15 .. 1e40), tiny numerators, zeros, subnormals,
+    huge, Inf / NaN, anything"""
+    for seed in (1, 2, 3):
+        assert N.selftest_division(1 << 24, seed) == 0
