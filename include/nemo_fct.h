@@ -258,6 +258,13 @@ int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int n
  *   3 = as 2, and the fused nonosc kernel also fed by a 2-stage TMA ring (measured slower than 2 on B200: kept for study).
  * Subdomains smaller than 20 x 20 always use 0.                                                                    */
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule);
+/* Arithmetic of the one-kernel schedule (4).  STRICT (default): every REAL(wp) operation of traadv_fct.F90 as an IEEE operation
+ * in the reference's order, no FMA contraction: bit-identical to the CPU restatement.  FAST: the six divisions per point (:164,
+ * :166, :393-396, :294) become a multiplication by a refined reciprocal (<= 1 ulp instead of <= 0.5 ulp); measured -12 % .. -32 %
+ * kernel time, max relative difference 5e-11 on near-zero trends (above the 1e-12 bar: opt-in only).                      */
+#define NEMO_FCT_ARITH_STRICT 0
+#define NEMO_FCT_ARITH_FAST   1
+int nemo_fct_set_arithmetic(nemo_fct_handle h, int mode);
 
 #ifdef __cplusplus
 }

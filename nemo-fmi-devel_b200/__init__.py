@@ -118,6 +118,7 @@ def lib():
         "nemo_group_lbc_lnk_multi_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.c_char_p, dp, i, i, d],
         "nemo_fct_comm_report": [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
         "nemo_fct_set_schedule": [vp, i],
+        "nemo_fct_set_arithmetic": [vp, i],
         "nemo_fct_set_profiling": [vp, i],
         "nemo_fct_profile_read": [vp, i, C.c_char_p, i, dp, C.POINTER(C.c_longlong)],
         "nemo_fct_abi_version": [],
@@ -143,7 +144,7 @@ ABI_SYMBOLS = (
     "nemo_fct_set_trend_diag "
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
-    "nemo_fct_profile_read nemo_fct_selftest_division").split()
+    "nemo_fct_profile_read nemo_fct_selftest_division nemo_fct_set_arithmetic").split()
 
 
 class NxtForcing(C.Structure):
@@ -313,6 +314,10 @@ class FctContext:
 
     def set_schedule(self, schedule):
         _check(lib().nemo_fct_set_schedule(self._h, schedule))
+
+    def set_arithmetic(self, mode):
+        """0 = STRICT (IEEE, bit-identical to the CPU restatement; default), 1 = FAST (relaxed divisions in schedule 4)"""
+        _check(lib().nemo_fct_set_arithmetic(self._h, mode))
 
     def comm_init(self, unique_id, nranks, rank):
         _check(lib().nemo_fct_comm_init(self._h, unique_id, nranks, rank))

@@ -403,12 +403,14 @@ void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache
     FusedMaps tm;
     memcpy(&tm, cache->maps, sizeof tm);
     const dim3 g((unsigned)(((ni + FOX - 1) / FOX) * a.kjpt), (unsigned)((nj + FOY - 1) / FOY), (unsigned)a.nkchunk);
-#define LFU(H, V) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_fused<H, V>, kFusedSmemBytes, done); \
-                       k_fct_fused<H, V><<<g, FX * FY, kFusedSmemBytes, s>>>(a, tm); } while (0)
-    if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LFU(2, 2);
-    else if (a.kn_fct_h == 2)               LFU(2, 4);
-    else if (a.kn_fct_v == 2)               LFU(4, 2);
-    else                                    LFU(4, 4);
+#define LFU(H, V, A) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_fused<H, V, A>, kFusedSmemBytes, done); \
+                          k_fct_fused<H, V, A><<<g, FX * FY, kFusedSmemBytes, s>>>(a, tm); } while (0)
+#define LFU2(H, V) do { if (a.arith == 0) LFU(H, V, 0); else LFU(H, V, 1); } while (0)
+    if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LFU2(2, 2);
+    else if (a.kn_fct_h == 2)               LFU2(2, 4);
+    else if (a.kn_fct_v == 2)               LFU2(4, 2);
+    else                                    LFU2(4, 4);
+#undef LFU2
 #undef LFU
     note_launch();
 }

@@ -44,6 +44,7 @@ struct FctArgs {
     double p2dt;
     int kjpt, kn_fct_h, kn_fct_v, ln_linssh, ln_isfcav;
     int nkchunk;                           // the jk loop is split in nkchunk chunks across blockIdx.y
+    int arith;                             // k_fct_fused: 0 = IEEE divisions (default), 1 = relaxed (nemo_fct_set_arithmetic)
 };
 
 // P4 (order 4): zltu, zltv on (2:jpim1,2:jpjm1,1:jpkm1)                     traadv_fct.F90:195-208

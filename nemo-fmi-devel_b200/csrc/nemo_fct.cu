@@ -147,6 +147,7 @@ struct nemo_fct_ctx {
     void *nccl_comm = nullptr; int nccl_nranks = 0;
     long long n_exchanges = 0, bytes_sent = 0;
     int schedule = 4;                                                  // 4: whole step fused in one kernel where possible; 2: three TMA-tiled kernels
+    int arith = 0;                                                     // nemo_fct_set_arithmetic: 0 strict (IEEE), 1 relaxed divisions in k_fct_fused
     TmaMapCache fused_maps;                                            // schedule 4: tensor maps of k_fct_fused, encoded once per (pointers, shape)
     TmaMapCache cpt_maps[3];                                           // tensor map of k_interp_4th_cpt_tiled: tra_adv_fct, tra_adv_cen, interp_4th_cpt entry
     // per-kernel CUDA-event timing (bench.py's roofline): off by default
@@ -477,6 +478,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         a.p2dt = p2dt; a.kjpt = kjpt; a.kn_fct_h = h; a.kn_fct_v = v; a.ln_linssh = c->ln_linssh; a.ln_isfcav = c->ln_isfcav;
         a.nkchunk = pick_nkchunk(c, kjpt);
         a.masks_from_t = c->masks_from_t;
+        a.arith = c->arith;
         a.zlx = a.zly = a.zlz = nullptr;
         a.out = Rect{0, -1, 0, -1};
         a.reg = Region();
@@ -1049,6 +1051,14 @@ int nemo_fct_set_schedule(nemo_fct_handle h, int schedule)
     if (!h) return fail("NULL handle");
     if (schedule < 0 || schedule > 4) return fail("nemo_fct_set_schedule: schedule %d is not available", schedule);
     for (Ctx *o : h->group) o->schedule = schedule;
+    return 0;
+}
+
+int nemo_fct_set_arithmetic(nemo_fct_handle h, int mode)
+{
+    if (!h) return fail("NULL handle");
+    if (mode != NEMO_FCT_ARITH_STRICT && mode != NEMO_FCT_ARITH_FAST) return fail("nemo_fct_set_arithmetic: mode %d is not available", mode);
+    for (Ctx *o : h->group) o->arith = mode;
     return 0;
 }
 

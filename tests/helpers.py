@@ -103,7 +103,7 @@ def oracle_fct(O, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_li
 
 
 def device_fct(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_linssh=False, ln_isfcav=False,
-               host_path=False, schedule=0, nsteps=1, kernels=None):
+               host_path=False, schedule=0, nsteps=1, kernels=None, arith=0):
     """Run the product on cuda:0 through the C ABI: single subdomain (jpni = jpnj = 1) or an in-process group of
     jpni x jpnj subdomains on one GPU.  Returns (global pta, list of local pta).  kernels: list that receives the names of
     the kernels subdomain 0 launched (per-kernel profiling of the library)"""
@@ -120,6 +120,8 @@ def device_fct(N, gf, jpiglo, jpjglo, jpk, jperio, jpni, jpnj, kjpt, h, v, ln_li
         grp = N.LocalGroup(jpiglo, jpjglo, jpk, jperio, jpni, jpnj, 0)
         ctxs = grp.ctx
     ctxs[0].set_schedule(schedule)
+    if arith:
+        ctxs[0].set_arithmetic(arith)
     if kernels is not None:
         ctxs[0].set_profiling(True)
     for r, c in enumerate(ctxs):

@@ -88,3 +88,19 @@ def test_inlined_division_is_the_ieee_division(N):
     huge, Inf / NaN, anything"""
     for seed in (1, 2, 3):
         assert N.selftest_division(1 << 24, seed) == 0
+
+
+def test_fast_arithmetic_is_opt_in_and_close(N, O):
+    """nemo_fct_set_arithmetic(FAST): divisions as multiplications by a refined reciprocal (<= 1 ulp each).  Not bit-identical
+    (that is why STRICT is the default): the absolute difference stays at round-off of the field scale, while the per-point
+    relative difference exceeds the 1e-12 bar of BASELINE.json on near-zero trends (measured 5e-11 at ORCA025)."""
+    G, GJ, K = 76, 45, 11
+    gf = H.random_fields(O, G, GJ, K, 4, kjpt=2, seed=470)
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, 4, 1, 1, 2, 4, 4)
+    strict, _ = H.device_fct(N, gf, G, GJ, K, 4, 1, 1, 2, 4, 4, schedule=4)
+    fast, _ = H.device_fct(N, gf, G, GJ, K, 4, 1, 1, 2, 4, 4, schedule=4, arith=1)
+    assert np.array_equal(strict, ref)
+    assert not np.array_equal(fast, ref)
+    assert np.abs(fast - ref).max() <= 1e-13 * np.abs(ref).max()
+    with pytest.raises(N.NemoFctError, match="arithmetic"):
+        N.FctContext(N.mpp_init(G, GJ, K, 4, 1, 1, 1), 0).set_arithmetic(7)
