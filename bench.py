@@ -103,7 +103,9 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle on the host cores (cpu_baseline of our arm, and the whole of --impl reference)
 # ----------------------------------------------------------------------------------------------------------------
-CPU_PARTITION = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2), 16: (4, 4), 32: (8, 4), 64: (8, 8)}   # tests/BENCH/EXPREF/best_jpni_jpnj_eorca025 (16: 4x4)
+CPU_PARTITION = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2), 16: (4, 4)}   # tests/BENCH/EXPREF/best_jpni_jpnj_eorca025 (16: 4x4)
+CPU_CORES_MAX = 16            # pinned: the boxes of the BENCH and SCALE runs have different core counts
+CPU_SAMPLE_PTS = 30.0e6       # points of the j-slab one CPU step works on (~0.5 s on 16 cores)
 
 
 def host_cores():
@@ -113,18 +115,23 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_sample_shape(cfg):
+    """The bounded sample both CPU legs time: same jpiglo, jpk, jperio, tracers and scheme, jpjglo cut to a j-slab"""
+    G, GJ, K, jperio, kjpt, h, v, rdt = cfg
+    gj = GJ if G * GJ * K <= CPU_SAMPLE_PTS else max(16, int(CPU_SAMPLE_PTS / (G * K)))
+    return G, gj, K
+
+
 def cpu_reference_run(cfg, steps, warmup):
     """Time the oracle's tra_adv_fct (threads standing in for MPI ranks, halo exchange through the restated
-    mpp_lnk) on a bounded j-slab of the workload.  Returns (Mpts/s, info dict)."""
+    mpp_lnk, ln_nnogather = .TRUE. as the reference's default) on the bounded j-slab.  Returns (Mpts/s, info dict)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers as H
     from oracle import oracle as O
     G, GJ, K, jperio, kjpt, h, v, rdt = cfg
-    cores = max(c for c in CPU_PARTITION if c <= host_cores())
+    cores = max(c for c in CPU_PARTITION if c <= min(host_cores(), CPU_CORES_MAX))
     jpni, jpnj = CPU_PARTITION[cores]
-    # bounded sample: same jpiglo, jpk, jperio, tracers and scheme; jpjglo cut so that one step is O(1-5 s) of CPU
-    target_pts = 30.0e6
-    gj = GJ if G * GJ * K <= target_pts else max(8 * jpnj, int(target_pts / (G * K)))
+    _, gj, _ = cpu_sample_shape(cfg)
     gf = H.global_bench_fields(O, G, gj, K, jperio, kjpt, rn_rdt=rdt)
     w = O.World(G, gj, K, jperio, jpni, jpnj, ln_nnogather=True)
     loc = {k: w.scatter(gf[k]) for k in H.DOM_KEYS + ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
@@ -141,34 +148,43 @@ def cpu_reference_run(cfg, steps, warmup):
     npts = G * gj * K
     ms = 1e3 * sum(times) / len(times)
     info = {"cores": cores, "kind": "port",
-            "sample": "%dx%dx%d of %dx%dx%d (same jpiglo/jpk/jperio=%d, kjpt=%d, FCT h%d/v%d), %dx%d subdomains = %d threads as MPI ranks, "
-                      "C restatement of tra_adv_fct (gcc -O2 -ffp-contract=off), not the Fortran binary" %
-                      (G, gj, K, G, GJ, K, jperio, kjpt, h, v, jpni, jpnj, cores),
+            "sample": "j-slab %dx%dx%d of %dx%dx%d (same jpiglo/jpk/jperio=%d, kjpt=%d, FCT h%d/v%d), %dx%d subdomains = %d host threads as MPI "
+                      "ranks (pinned to <= %d), C restatement of tra_adv_fct with the reference's per-call work arrays "
+                      "(gcc -O3 -ffp-contract=off, as arch-linux_gfortran.fcm: -O3, no fast-math), not the Fortran binary" %
+                      (G, gj, K, G, GJ, K, jperio, kjpt, h, v, jpni, jpnj, cores, CPU_CORES_MAX),
             "ms_per_step": ms}
     return npts / (ms * 1e-3) / 1e6, info
 
 
 def run_reference(args, cfg, rank):
+    """--impl reference: the CPU arm on OUR arm's config / metric / unit; each step is the bounded j-slab sample"""
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
-    val, info = cpu_reference_run(cfg, steps, warm)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+    BF = importlib.import_module("nemo-fmi-devel_b200.bench_fields")
+    val, info = cpu_reference_run(cfg, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.workload, cfg, 1, (1, 1)),
+            "config": workload_config(args.workload, cfg, args.gpus, BF.best_partition(args.gpus), default_schedule(args), args.scheme),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, cfg, n_gpus, part, schedule=None):
+def default_schedule(args):
+    return 4 if args.schedule is None else args.schedule
+
+
+def workload_config(name, cfg, n_gpus, part, schedule, scheme):
+    """identical for both arms (the driver compares them): the GPU arm runs the whole workload, the CPU legs a j-slab of it"""
     G, GJ, K, jperio, kjpt, h, v, rdt = cfg
+    sg, sgj, sk = cpu_sample_shape(cfg)
     return {"workload": "%s: tests/BENCH-style %dx%dx%d, jperio=%d, kjpt=%d, FCT h%d/v%d, z-star (ln_linssh=F)" %
                         (name, G, GJ, K, jperio, kjpt, h, v),
-            "jpni_x_jpnj": "%dx%d" % part, "n_gpus": n_gpus, "schedule": schedule,
-            "cache": "inputs larger than L2 (working set >> 126 MB), no explicit flush"}
+            "jpni_x_jpnj": "%dx%d" % part, "n_gpus": n_gpus, "schedule": schedule, "scheme": scheme,
+            "cache": "inputs larger than L2 (working set >> 126 MB), no explicit flush",
+            "cpu_sample": "the CPU legs (cpu_baseline, --impl reference) time a bounded j-slab %dx%dx%d of this workload on <= %d host "
+                          "threads; the GPU arm runs all of it on jpni_x_jpnj GPUs" % (sg, sgj, sk, CPU_CORES_MAX)}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -217,7 +233,7 @@ def main():
     part = BF.best_partition(world)
     dom = N.mpp_init(G, GJ, K, jperio, part[0], part[1], rank + 1)
     ctx = N.FctContext(dom, local_rank)
-    sched = 4 if args.schedule is None else args.schedule
+    sched = default_schedule(args)
     ctx.set_schedule(sched)
     if world > 1:
         idt = torch.zeros(N.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
@@ -294,9 +310,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = npts_global / (ms_max * 1e-3) / 1e6
-    checksum = float(f["pta"].double().abs().sum().item())
-    if not np.isfinite(checksum):
+    if not bool(torch.isfinite(f["pta"]).all().item()):
         raise SystemExit("bench.py: non-finite result")
+    # decomposition-invariant checksum: wrapping int64 sum of the bit patterns of pta over the GLOBAL interior
+    # (2:jpiglo-1, 2:jpjglo-1, all levels and tracers), every global point taken from the one rank that owns it.  The same
+    # workload gives the same number at N = 1, 2, 4, 8 and for every schedule (the step is bit-reproducible).
+    i0 = max(dom.nldi, 2 - dom.nimpp + 1); i1 = min(dom.nlei, G - 1 - dom.nimpp + 1)
+    j0 = max(dom.nldj, 2 - dom.njmpp + 1); j1 = min(dom.nlej, GJ - 1 - dom.njmpp + 1)
+    bits = f["pta"][..., j0 - 1:j1, i0 - 1:i1].contiguous().view(torch.int64)
+    csum = bits.sum(dtype=torch.int64).reshape(1)
+    cnt = torch.tensor([bits.numel()], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(csum); dist.all_reduce(cnt)
+    checksum = {"int64_sum_of_pta_bits_global_interior": int(csum.item()), "points": int(cnt.item()),
+                "expected_points": (G - 2) * (GJ - 2) * K * kjpt, "steps_applied": args.steps}
 
     # ---- roofline ---------------------------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
@@ -402,7 +429,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cval, info = cpu_reference_run(cfg, 1, 0)
+            cval, info = cpu_reference_run(cfg, 3, 1)
             cpu = {"value": round(cval, 3), "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
         except Exception as ex:                                                    # never lose the GPU numbers
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
@@ -411,9 +438,9 @@ def main():
         metric = METRIC if args.scheme == "fct" else {"mus": "MUSCL tracer-advection Mpts/s per step", "nxt": "tra_nxt (Asselin filter + swap) Mpts/s per step"}[args.scheme]
         line = {"metric": metric, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_max, 4), "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(workload_config(args.workload, cfg, world, part, sched), scheme=args.scheme),
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, cfg, world, part, sched, args.scheme),
                 "tracer_mpts_per_s": round(value * kjpt, 2), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clocks, "checksum_abs_pta": checksum}
+                "gpu_launches": int(launches), "clocks": clocks, "checksum": checksum}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -26,12 +26,12 @@ def main():
     part = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
     G, GJ, K, kjpt = 130, 96, 12, 2
     ok_all = True
-    only_new = os.environ.get("MGPU_ONLY_NEW", "0") == "1"          # skip the tra_adv_fct matrix (8-GPU time is expensive)
-    for jperio in (() if only_new else (0, 1, 4, 6)):
+    only_fct = os.environ.get("MGPU_ONLY_FCT", "0") == "1"          # tests/test_gpu_multi.py: the tra_adv_fct matrix only
+    for jperio in (0, 1, 4, 6):
         gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=50 + jperio)
         for (h, v) in ((2, 2), (4, 4)):
             ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v)
-            for schedule in (0, 1, 2):
+            for schedule in (0, 2, 4):
                 w = O.World(G, GJ, K, jperio, part[0], part[1])
                 loc = {k: w.scatter(gf[k])[rank] for k in H.DOM_KEYS + ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
                 od = w.doms[rank]
@@ -87,7 +87,7 @@ def main():
             print("%s %dx%d: %s" % (what, part[0], part[1], "BIT-IDENTICAL" if flag.item() else "MISMATCH"), flush=True)
         return bool(flag.item())
 
-    for jperio in (0, 1, 4, 6):
+    for jperio in (() if only_fct else (0, 1, 4, 6)):
         gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=70 + jperio)
         mx = H.mus_extra_fields(O, gf, G, GJ, K, jperio, seed=70 + jperio)
         _, refl = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, part[0], part[1], kjpt)

@@ -396,3 +396,65 @@ def test_fused_schedule_random_shapes(emu):
         pta, plan = emu_api.fct_step_fused(emu, gf, kjpt, h, v, lin, isf, 1, lbc, jperio in (3, 4, 5, 6), from_t, want_split=split, tma=tma)
         w.close()
         assert np.array_equal(pta, ref), (G, GJ, jperio, K, kjpt, h, v, lin, isf, split, tma, from_t)
+
+
+# ---- schedule 4: the whole step of the inner region in ONE kernel (k_fct_fused) ------------------------------------------------
+@pytest.mark.parametrize("G,GJ,K,jperio,kjpt,h,v,lin,isf,nkf", [
+    (40, 30, 7, 0, 2, 2, 2, False, False, 1),        # one tile row, closed
+    (40, 30, 7, 1, 2, 4, 4, False, False, 1),        # E-W cyclic, 4th order + compact
+    (44, 38, 9, 4, 2, 4, 4, False, False, 1),        # T-pivot fold, 2 x 3 tiles with overhang
+    (66, 40, 13, 6, 1, 4, 2, True, True, 1),         # F-pivot, linear free surface + cavities, one tracer
+    (66, 40, 26, 6, 3, 2, 4, True, False, 2),        # jk loop of the fused kernel split in 2 chunks, three tracers
+    (36, 24, 5, 0, 2, 4, 4, False, False, 1),        # smallest size that still splits; jpk = 5: no steady-state iteration
+    (52, 34, 3, 1, 2, 2, 2, False, False, 1),        # jpk = 3
+])
+def test_fct_one_kernel_schedule_on_the_host(emu, G, GJ, K, jperio, kjpt, h, v, lin, isf, nkf):
+    """schedule 4 of run_fct on the CPU: k_fct_fused (512 host threads per block: TMA boxes as box copies with zero fill, mbarrier
+    phases as counters, three software-pipelined stages per level, one barrier per level) on K2's rectangle straight from the
+    inputs + the band of K1 (which leaves pta alone there) + the frame chain with X1..X4: whole-array equality with the oracle.
+    The emulation also checks the TMA box rules (origins >= 0, even in ji)."""
+    fold = jperio in (3, 4, 5, 6)
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=1100 + G + K, ln_linssh=lin, ln_isfcav=isf)
+    w = O.World(G, GJ, K, jperio, 1, 1)
+
+    def lbc(trip):
+        w.lbc_lnk([[a.reshape(-1, GJ, G)] for a, _, _ in trip], "".join(n for _, n, _ in trip), [s for _, _, s in trip])
+
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v, ln_linssh=lin, ln_isfcav=isf)
+    pta, plan = emu_api.fct_step_one_kernel(emu, gf, kjpt, h, v, lin, isf, 1, lbc, fold, nk_fused=nkf)
+    w.close()
+    assert pta is not None and plan["split"]
+    bad = np.argwhere(pta != ref)
+    assert np.array_equal(pta, ref), (bad[:5].tolist(), len(bad), plan["k2_out"])
+    assert not np.array_equal(ref, gf["pta"])
+
+
+def test_fct_one_kernel_falls_back_like_the_launcher(emu):
+    """odd jpi (TMA strides) and subdomains too small to split keep the three-kernel schedule"""
+    for (G, GJ) in ((41, 30), (22, 22)):
+        gf = H.random_fields(O, G, GJ, 6, 0, 2, seed=1200)
+        pta, plan = emu_api.fct_step_one_kernel(emu, gf, 2, 4, 4, False, False, 1, None, False)
+        assert pta is None
+
+
+@pytest.mark.parametrize("G,GJ,K,isf,jperio", [(26, 22, 19, False, 1), (26, 22, 19, True, 1), (70, 31, 75, False, 4), (34, 9, 3, False, 0),
+                                               (34, 12, 10, True, 6)])
+def test_interp_4th_cpt_tiled_kernel(emu, G, GJ, K, isf, jperio):
+    """k_interp_4th_cpt_tiled (TMA boxes of 8 levels in a 4-deep ring, forward sweep in shared memory, tabulated elimination
+    factors and once-refined reciprocal pivots on the simple columns) == interp_4th_cpt of the oracle on (2:jpim1, 2:jpjm1,
+    2:jpkm1), with and without the simple-column shortcut; nothing else is written"""
+    gf = H.random_fields(O, G, GJ, K, jperio, 2, seed=800 + K, ln_isfcav=isf)
+    w = O.World(G, GJ, K, jperio, 1, 1)
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS], ln_isfcav=isf)
+    ref = np.zeros_like(gf["ptn"])
+    for jn in range(2):
+        O.lib().interp_4th_cpt(d.h, gf["ptn"][jn].ctypes.data_as(C.c_void_p), ref[jn].ctypes.data_as(C.c_void_p))
+    w.close()
+    inner = (slice(None), slice(1, K - 1), slice(1, -1), slice(1, -1))
+    for simple in (True, False):
+        out = np.full_like(ref, -7.0)
+        assert emu_api.interp_4th_cpt_tiled(emu, gf, gf["ptn"], out, simple) == 0
+        assert np.array_equal(out[inner], ref[inner]), simple
+        out[inner] = -7.0
+        assert (out == -7.0).all()
