@@ -235,6 +235,15 @@ const char *nemo_fct_last_error(void);
 int nemo_fct_abi_version(void);
 /* number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches)                */
 long long nemo_fct_launch_count(void);
+/* glob_sum (src/OCE/lib_fortran_generic.h90:32-65; DDPDD lib_fortran.F90:300-332; MPI_SUMDD lib_mpp.F90:1158-1186): for each of
+ * the nfld device fields ptab[f](jpi,jpj,ipk), out[f] = REAL( SUM in double-double of ptab[f] [* pw3d] * tmask_i ) over this
+ * subdomain and, through the communicator, over all ranks -- the same bits on every rank and for every decomposition.  pw3d
+ * (device, same shape, or NULL) is multiplied in point by point: the array expression the reference's callers form before the
+ * call (e.g. tr * cvol, trcrad.F90).  tmask_i: dom_oce's interior mask (jpi,jpj), device.  out: host, nfld values.  Collective. */
+int nemo_glob_sum_dev(nemo_fct_handle h, const char *cdname, int nfld, const double *const *ptab, const double *pw3d,
+                      const double *tmask_i, int ipk, double *out);
+int nemo_group_glob_sum_dev(nemo_fct_handle *hs, int n, const char *cdname, int nfld, const double *const *const *ptab,
+                            const double *const *pw3d, const double *const *tmask_i, int ipk, double *out);
 /* Self-test of the inlined IEEE division of the fused kernel (csrc/fct_fused_kernel.cuh: div_rn): n pseudo-random operand
  * pairs per class (ordinary magnitudes, the FCT ranges 1e-15 .. 1e40, zeros, subnormals, huge, Inf/NaN) are divided on device
  * `device` by div_rn and by the compiler's x / y; *nbad = number of pairs whose bit patterns differ (NaN payloads aside).

@@ -119,6 +119,8 @@ def lib():
         "nemo_fct_comm_report": [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
         "nemo_fct_set_schedule": [vp, i],
         "nemo_fct_set_arithmetic": [vp, i],
+        "nemo_glob_sum_dev": [vp, C.c_char_p, i, C.POINTER(vp), vp, vp, i, dp],
+        "nemo_group_glob_sum_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.POINTER(vp), C.POINTER(vp), i, dp],
         "nemo_fct_set_profiling": [vp, i],
         "nemo_fct_profile_read": [vp, i, C.c_char_p, i, dp, C.POINTER(C.c_longlong)],
         "nemo_fct_abi_version": [],
@@ -144,7 +146,8 @@ ABI_SYMBOLS = (
     "nemo_fct_set_trend_diag "
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
-    "nemo_fct_profile_read nemo_fct_selftest_division nemo_fct_set_arithmetic").split()
+    "nemo_fct_profile_read nemo_fct_selftest_division nemo_fct_set_arithmetic "
+    "nemo_glob_sum_dev nemo_group_glob_sum_dev").split()
 
 
 class NxtForcing(C.Structure):
@@ -471,6 +474,16 @@ class FctContext:
         _check(fn(self._h, cdname.encode(), nfld, tab, "".join(nats).encode(), sg, ipk, int(pval is not None),
                   float(pval or 0.0)))
 
+    def glob_sum(self, cdname, fields, tmask_i, w3d=None):
+        """glob_sum( cdname, ptab ) (lib_fortran_generic.h90:32-65) for each device field (ipk,jpj,jpi) of `fields`: masked sum in
+        double-double over all ranks of the communicator; w3d (same shape) is multiplied in first.  Returns a list of floats."""
+        nfld = len(fields)
+        ipk = int(np.prod(fields[0].shape[:-2])) if len(fields[0].shape) > 2 else 1
+        tab = (C.c_void_p * nfld)(*[_ptr(_f64(a, "glob_sum")) for a in fields])
+        out = (C.c_double * nfld)()
+        _check(lib().nemo_glob_sum_dev(self._h, cdname.encode(), nfld, tab, None if w3d is None else _ptr(w3d), _ptr(tmask_i), ipk, out))
+        return list(out)
+
     def lbc_lnk(self, cdname, pt, cd_nat, psgn, pval=None):
         """lbc_lnk( cdname, ptab, cd_nat, psgn [, pval] ) (lbclnk.F90:21-29)"""
         self.lbc_lnk_multi(cdname, pt, cd_nat, psgn, pval=pval)
@@ -533,6 +546,17 @@ class LocalGroup:
         sg = (C.c_double * nfld)(*[float(s) for s in sgns])
         _check(lib().nemo_group_lbc_lnk_multi_dev(self._hs, self.n, cdname.encode(), nfld, tabs, "".join(nats).encode(),
                                                   sg, ipk, int(pval is not None), float(pval or 0.0)))
+
+    def glob_sum(self, cdname, fields, tmask_i, w3d=None):
+        """fields[f][rank], tmask_i[rank], w3d[rank] (or None): the same sums as FctContext.glob_sum over the in-process group"""
+        nfld = len(fields)
+        ipk = int(np.prod(fields[0][0].shape[:-2])) if len(fields[0][0].shape) > 2 else 1
+        per_rank = [(C.c_void_p * nfld)(*[_ptr(fields[f][r]) for f in range(nfld)]) for r in range(self.n)]
+        tabs = (C.POINTER(C.c_void_p) * self.n)(*[C.cast(t, C.POINTER(C.c_void_p)) for t in per_rank])
+        out = (C.c_double * nfld)()
+        _check(lib().nemo_group_glob_sum_dev(self._hs, self.n, cdname.encode(), nfld, tabs, None if w3d is None else self._tab(w3d),
+                                             self._tab(tmask_i), ipk, out))
+        return list(out)
 
     def synchronize(self):
         self.ctx[0].synchronize()

@@ -167,6 +167,11 @@ void launch_lbc_pack(const PackJob *jobs_dev, int njobs, int maxcell, int nlev, 
 void launch_lbc_unpack(const UnpackJob *jobs_dev, int njobs, int maxcell, int nlev, size_t jpij, cudaStream_t s);
 void launch_lbc_fill(const FillJob *jobs_dev, int njobs, int maxcell, int nlev, size_t jpij, cudaStream_t s);
 
+// ---- glob_sum (lib_fortran_generic.h90:32-65): double-double masked sums of nfld fields, out_pairs[2*f] = REAL, [2*f+1] = AIMAG
+constexpr int kGlobSumBlocks = 148 * 4;
+void launch_glob_sum(const double *const *ptab_dev, int nfld, const double *pw3d, const double *tmask_i, size_t jpij, int ipk, double *partial,
+                     double *out_pairs, cudaStream_t s);
+
 long long kernel_launch_count();
 // div_rn (fct_fused_kernel.cuh) against x / y on n operand pairs per class; returns the number of differing results, < 0 on error
 long long division_selftest(long long n, unsigned long long seed, cudaStream_t s);

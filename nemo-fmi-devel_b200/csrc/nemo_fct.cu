@@ -53,6 +53,7 @@ struct NcclApi {
     int (*CommDestroy)(void *) = nullptr;
     int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -67,7 +68,7 @@ int load_nccl()
     for (const char *n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
     if (!g_nccl.lib) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
 #define SYM(f) *(void **)(&g_nccl.f) = dlsym(g_nccl.lib, "nccl" #f); if (!g_nccl.f) return fail("libnccl: missing symbol nccl" #f)
-    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllGather); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
     return 0;
 }
@@ -149,6 +150,7 @@ struct nemo_fct_ctx {
     int schedule = 4;                                                  // 4: whole step fused in one kernel where possible; 2: three TMA-tiled kernels
     int arith = 0;                                                     // nemo_fct_set_arithmetic: 0 strict (IEEE), 1 relaxed divisions in k_fct_fused
     TmaMapCache fused_maps;                                            // schedule 4: tensor maps of k_fct_fused, encoded once per (pointers, shape)
+    DevBuf<double> gs_partial, gs_pairs, gs_gather; DevBuf<const double *> gs_ptrs;     // glob_sum scratch
     TmaMapCache cpt_maps[3];                                           // tensor map of k_interp_4th_cpt_tiled: tra_adv_fct, tra_adv_cen, interp_4th_cpt entry
     // per-kernel CUDA-event timing (bench.py's roofline): off by default
     bool profiling = false;
@@ -1488,6 +1490,79 @@ int nemo_lbc_lnk_multi_dev(nemo_fct_handle h, const char *cdname, int nfld, doub
     std::vector<Ctx *> g = {h};
     double *const *tabs[1] = {ptab};
     return lnk_common(g, nfld, tabs, cd_nat, psgn, ipk, has_pval, pval);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// glob_sum (lib_fortran_generic.h90:32-65): masked double-double sums, identical on every rank
+// ------------------------------------------------------------------------------------------------------------
+static void ddpdd_host(const double a[2], double b[2])                 // b = a + b, lib_fortran.F90:314-331
+{
+    volatile double zt1 = a[0] + b[0];
+    volatile double zerr = zt1 - a[0];
+    volatile double zt2 = ((b[0] - zerr) + (a[0] - (zt1 - zerr))) + a[1] + b[1];
+    volatile double s = zt1 + zt2;
+    b[1] = zt2 - (s - zt1);
+    b[0] = s;
+}
+
+// ptab[m][f]: field f of member m (device, jpi*jpj*ipk); pw3d[m] (or NULL): multiplied in point by point; tmask_i[m]: (jpi, jpj)
+static int glob_sum_common(std::vector<Ctx *> &g, int nfld, const double *const *const *ptab, const double *const *pw3d,
+                           const double *const *tmask_i, int ipk, double *out)
+{
+    const int ng = (int)g.size();
+    if (nfld < 1 || nfld > 64 || ipk < 1 || !ptab || !tmask_i || !out) return fail("glob_sum: bad arguments");
+    std::vector<double> pairs((size_t)ng * nfld * 2);
+    for (int m = 0; m < ng; ++m) {
+        Ctx *c = g[m];
+        if (!ptab[m] || !tmask_i[m]) return fail("glob_sum: NULL array");
+        CU(cudaSetDevice(c->device));
+        try {
+            if (c->gs_partial.n < (size_t)64 * kGlobSumBlocks * 2) { c->gs_partial.alloc((size_t)64 * kGlobSumBlocks * 2); c->gs_pairs.alloc(64 * 2); c->gs_ptrs.alloc(64); }
+        } catch (const std::exception &e) { return fail("glob_sum: %s", e.what()); }
+        for (int f = 0; f < nfld; ++f) if (!ptab[m][f]) return fail("glob_sum: NULL field");
+        CU(cudaMemcpyAsync(c->gs_ptrs.p, ptab[m], nfld * sizeof(double *), cudaMemcpyHostToDevice, c->stream));
+        launch_glob_sum(c->gs_ptrs.p, nfld, pw3d ? pw3d[m] : nullptr, tmask_i[m], c->jpij, ipk, c->gs_partial.p, c->gs_pairs.p, c->stream);
+        CU(cudaMemcpyAsync(&pairs[(size_t)m * nfld * 2], c->gs_pairs.p, (size_t)nfld * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    for (int m = 0; m < ng; ++m) CU(cudaStreamSynchronize(g[m]->stream));
+    Ctx *c0 = g[0];
+    if (ng == 1 && c0->nccl_nranks > 1) {                              // MPI_SUMDD across the ranks: gather the pairs, fold in rank order
+        const int nr = c0->nccl_nranks;
+        try { if (c0->gs_gather.n < (size_t)nr * 64 * 2) c0->gs_gather.alloc((size_t)nr * 64 * 2); }
+        catch (const std::exception &e) { return fail("glob_sum: %s", e.what()); }
+        NC(g_nccl.AllGather(c0->gs_pairs.p, c0->gs_gather.p, (size_t)nfld * 2, kNcclFloat64, c0->nccl_comm, c0->stream));
+        pairs.assign((size_t)nr * nfld * 2, 0.0);
+        CU(cudaMemcpyAsync(pairs.data(), c0->gs_gather.p, pairs.size() * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+        CU(cudaStreamSynchronize(c0->stream));
+    }
+    const int nparts = (int)(pairs.size() / ((size_t)nfld * 2));
+    for (int f = 0; f < nfld; ++f) {
+        double tot[2] = {0.0, 0.0};
+        for (int m = 0; m < nparts; ++m) ddpdd_host(&pairs[((size_t)m * nfld + f) * 2], tot);
+        out[f] = tot[0];                                               // REAL(ctmp, wp)  (lib_fortran_generic.h90:64)
+    }
+    return 0;
+}
+
+int nemo_glob_sum_dev(nemo_fct_handle h, const char *cdname, int nfld, const double *const *ptab, const double *pw3d, const double *tmask_i,
+                      int ipk, double *out)
+{
+    (void)cdname;
+    if (need_single(h, "nemo_glob_sum_dev")) return 1;
+    std::vector<Ctx *> g{h};
+    const double *const *pt[1] = {ptab};
+    const double *w[1] = {pw3d}, *t[1] = {tmask_i};
+    return glob_sum_common(g, nfld, pt, pw3d ? w : nullptr, t, ipk, out);
+}
+
+int nemo_group_glob_sum_dev(nemo_fct_handle *hs, int n, const char *cdname, int nfld, const double *const *const *ptab, const double *const *pw3d,
+                            const double *const *tmask_i, int ipk, double *out)
+{
+    (void)cdname;
+    if (!hs || n < 1) return fail("bad arguments");
+    std::vector<Ctx *> g(hs, hs + n);
+    if ((int)g[0]->group.size() != n) return fail("nemo_group_glob_sum_dev: call nemo_fct_comm_init_local first");
+    return glob_sum_common(g, nfld, ptab, pw3d, tmask_i, ipk, out);
 }
 
 int nemo_group_lbc_lnk_multi_dev(nemo_fct_handle *hs, int n, const char *cdname, int nfld, double *const *const *ptab,
