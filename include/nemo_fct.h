@@ -145,6 +145,12 @@ int nemo_tra_adv_transports_dev(nemo_fct_handle h, const double *e2u, const doub
  * mle additions are not applied) into work arrays owned by the context, and calls tra_adv_fct on tsb, tsn, tsa (jpts tracers).
  * nemo_trc_adv_dev is trc_adv (trcadv.F90:70-145) for the passive tracers: it REUSES the transports of the last
  * nemo_tra_adv_dev call instead of rebuilding them (the reference recomputes the same three arrays, trcadv.F90:93-108).   */
+/* The additions of tra_adv to the Eulerian transports that nemo_tra_adv_dev does NOT apply: Stokes drift (ln_wave .AND. ln_sdw,
+ * traadv.F90:103-107), the z-tilde / layer thickness transports (ln_vvl_ztilde .OR. ln_vvl_layer, :116-119), the eddy-induced
+ * transport (ln_ldfeiv .AND. .NOT. ln_ldfeiv_dia, :126-127) and the mixed-layer eddy transport (ln_mle, :129).  The host
+ * declares its namelist switches once; with any of them set nemo_tra_adv_dev / nemo_trc_adv_dev fail (no silent omission):
+ * such a host builds zun, zvn, zwn itself and calls nemo_tra_adv_fct_dev.                                                */
+int nemo_fct_declare_transport_options(nemo_fct_handle h, int ln_wave_sdw, int ln_vvl_ztilde_or_layer, int ln_ldfeiv, int ln_mle);
 int nemo_tra_adv_dev(nemo_fct_handle h, int kt, int nit000, int neuler, double rdt, const double *e2u, const double *e1v,
                      const double *e3u_n, const double *e3v_n, const double *un, const double *vn, const double *wn,
                      const double *tsb, const double *tsn, double *tsa, int jpts, int nn_fct_h, int nn_fct_v);

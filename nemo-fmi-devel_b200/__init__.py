@@ -119,6 +119,7 @@ def lib():
         "nemo_fct_comm_report": [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
         "nemo_fct_set_schedule": [vp, i],
         "nemo_fct_set_arithmetic": [vp, i],
+        "nemo_fct_declare_transport_options": [vp, i, i, i, i],
         "nemo_glob_sum_dev": [vp, C.c_char_p, i, C.POINTER(vp), vp, vp, i, dp],
         "nemo_group_glob_sum_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.POINTER(vp), C.POINTER(vp), i, dp],
         "nemo_fct_set_profiling": [vp, i],
@@ -147,7 +148,7 @@ ABI_SYMBOLS = (
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
     "nemo_fct_profile_read nemo_fct_selftest_division nemo_fct_set_arithmetic "
-    "nemo_glob_sum_dev nemo_group_glob_sum_dev").split()
+    "nemo_glob_sum_dev nemo_group_glob_sum_dev nemo_fct_declare_transport_options").split()
 
 
 class NxtForcing(C.Structure):
@@ -366,6 +367,11 @@ class FctContext:
         if not all(_is_dev(a) for a in arrs):
             raise ValueError("tra_adv: device tensors only")
         _check(lib().nemo_tra_adv_dev(self._h, kt, nit000, neuler, float(rdt), *[_ptr(a) for a in arrs], jpts, nn_fct_h, nn_fct_v))
+
+    def declare_transport_options(self, ln_wave_sdw=False, ln_vvl_ztilde_or_layer=False, ln_ldfeiv=False, ln_mle=False):
+        """namelist switches of the host that add to the Eulerian transports in tra_adv (traadv.F90:103-129); tra_adv / trc_adv
+        refuse to run with any of them set (they would silently drop the addition)"""
+        _check(lib().nemo_fct_declare_transport_options(self._h, int(ln_wave_sdw), int(ln_vvl_ztilde_or_layer), int(ln_ldfeiv), int(ln_mle)))
 
     def trc_adv(self, kt, nittrc000, r2dttrc, trb, trn, tra, jptra, nn_fct_h, nn_fct_v):
         """trc_adv( kt ) of trcadv.F90:70 with nadv = np_FCT; reuses the transports built by the last tra_adv call."""

@@ -148,6 +148,7 @@ struct nemo_fct_ctx {
     void *nccl_comm = nullptr; int nccl_nranks = 0;
     long long n_exchanges = 0, bytes_sent = 0;
     int schedule = 4;                                                  // 4: whole step fused in one kernel where possible; 2: three TMA-tiled kernels
+    int trp_extra = 0;                                                 // nemo_fct_declare_transport_options: bit mask of transport additions the host uses
     int arith = 0;                                                     // nemo_fct_set_arithmetic: 0 strict (IEEE), 1 relaxed divisions in k_fct_fused
     TmaMapCache fused_maps;                                            // schedule 4: tensor maps of k_fct_fused, encoded once per (pointers, shape)
     DevBuf<double> gs_partial, gs_pairs, gs_gather; DevBuf<const double *> gs_ptrs;     // glob_sum scratch
@@ -274,6 +275,13 @@ static int lbc_exchange(std::vector<Ctx *> &g, const LnkCall &call)
             }
         }
         if (grown) for (Ctx *c : g) { CUTHROW(cudaStreamSynchronize(c->stream)); c->jobcache.clear(); }
+        // unbounded distinct calls (raw field pointers are part of the key): start over -- for the WHOLE group and BEFORE any
+        // table of this call is looked up, so that no pointer taken below can be left dangling by a later member's eviction
+        {
+            bool evict = false;
+            for (Ctx *c : g) if (c->jobcache.size() > 64) evict = true;
+            if (evict) for (Ctx *c : g) { CUTHROW(cudaStreamSynchronize(c->stream)); c->jobcache.clear(); }
+        }
         // pass 1b: cached job tables
         for (int m = 0; m < ng; ++m) {
             Ctx *c = g[m];
@@ -284,10 +292,6 @@ static int lbc_exchange(std::vector<Ctx *> &g, const LnkCall &call)
             for (Ctx *o : g) key.append((const char *)&o, sizeof(Ctx *));
             auto it = c->jobcache.find(key);
             if (it == c->jobcache.end()) {
-                if (c->jobcache.size() > 64) {                          // unbounded distinct calls: start over
-                    for (Ctx *o : g) { CUTHROW(cudaStreamSynchronize(o->stream)); o->jobcache.clear(); }
-                    for (int q = 0; q < m; ++q) fresh[q] = true;
-                }
                 it = c->jobcache.emplace(key, std::make_unique<JobTables>()).first;
                 fresh[m] = true;
                 JobTables &t = *it->second;
@@ -557,7 +561,12 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     for (int m = 0; m < ng; ++m) mainst[m] = g[m]->stream;
     auto to_side = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = side; };
     auto to_main = [&]() { for (int m = 0; m < ng; ++m) g[m]->stream = mainst[m]; };
-    struct Restore { std::function<void()> f; ~Restore() { f(); } } restore{to_main};
+    // On every exit -- the early `return 1` of a failed launch or exchange included -- the main stream is made to wait for
+    // whatever the side stream still has in flight, and the contexts get their own stream back
+    struct Restore { std::function<void()> f; ~Restore() { f(); } } restore{[&]() {
+        to_main();
+        if (side != mainst[0] && cudaEventRecord(g[0]->ev_t, side) == cudaSuccess) cudaStreamWaitEvent(mainst[0], g[0]->ev_t, 0);
+    }};
 
     // K1 is split: a band of 8 columns/rows along the edges of its rectangle (everything X2 and the frame read) goes to
     // the side stream, so the whole exchange chain X2..X4 starts after a small launch and hides behind K1-centre + K2
@@ -969,7 +978,15 @@ int nemo_fct_create(const nemo_fct_domain *dom, int device, nemo_fct_handle *out
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev < 1)
         return fail("nemo_fct_create: no usable CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
-    if (device < 0) { const char *lr = getenv("LOCAL_RANK"); device = lr ? atoi(lr) % ndev : 0; }
+    if (device < 0) {                                                  // one rank per GPU: node-local rank from the launcher's environment
+        const char *vars[] = {"LOCAL_RANK", "SLURM_LOCALID", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "PMI_LOCAL_RANK"};
+        const char *lr = nullptr;
+        for (const char *v : vars) if (!lr) lr = getenv(v);
+        if (!lr && L.jpnij > 1)
+            return fail("nemo_fct_create: device = -1 on a %d-rank layout but none of LOCAL_RANK / SLURM_LOCALID / OMPI_COMM_WORLD_LOCAL_RANK / "
+                        "MV2_COMM_WORLD_LOCAL_RANK / MPI_LOCALRANKID / PMI_LOCAL_RANK is set: pass the device explicitly", L.jpnij);
+        device = lr ? atoi(lr) % ndev : 0;
+    }
     if (device >= ndev) return fail("nemo_fct_create: device %d out of range (%d devices)", device, ndev);
     CU(cudaSetDevice(device));
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
@@ -1166,10 +1183,10 @@ int nemo_fct_comm_init(nemo_fct_handle h, const void *id128, int nranks, int ran
 int nemo_fct_comm_init_local(nemo_fct_handle *hs, int n)
 {
     if (!hs || n < 1) return fail("nemo_fct_comm_init_local: bad arguments");
+    for (int m = 0; m < n; ++m) if (!hs[m]) return fail("nemo_fct_comm_init_local: hs[%d] is NULL", m);
     if (n != hs[0]->L.jpnij) return fail("nemo_fct_comm_init_local: %d subdomains given but jpni*jpnj = %d", n, hs[0]->L.jpnij);
     std::vector<Ctx *> g(hs, hs + n);
     for (int m = 0; m < n; ++m) {
-        if (!hs[m]) return fail("NULL handle");
         if (hs[m]->rank != m) return fail("nemo_fct_comm_init_local: hs[%d] has narea-1 = %d (handles must be in rank order)", m, hs[m]->rank);
         if (hs[m]->device != hs[0]->device) return fail("nemo_fct_comm_init_local: all subdomains must be on one device");
     }
@@ -1182,6 +1199,18 @@ int nemo_fct_comm_report(nemo_fct_handle h, long long *n_exchanges, long long *b
     if (!h) return fail("NULL handle");
     if (n_exchanges) *n_exchanges = h->n_exchanges;
     if (bytes_sent) *bytes_sent = h->bytes_sent;
+    return 0;
+}
+
+// the handles of a nemo_group_* call must be exactly the registered in-process communicator, in rank order
+static int group_of(nemo_fct_handle *hs, int n, const char *what, std::vector<Ctx *> &g)
+{
+    if (!hs || n < 1) return fail("%s: bad arguments", what);
+    for (int m = 0; m < n; ++m) if (!hs[m]) return fail("%s: hs[%d] is NULL", what, m);
+    g.assign(hs, hs + n);
+    if ((int)g[0]->group.size() != n) return fail("%s: call nemo_fct_comm_init_local first", what);
+    for (int m = 0; m < n; ++m)
+        if (g[m]->group != g[0]->group || g[0]->group[m] != g[m]) return fail("%s: hs[] is not the registered communicator in rank order", what);
     return 0;
 }
 
@@ -1210,8 +1239,8 @@ int nemo_group_tra_adv_fct_dev(nemo_fct_handle *hs, int n, int kt, int kit000, c
 {
     (void)kt; (void)kit000; (void)cdtype;
     if (!hs || n < 1) return fail("bad arguments");
-    std::vector<Ctx *> g(hs, hs + n);
-    if ((int)g[0]->group.size() != n) return fail("nemo_group_tra_adv_fct_dev: call nemo_fct_comm_init_local first");
+    std::vector<Ctx *> g;
+    if (group_of(hs, n, "nemo_group_tra_adv_fct_dev", g)) return 1;
     std::vector<FctCall> a(n);
     for (int m = 0; m < n; ++m) a[m] = FctCall{pun[m], pvn[m], pwn[m], ptb[m], ptn[m], pta[m]};
     return run_fct(g, a, p2dt, kjpt, kn_fct_h, kn_fct_v);
@@ -1283,11 +1312,27 @@ int nemo_tra_adv_transports_dev(nemo_fct_handle h, const double *e2u, const doub
     return 0;
 }
 
+int nemo_fct_declare_transport_options(nemo_fct_handle h, int ln_wave_sdw, int ln_vvl_ztilde_or_layer, int ln_ldfeiv, int ln_mle)
+{
+    if (!h) return fail("NULL handle");
+    for (Ctx *o : h->group) o->trp_extra = (ln_wave_sdw ? 1 : 0) | (ln_vvl_ztilde_or_layer ? 2 : 0) | (ln_ldfeiv ? 4 : 0) | (ln_mle ? 8 : 0);
+    return 0;
+}
+
+static int refuse_transport_additions(const Ctx *h, const char *what)
+{
+    if (!h->trp_extra) return 0;
+    return fail("%s: the host declared transport additions (%s%s%s%s) that this entry point does not apply (traadv.F90:103-129): build zun, zvn, "
+                "zwn on the host side and call nemo_tra_adv_fct_dev", what, h->trp_extra & 1 ? "Stokes drift " : "", h->trp_extra & 2 ? "z-tilde/layer " : "",
+                h->trp_extra & 4 ? "ldf_eiv_trp " : "", h->trp_extra & 8 ? "tra_mle_trp" : "");
+}
+
 int nemo_tra_adv_dev(nemo_fct_handle h, int kt, int nit000, int neuler, double rdt, const double *e2u, const double *e1v,
                      const double *e3u_n, const double *e3v_n, const double *un, const double *vn, const double *wn,
                      const double *tsb, const double *tsn, double *tsa, int jpts, int nn_fct_h, int nn_fct_v)
 {
     if (need_single(h, "nemo_tra_adv_dev")) return 1;
+    if (refuse_transport_additions(h, "nemo_tra_adv_dev")) return 1;
     if (!e2u || !e1v || !e3u_n || !e3v_n || !un || !vn || !wn || !tsb || !tsn || !tsa) return fail("tra_adv: NULL array");
     // set time step (traadv.F90:95-97): Euler at nit000 when neuler = 0, else leap-frog; unchanged after nit000+1
     if (neuler == 0 && kt == nit000) h->r2dt = rdt;
@@ -1306,6 +1351,7 @@ int nemo_trc_adv_dev(nemo_fct_handle h, int kt, int nittrc000, double r2dttrc, c
                      int jptra, int nn_fct_h, int nn_fct_v)
 {
     if (need_single(h, "nemo_trc_adv_dev")) return 1;
+    if (refuse_transport_additions(h, "nemo_trc_adv_dev")) return 1;
     if (!h->have_trp) return fail("trc_adv: the effective transports have not been built yet (call nemo_tra_adv_dev first)");
     if (!trb || !trn || !tra) return fail("trc_adv: NULL array");
     return nemo_tra_adv_fct_dev(h, kt, nittrc000, "TRC", r2dttrc, h->zun.p, h->zvn.p, h->zwn.p, trb, trn, tra, jptra, nn_fct_h, nn_fct_v);
@@ -1380,8 +1426,8 @@ int nemo_group_tra_adv_mus_dev(nemo_fct_handle *hs, int n, int kt, int kit000, c
 {
     (void)kt; (void)kit000; (void)cdtype;
     if (!hs || n < 1) return fail("bad arguments");
-    std::vector<Ctx *> g(hs, hs + n);
-    if ((int)g[0]->group.size() != n) return fail("nemo_group_tra_adv_mus_dev: call nemo_fct_comm_init_local first");
+    std::vector<Ctx *> g;
+    if (group_of(hs, n, "nemo_group_tra_adv_mus_dev", g)) return 1;
     std::vector<MusCall> a(n);
     for (int m = 0; m < n; ++m) a[m] = MusCall{pun[m], pvn[m], pwn[m], ptb[m], pta[m]};
     return run_mus(g, a, p2dt, kjpt);
@@ -1436,8 +1482,8 @@ int nemo_group_tra_adv_cen_dev(nemo_fct_handle *hs, int n, int kt, int kit000, c
 {
     (void)kt; (void)kit000; (void)cdtype;
     if (!hs || n < 1) return fail("bad arguments");
-    std::vector<Ctx *> g(hs, hs + n);
-    if ((int)g[0]->group.size() != n) return fail("nemo_group_tra_adv_cen_dev: call nemo_fct_comm_init_local first");
+    std::vector<Ctx *> g;
+    if (group_of(hs, n, "nemo_group_tra_adv_cen_dev", g)) return 1;
     std::vector<CenCall> a(n);
     for (int m = 0; m < n; ++m) a[m] = CenCall{pun[m], pvn[m], pwn[m], ptn[m], pta[m]};
     return run_cen(g, a, kjpt, kn_cen_h, kn_cen_v);
@@ -1459,8 +1505,8 @@ int nemo_group_tra_nxt_dev(nemo_fct_handle *hs, int n, int kt, int nit000, int l
 {
     (void)kt; (void)nit000;
     if (!hs || n < 1 || !ptb || !ptn || !pta) return fail("bad arguments");
-    std::vector<Ctx *> g(hs, hs + n);
-    if ((int)g[0]->group.size() != n) return fail("nemo_group_tra_nxt_dev: call nemo_fct_comm_init_local first");
+    std::vector<Ctx *> g;
+    if (group_of(hs, n, "nemo_group_tra_nxt_dev", g)) return 1;
     std::vector<NxtCall> a(n);
     for (int m = 0; m < n; ++m)
         a[m] = NxtCall{f ? f[m] : nullptr, ptb[m], ptn[m], pta[m], psbc_tc ? psbc_tc[m] : nullptr, psbc_tc_b ? psbc_tc_b[m] : nullptr};
@@ -1560,8 +1606,8 @@ int nemo_group_glob_sum_dev(nemo_fct_handle *hs, int n, const char *cdname, int 
 {
     (void)cdname;
     if (!hs || n < 1) return fail("bad arguments");
-    std::vector<Ctx *> g(hs, hs + n);
-    if ((int)g[0]->group.size() != n) return fail("nemo_group_glob_sum_dev: call nemo_fct_comm_init_local first");
+    std::vector<Ctx *> g;
+    if (group_of(hs, n, "nemo_group_glob_sum_dev", g)) return 1;
     return glob_sum_common(g, nfld, ptab, pw3d, tmask_i, ipk, out);
 }
 
@@ -1570,8 +1616,8 @@ int nemo_group_lbc_lnk_multi_dev(nemo_fct_handle *hs, int n, const char *cdname,
 {
     (void)cdname;
     if (!hs || n < 1) return fail("bad arguments");
-    std::vector<Ctx *> g(hs, hs + n);
-    if ((int)g[0]->group.size() != n) return fail("nemo_group_lbc_lnk_multi_dev: call nemo_fct_comm_init_local first");
+    std::vector<Ctx *> g;
+    if (group_of(hs, n, "nemo_group_lbc_lnk_multi_dev", g)) return 1;
     return lnk_common(g, nfld, ptab, cd_nat, psgn, ipk, has_pval, pval);
 }
 

@@ -30,6 +30,11 @@ MODULE traadv_fct
    USE lbcnfd  , ONLY : isendto, nsndto   ! no-gather fold partners (lbcnfd.F90:53-55), part of the domain descriptor
 
    IMPLICIT NONE
+#if defined key_mpp_mpi
+   ! lib_mpp is PRIVATE and includes mpif.h inside the module (lib_mpp.F90:63,116): only mpi_comm_oce is exported, so the MPI
+   ! constants and MPI_BCAST used by tra_adv_fct_gpu_init have to come from here
+   INCLUDE 'mpif.h'
+#endif
    PRIVATE
 
    PUBLIC   tra_adv_fct        ! called by traadv.F90 and trcadv.F90
@@ -151,7 +156,8 @@ CONTAINS
 #else
       ydom%key_mpp_mpi = 0
 #endif
-      ! device = -1 : the library uses LOCAL_RANK (one MPI rank per GPU)
+      ! device = -1 : the library takes the node-local rank from the launcher's environment (LOCAL_RANK, SLURM_LOCALID,
+      ! OMPI_COMM_WORLD_LOCAL_RANK, MV2_COMM_WORLD_LOCAL_RANK, MPI_LOCALRANKID: one MPI rank per GPU) and refuses to guess
       IF( nemo_fct_create( ydom, -1_C_INT, nhandle ) /= 0 )   CALL gpu_stop( 'tra_adv_fct_gpu_init' )
       IF( nemo_fct_set_domain_arrays( nhandle, tmask, umask, vmask, wmask, e1e2t, r1_e1e2t, mikt, mbkt,   &
          &                            MERGE( 1, 0, ln_linssh ), MERGE( 1, 0, ln_isfcav ) ) /= 0 )   CALL gpu_stop( 'tra_adv_fct_gpu_init' )

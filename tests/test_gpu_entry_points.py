@@ -167,4 +167,10 @@ def test_tra_adv_and_trc_adv_device_resident(N, O):
     c2.set_e3t(gf["e3t_b"], gf["e3t_n"], gf["e3t_a"])
     with pytest.raises(N.NemoFctError, match="tra_adv"):
         c2.trc_adv(1, 1, rdt, dev(trb), dev(trn), tra, 5, 2, 2)       # transports not built yet
+    # a host whose namelist adds eddy-induced / Stokes / mle transports (traadv.F90:103-129) is refused, not served a wrong answer
+    c2.declare_transport_options(ln_ldfeiv=True)
+    with pytest.raises(N.NemoFctError, match="ldf_eiv_trp"):
+        c2.tra_adv(nit000, nit000, 0, rdt, *t, dev(gf["pta"]), 2, 4, 4)
+    c2.declare_transport_options()
+    c2.tra_adv(nit000, nit000, 0, rdt, *t, dev(gf["pta"]), 2, 4, 4)
     c2.close(); w.close()

@@ -9,6 +9,20 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
+def _tmask_i(dom, tmask):
+    """dom_oce's interior mask of one subdomain (dommsk.F90:200-238): 0 on the local halo rows / columns and, under a
+    T-pivot fold, on the duplicated half of the last interior row; times the surface mask"""
+    jpj, jpi = tmask.shape[-2:]
+    th = np.ones((jpj, jpi))
+    th[:, :1] = 0.0; th[:, dom.nlci - 1:] = 0.0
+    th[:1, :] = 0.0; th[dom.nlcj - 1:, :] = 0.0
+    if dom.jperio in (3, 4) and dom.nlej + dom.njmpp - 1 == dom.jpjglo:
+        mig = np.arange(1, jpi + 1) + dom.nimpp - 1
+        tpol = np.where(mig >= dom.jpiglo // 2 + 1, 0.0, 1.0)
+        th[dom.nlej - 2, 1:dom.nlci - 1] *= tpol[1:dom.nlci - 1]
+    return np.ascontiguousarray(tmask.max(axis=0) * th)
+
+
 def _fields(O, G, GJ, K, jperio, seed):
     gf = H.random_fields(O, G, GJ, K, jperio, kjpt=3, seed=seed)
     cvol = gf["e1e2t"][None] * gf["e3t_n"] * gf["tmask"]
@@ -25,7 +39,10 @@ def test_glob_sum_equals_the_oracle_and_ignores_the_decomposition(N, O, jperio):
     want = None
     for (jpni, jpnj) in ((1, 1), (2, 2), (3, 2)):
         w = O.World(G, GJ, K, jperio, jpni, jpnj)
-        ti = w.scatter(np.ascontiguousarray(gf["tmask_i"]))
+        doms = [N.mpp_init(G, GJ, K, jperio, jpni, jpnj, r + 1) for r in range(jpni * jpnj)]
+        ti = [_tmask_i(d, tm) for d, tm in zip(doms, w.scatter(gf["tmask"]))]
+        if jpni * jpnj == 1:
+            assert np.array_equal(ti[0], gf["tmask_i"])                             # the helper restates dom_msk
         lv = w.scatter(cvol)
         lt = [w.scatter(np.ascontiguousarray(big[jn])) for jn in range(3)]
         ref = [O.glob_sum(w, [np.ascontiguousarray(a * v) for a, v in zip(lt[jn], lv)], ti)[0] for jn in range(3)]
