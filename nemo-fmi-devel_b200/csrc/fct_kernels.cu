@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <type_traits>
@@ -66,6 +67,10 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 // makes the initialised mbarriers visible to the async proxy (TMA) before the first copy is issued
 __device__ __forceinline__ void mbar_init_fence()
@@ -397,14 +402,15 @@ bool prepare_fct_fused(const FctArgs &a, TmaMapCache *cache)
     return true;
 }
 
-void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache)
+void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache, int max_blocks)
 {
     const int ni = a.out.i1 - a.out.i0 + 1, nj = a.out.j1 - a.out.j0 + 1;
     FusedMaps tm;
     memcpy(&tm, cache->maps, sizeof tm);
-    const dim3 g((unsigned)(((ni + FOX - 1) / FOX) * a.kjpt), (unsigned)((nj + FOY - 1) / FOY), (unsigned)a.nkchunk);
+    const int gx = ((ni + FOX - 1) / FOX) * a.kjpt, gy = (nj + FOY - 1) / FOY, nwork = gx * gy * a.nkchunk;
+    const int nblk = std::max(1, std::min(nwork, max_blocks));
 #define LFU(H, V, A) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_fused<H, V, A>, kFusedSmemBytes, done); \
-                          k_fct_fused<H, V, A><<<g, FX * FY, kFusedSmemBytes, s>>>(a, tm); } while (0)
+                          k_fct_fused<H, V, A><<<nblk, FX * FY, kFusedSmemBytes, s>>>(a, tm, gx, gy, nwork); } while (0)
 #define LFU2(H, V) do { if (a.arith == 0) LFU(H, V, 0); else LFU(H, V, 1); } while (0)
     if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LFU2(2, 2);
     else if (a.kn_fct_h == 2)               LFU2(2, 4);

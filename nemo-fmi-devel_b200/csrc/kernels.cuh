@@ -77,7 +77,8 @@ struct TmaMapCache {
 // prepare: false if the TMA path cannot be used (odd jpi, even out.i0, masks not derived from tmask, unaligned arrays, no
 // driver entry point) -- nothing has been launched then and the caller falls back to the three-kernel schedule
 bool prepare_fct_fused(const FctArgs &a, TmaMapCache *cache);
-void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache);
+// max_blocks: persistent grid size (<= number of SMs to occupy)
+void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache, int max_blocks);
 
 // interp_4th_cpt                                                            traadv_fct.F90:517-616
 void launch_cpt_pivots(int jpi, int jpj, int jpk, const double *wmask, const int *mikt, const int *mbkt,

@@ -150,6 +150,7 @@ struct nemo_fct_ctx {
     int schedule = 4;                                                  // 4: whole step fused in one kernel where possible; 2: three TMA-tiled kernels
     int trp_extra = 0;                                                 // nemo_fct_declare_transport_options: bit mask of transport additions the host uses
     int arith = 0;                                                     // nemo_fct_set_arithmetic: 0 strict (IEEE), 1 relaxed divisions in k_fct_fused
+    int nsm = 148;                                                     // SMs of the device (persistent k_fct_fused: one block per SM it occupies)
     TmaMapCache fused_maps;                                            // schedule 4: tensor maps of k_fct_fused, encoded once per (pointers, shape)
     DevBuf<double> gs_partial, gs_pairs, gs_gather; DevBuf<const double *> gs_ptrs;     // glob_sum scratch
     TmaMapCache cpt_maps[3];                                           // tensor map of k_interp_4th_cpt_tiled: tra_adv_fct, tra_adv_cen, interp_4th_cpt entry
@@ -607,8 +608,17 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     if (early_side) CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
     if (v == 4) CPT();                                                                             // ztw, whole interior
     if (!early_side) CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
-    if (one_kernel && frame_order >= 1) side = mainst[0];                                          // frame chain first, same stream
-    if (one_kernel) { if (frame_order != 1) EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps)); }
+    if (one_kernel && frame_order >= 1) side = mainst[0];
+    // k_fct_fused is persistent, one 512-thread block per SM it occupies.  When the frame chain runs beside it, a few SMs are
+    // left free for that chain's small kernels and the NCCL transfers: otherwise each of their ~25 launches waits for whole-SM
+    // blocks to retire (measured at 4x2 ORCA025: the chain, not the inner kernel, set the step time).
+    static const int reserve_env = getenv("NEMO_FCT_RESERVE_SMS") ? atoi(getenv("NEMO_FCT_RESERVE_SMS")) : -1;
+    const int reserve = (one_kernel && frame_order == 0) ? (reserve_env >= 0 ? reserve_env : 12) : 0;
+    // Without a reservation every work item is its own block (the hardware scheduler staggers them: measured 5 % faster and
+    // 30 % less DRAM traffic than 148 persistent blocks marching in lockstep, whose tracer pairs miss each other in L2)
+    const int fused_blocks = reserve > 0 ? std::max(8, g[0]->nsm - reserve) : (1 << 30);
+                                          // frame chain first, same stream
+    if (one_kernel) { if (frame_order != 1) EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps, fused_blocks)); }
     else EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1c[m], c->stream))) launch_fct_low_antidiff_inner(k1c[m], c->stream));
     if (!split) CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
     // frame
@@ -637,7 +647,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     EACH(P_FINAL, launch_fct_final(fin[m], c->stream));
     CU(cudaEventRecord(g[0]->ev_t, side));
     to_main();
-    if (one_kernel && frame_order == 1) EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps));
+    if (one_kernel && frame_order == 1) EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps, fused_blocks));
     if (!one_kernel) {
         if (split) CU(cudaStreamWaitEvent(mainst[0], g[0]->ev_k1, 0));                             // K2 reads the band as well
         EACH(P_NONOSC_FINAL, if (!(c->schedule == 3 && launch_fct_nonosc_final_tma(k2[m], c->stream))) launch_fct_nonosc_final(k2[m], c->stream));
@@ -992,7 +1002,7 @@ int nemo_fct_create(const nemo_fct_domain *dom, int device, nemo_fct_handle *out
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("nemo_fct_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     Ctx *c = new Ctx();
-    c->dom = *dom; c->L = L; c->device = device; c->rank = dom->narea - 1;
+    c->dom = *dom; c->L = L; c->device = device; c->rank = dom->narea - 1; c->nsm = prop.multiProcessorCount;
     c->jpij = (size_t)dom->jpi * dom->jpj; c->n3 = c->jpij * dom->jpk;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
     c->stream = c->own_stream;

@@ -32,6 +32,7 @@ static void emu_run_blocks3(int gx, int gy, int gz, int nthreads, size_t smem_by
                     blockIdx = {(unsigned)bx, (unsigned)by, (unsigned)bz};
                     threadIdx = {(unsigned)t, 0, 0};
                     blockDim = {(unsigned)nthreads, 1, 1};
+                    gridDim = {(unsigned)gx, (unsigned)gy, (unsigned)gz};
                     emu_block_barrier = &bar;
                     emu_block_smem = base;
                     kernel(args...);

@@ -55,7 +55,9 @@ int emu_fct_fused(int jpi, int jpj, int jpk, int kjpt, int h, int v, int ln_lins
     for (int q = 0; q < FP_COUNT; ++q) set_map(&tm.p[q], pb[q], jpi, jpj, pn[q], FX, FY);
     const int gx = ((ni + FOX - 1) / FOX) * kjpt, gy = (nj + FOY - 1) / FOY;
     emu_tma_violations = 0;
-#define LFU(H, V) emu_run_blocks3(gx, gy, nkchunk, FX * FY, kFusedSmemBytes, k_fct_fused<H, V, 0>, a, tm)
+    // persistent grid: 3 blocks share the (tile, tracer, chunk) work items round-robin, as on the device with one block per SM
+    const int nwork = gx * gy * nkchunk, nblk = nwork < 3 ? nwork : 3;
+#define LFU(H, V) emu_run_blocks3(nblk, 1, 1, FX * FY, kFusedSmemBytes, k_fct_fused<H, V, 0>, a, tm, gx, gy, nwork)
     if (h == 2 && v == 2) LFU(2, 2); else if (h == 2) LFU(2, 4); else if (v == 2) LFU(4, 2); else LFU(4, 4);
 #undef LFU
     return emu_tma_violations;

@@ -25,6 +25,7 @@ inline void mbar_init(unsigned long long *bar, unsigned)
     __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST);
 }
 inline void mbar_init_fence() {}
+inline void mbar_inval(unsigned long long *) {}
 inline void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
     std::lock_guard<std::mutex> g(emu_bars_mutex);
