@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -409,8 +410,10 @@ void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache
     memcpy(&tm, cache->maps, sizeof tm);
     const int gx = ((ni + FOX - 1) / FOX) * a.kjpt, gy = (nj + FOY - 1) / FOY, nwork = gx * gy * a.nkchunk;
     const int nblk = std::max(1, std::min(nwork, max_blocks));
+    static const int skew_env = getenv("NEMO_FCT_SKEW_NS") ? atoi(getenv("NEMO_FCT_SKEW_NS")) : 600;
+    const int skew_ns = nblk < nwork ? skew_env : 0;                  // persistent blocks only
 #define LFU(H, V, A) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_fused<H, V, A>, kFusedSmemBytes, done); \
-                          k_fct_fused<H, V, A><<<nblk, FX * FY, kFusedSmemBytes, s>>>(a, tm, gx, gy, nwork); } while (0)
+                          k_fct_fused<H, V, A><<<nblk, FX * FY, kFusedSmemBytes, s>>>(a, tm, gx, gy, nwork, skew_ns); } while (0)
 #define LFU2(H, V) do { if (a.arith == 0) LFU(H, V, 0); else LFU(H, V, 1); } while (0)
     if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LFU2(2, 2);
     else if (a.kn_fct_h == 2)               LFU2(2, 4);

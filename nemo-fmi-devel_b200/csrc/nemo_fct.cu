@@ -604,7 +604,8 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     // Schedule 4 overlaps the whole frame chain with the compact-scheme solve of the main stream (small blocks that leave room
     // on every SM; k_fct_fused owns whole SMs and would be displaced block by block): the side stream starts before CPT and
     // solves the frame's own columns itself.
-    const bool early_side = one_kernel && frame_order == 0;
+    static const int early_env = getenv("NEMO_FCT_EARLY_SIDE") ? atoi(getenv("NEMO_FCT_EARLY_SIDE")) : 0;
+    const bool early_side = one_kernel && frame_order == 0 && early_env != 0;
     if (early_side) CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
     if (v == 4) CPT();                                                                             // ztw, whole interior
     if (!early_side) CU(cudaEventRecord(g[0]->ev_a, mainst[0]));
@@ -613,11 +614,18 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     // left free for that chain's small kernels and the NCCL transfers: otherwise each of their ~25 launches waits for whole-SM
     // blocks to retire (measured at 4x2 ORCA025: the chain, not the inner kernel, set the step time).
     static const int reserve_env = getenv("NEMO_FCT_RESERVE_SMS") ? atoi(getenv("NEMO_FCT_RESERVE_SMS")) : -1;
-    const int reserve = (one_kernel && frame_order == 0) ? (reserve_env >= 0 ? reserve_env : 12) : 0;
+    const int reserve = (one_kernel && frame_order == 0) ? (reserve_env >= 0 ? reserve_env : 16) : 0;
     // Without a reservation every work item is its own block (the hardware scheduler staggers them: measured 5 % faster and
     // 30 % less DRAM traffic than 148 persistent blocks marching in lockstep, whose tracer pairs miss each other in L2)
-    const int fused_blocks = reserve > 0 ? std::max(8, g[0]->nsm - reserve) : (1 << 30);
-                                          // frame chain first, same stream
+    static const int force_pers = getenv("NEMO_FCT_FORCE_PERSISTENT") ? atoi(getenv("NEMO_FCT_FORCE_PERSISTENT")) : 0;   // experiment knob
+    const int fused_blocks = (reserve > 0 || force_pers) ? std::max(8, g[0]->nsm - reserve) : (1 << 30);
+    // The band of K1 (8 columns / rows along the edges: ~1000 blocks at 362 x 605) is too heavy for the reserved SMs: in the
+    // overlapped arrangement it runs on the main stream, on the whole GPU, before k_fct_fused takes the SMs (0.1 ms at 4x2)
+    const bool band_on_main = one_kernel && frame_order == 0 && !early_side && split;
+    if (band_on_main) {
+        EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff_inner(k1b[m], c->stream));
+        CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
+    }
     if (one_kernel) { if (frame_order != 1) EACH(P_FUSED, launch_fct_fused(k2[m], c->stream, &c->fused_maps, fused_blocks)); }
     else EACH(P_LOW_INNER, if (!(c->schedule >= 2 && launch_fct_low_antidiff_tma(k1c[m], c->stream))) launch_fct_low_antidiff_inner(k1c[m], c->stream));
     if (!split) CU(cudaEventRecord(g[0]->ev_k1, mainst[0]));
@@ -633,7 +641,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         if (exch({&Ctx::zltu, &Ctx::zltv}, "TT", {1.0, 1.0})) return 1;                            // X1
     }
     EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff(lowf[m], c->stream));
-    if (split) {
+    if (split && !band_on_main) {
         EACH(P_LOW_ANTIDIFF, launch_fct_low_antidiff_inner(k1b[m], c->stream));
         CU(cudaEventRecord(g[0]->ev_k1, side));
     } else {

@@ -57,7 +57,7 @@ int emu_fct_fused(int jpi, int jpj, int jpk, int kjpt, int h, int v, int ln_lins
     emu_tma_violations = 0;
     // persistent grid: 3 blocks share the (tile, tracer, chunk) work items round-robin, as on the device with one block per SM
     const int nwork = gx * gy * nkchunk, nblk = nwork < 3 ? nwork : 3;
-#define LFU(H, V) emu_run_blocks3(nblk, 1, 1, FX * FY, kFusedSmemBytes, k_fct_fused<H, V, 0>, a, tm, gx, gy, nwork)
+#define LFU(H, V) emu_run_blocks3(nblk, 1, 1, FX * FY, kFusedSmemBytes, k_fct_fused<H, V, 0>, a, tm, gx, gy, nwork, 0)
     if (h == 2 && v == 2) LFU(2, 2); else if (h == 2) LFU(2, 4); else if (v == 2) LFU(4, 2); else LFU(4, 4);
 #undef LFU
     return emu_tma_violations;
