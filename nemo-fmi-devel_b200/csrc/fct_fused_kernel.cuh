@@ -120,7 +120,7 @@ template <int ARITH> inline double div_a(double x, double y) { return x / y; }
 // Persistent: the grid is at most one block per SM the launcher wants to use (it may leave a few SMs to the frame chain and the
 // NCCL kernels of the side stream); block b takes the (tile, tracer, jk chunk) work items b, b + gridDim.x, ... (tracer index
 // fastest; all items cost the same, so a static assignment balances as well as a counter).
-template <int H, int V, int ARITH>
+template <int H, int V, int ARITH, bool PERSISTENT>
 __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const __grid_constant__ FusedMaps maps, int gx, int gy, int nwork, int skew_ns)
 {
     NEMO_DYN_SMEM_ALIGNED(unsigned char, fu_smem, 128);
@@ -137,18 +137,21 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
     const CUtensorMap *mh = maps.h, *mp = maps.p;                       // descriptor addresses stay in the parameter space
     bool first_item = true;
 
-  // static round-robin over the work items: every index below derives from blockIdx / gridDim / the loop counter, so the
-  // compiler keeps the tile geometry in uniform registers (a counter fetched through shared memory cost 10 vector registers
-  // at the 128-register cap: +4.6 % kernel time, measured)
-  for (int work = (int)blockIdx.x; work < nwork; work += (int)gridDim.x) {
-    __syncthreads();                                     // the previous work item is finished by every thread
-    const int wx = work % gx, wy = (work / gx) % gy, chunk = work / (gx * gy);
+  // PERSISTENT: static round-robin over the work items -- every index below derives from blockIdx / gridDim / the loop
+  // counter, so the compiler keeps the tile geometry in uniform registers (a counter fetched through shared memory cost 10
+  // vector registers at the 128-register cap: +4.6 % kernel time, measured).  Otherwise one block per work item, no loop:
+  // the loop form alone costs 3.7 % (measured), so the lone-subdomain path does not pay for it.
+  int work = (int)blockIdx.x;
+  do {
+    if (PERSISTENT) __syncthreads();                     // the previous work item is finished by every thread
+    const int wx = PERSISTENT ? work % gx : (int)blockIdx.x, wy = PERSISTENT ? (work / gx) % gy : (int)blockIdx.y,
+              chunk = PERSISTENT ? work / (gx * gy) : (int)blockIdx.z;
     const int jn = wx % a.kjpt;                                          // tracer index fastest: the shared boxes of a tile hit L2
     const int X0 = a.out.i0 - 1 - FHALO + (wx / a.kjpt) * FOX;           // 0-based column / row of thread (0,0)
     const int Y0 = a.out.j0 - 1 - FHALO + wy * FOY;
     int ka, kb;
     { const int per = (jpk - 1 + a.nkchunk - 1) / a.nkchunk; ka = 1 + chunk * per; kb = min(jpk - 1, ka + per - 1); }
-    if (ka > kb) continue;
+    if (ka > kb) { if (PERSISTENT) { work += (int)gridDim.x; continue; } else return; }
     const int a_lo = max(1, ka - 2), a_hi = min(jpk, kb + 2);          // levels of stage A
     const int b_lo = max(1, ka - 1), b_hi = min(jpk - 1, kb + 1);      // levels of stage B
     const int lastlev = min(jpk, a_hi + 1);                             // last level whose boxes are loaded
@@ -171,9 +174,9 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
         // Persistent blocks march in lockstep: the blocks of the kjpt tracers of one tile would request the shared boxes (tmask, pun,
         // pvn, pwn, e3t_*) in the same instant and BOTH miss in L2 (measured: +41 % DRAM reads).  A skew of a fraction of a level
         // per tracer lets the later ones hit, as the staggered start of a one-block-per-item launch does by itself.
-        if (skew_ns > 0 && jn > 0) __nanosleep((unsigned)(jn * skew_ns));
+        if (PERSISTENT && skew_ns > 0 && jn > 0) __nanosleep((unsigned)(jn * skew_ns));
 #endif
-        for (int s = 0; s < FSTAGES; ++s) { if (!first_item) mbar_inval(&full[s]); mbar_init(&full[s], 1); }
+        for (int s = 0; s < FSTAGES; ++s) { if (PERSISTENT && !first_item) mbar_inval(&full[s]); mbar_init(&full[s], 1); }
         mbar_init_fence();
         issue(a_lo);
         if (a_lo + 1 <= lastlev) issue(a_lo + 1);
@@ -344,5 +347,6 @@ __global__ void __launch_bounds__(FX * FY, 1) k_fct_fused(const FctArgs a, const
 #pragma unroll 3
     for (; it <= steady_hi; ++it) level_step(std::true_type{}, it);
     for (; it <= kb + 2; ++it) level_step(std::false_type{}, it);
-  }
+    work += (int)gridDim.x;
+  } while (PERSISTENT && work < nwork);
 }

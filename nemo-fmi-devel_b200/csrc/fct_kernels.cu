@@ -410,10 +410,13 @@ void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache
     memcpy(&tm, cache->maps, sizeof tm);
     const int gx = ((ni + FOX - 1) / FOX) * a.kjpt, gy = (nj + FOY - 1) / FOY, nwork = gx * gy * a.nkchunk;
     const int nblk = std::max(1, std::min(nwork, max_blocks));
-    static const int skew_env = getenv("NEMO_FCT_SKEW_NS") ? atoi(getenv("NEMO_FCT_SKEW_NS")) : 600;
+    static const int skew_env = getenv("NEMO_FCT_SKEW_NS") ? atoi(getenv("NEMO_FCT_SKEW_NS")) : 0;   // experiment knob: measured to hurt
     const int skew_ns = nblk < nwork ? skew_env : 0;                  // persistent blocks only
-#define LFU(H, V, A) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_fused<H, V, A>, kFusedSmemBytes, done); \
-                          k_fct_fused<H, V, A><<<nblk, FX * FY, kFusedSmemBytes, s>>>(a, tm, gx, gy, nwork, skew_ns); } while (0)
+#define LFU(H, V, A) do { static bool done[kMaxDevices] = {}, donep[kMaxDevices] = {}; \
+                          if (nblk < nwork) { allow_dynamic_smem(k_fct_fused<H, V, A, true>, kFusedSmemBytes, donep); \
+                                              k_fct_fused<H, V, A, true><<<nblk, FX * FY, kFusedSmemBytes, s>>>(a, tm, gx, gy, nwork, skew_ns); } \
+                          else              { allow_dynamic_smem(k_fct_fused<H, V, A, false>, kFusedSmemBytes, done); \
+                                              k_fct_fused<H, V, A, false><<<dim3(gx, gy, a.nkchunk), FX * FY, kFusedSmemBytes, s>>>(a, tm, gx, gy, nwork, 0); } } while (0)
 #define LFU2(H, V) do { if (a.arith == 0) LFU(H, V, 0); else LFU(H, V, 1); } while (0)
     if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LFU2(2, 2);
     else if (a.kn_fct_h == 2)               LFU2(2, 4);
@@ -470,8 +473,14 @@ void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wm
                            const double *pt_in, double *pt_out, cudaStream_t s, TmaMapCache *cache)
 {
     (void)ln_isfcav;
-    // tiled kernel: even jpi (16-byte global strides), 16-byte aligned input, the forward sweep of a tile fits in shared memory
-    const size_t smem = cpt_tiled_smem_bytes(jpk);
+    // tiled kernel: even jpi (16-byte global strides), 16-byte aligned input.  ksplit = levels whose forward sweep stays in shared
+    // memory (the rest is parked in pt_out).  Measured at ORCA025: the whole column in shared memory (8 warps / SM) 1.21 ms;
+    // ksplit 40 / 22 / 10 / 1 (12-20 warps / SM) 1.24 / 1.37 / 1.25 / 1.26 ms -- more resident warps do not pay for the extra global
+    // round trip, so the default keeps every level in shared memory when it fits
+    static const int ks_env = getenv("NEMO_CPT_KSPLIT") ? atoi(getenv("NEMO_CPT_KSPLIT")) : -1;
+    int ksplit = std::max(1, std::min(jpk, ks_env >= 0 ? ks_env : jpk));
+    while (ksplit > 1 && cpt_tiled_smem_bytes(jpk, ksplit) > 110 * 1024) --ksplit;     // deep grids: keep two blocks per SM
+    const size_t smem = cpt_tiled_smem_bytes(jpk, ksplit);
     if (cache && !(jpi & 1) && jpk >= 3 && smem <= 200 * 1024 && utab && simple) {
         const void *key[12] = {pt_in};
         const int dims[4] = {jpi, jpj, jpk, nfld};
@@ -499,7 +508,7 @@ void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wm
             static bool done[kMaxDevices] = {};
             allow_dynamic_smem(k_interp_4th_cpt_tiled, 200 * 1024, done);
             const dim3 g((unsigned)((jpi - 1 + CTX - 1) / CTX), (unsigned)((jpj - 2 + CTY - 1) / CTY), (unsigned)nfld);
-            k_interp_4th_cpt_tiled<<<g, CTX * CTY, smem, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_out, m);
+            k_interp_4th_cpt_tiled<<<g, CTX * CTY, smem, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_out, m, ksplit);
             note_launch();
             return;
         }
