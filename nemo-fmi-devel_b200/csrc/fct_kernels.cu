@@ -479,7 +479,7 @@ void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wm
     // round trip, so the default keeps every level in shared memory when it fits
     static const int ks_env = getenv("NEMO_CPT_KSPLIT") ? atoi(getenv("NEMO_CPT_KSPLIT")) : -1;
     int ksplit = std::max(1, std::min(jpk, ks_env >= 0 ? ks_env : jpk));
-    while (ksplit > 1 && cpt_tiled_smem_bytes(jpk, ksplit) > 110 * 1024) --ksplit;     // deep grids: keep two blocks per SM
+    while (ksplit > 1 && cpt_tiled_smem_bytes(jpk, ksplit) > 116224) --ksplit;     // deep grids: keep two blocks per SM
     const size_t smem = cpt_tiled_smem_bytes(jpk, ksplit);
     if (cache && !(jpi & 1) && jpk >= 3 && smem <= 200 * 1024 && utab && simple) {
         const void *key[12] = {pt_in};
