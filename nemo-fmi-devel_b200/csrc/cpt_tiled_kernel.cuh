@@ -14,30 +14,23 @@
 // rcp_refined, mbarrier + TMA helpers) and fct_column_kernels.cuh (cpt_row); also compiled for the host by tests/emu.
 #pragma once
 
-#ifndef NEMO_CPT_TX
-#define NEMO_CPT_TX 32
-#define NEMO_CPT_TY 4
-#endif
-constexpr int CTX = NEMO_CPT_TX, CTY = NEMO_CPT_TY, CKL = 8, CNB = 4;
+constexpr int CTX = 32, CTY = 4, CKL = 8, CNB = 4;
 constexpr int kCptBoxBytes = CTX * CTY * CKL * 8;
-// forward-sweep values of the levels 2..ksplit stay in shared memory; the levels above ksplit are parked in pt_out itself (global,
-// read back from L2 a few microseconds later and then overwritten by the solution): shared memory per column is what caps
-// the number of resident warps of this latency-bound solve (8 warps / SM with the whole column in shared memory)
-inline size_t cpt_tiled_smem_bytes(int jpk, int ksplit) { return (size_t)(ksplit + 1) * CTX * CTY * 8 + (size_t)CNB * kCptBoxBytes + 3 * (size_t)(jpk + 2) * 8 + 64; }
+inline size_t cpt_tiled_smem_bytes(int jpk) { return (size_t)(jpk + 1) * CTX * CTY * 8 + (size_t)CNB * kCptBoxBytes + 3 * (size_t)(jpk + 2) * 8 + 64; }
 
 struct CptMap { CUtensorMap m; };
 
 __global__ void __launch_bounds__(CTX * CTY) k_interp_4th_cpt_tiled(int jpi, int jpj, int jpk, const double *__restrict__ wmask,
                                                                     const int *__restrict__ mikt, const int *__restrict__ mbkt,
                                                                     const double *__restrict__ zwt, const unsigned char *__restrict__ simple,
-                                                                    const double *__restrict__ utab, double *pt_out_all,
-                                                                    const __grid_constant__ CptMap map, int ksplit)
+                                                                    const double *__restrict__ utab, double *__restrict__ pt_out_all,
+                                                                    const __grid_constant__ CptMap map)
 {
     NEMO_DYN_SMEM_ALIGNED(unsigned char, cpt_smem, 128);
     constexpr int NT = CTX * CTY;
     double *ring = reinterpret_cast<double *>(cpt_smem);                                  // [CNB][CKL][CTY][CTX]
-    double *zbuf = ring + (size_t)CNB * CKL * NT;                                         // [ksplit + 1][NT]: forward sweep, levels <= ksplit
-    double *ut = zbuf + (size_t)(ksplit + 1) * NT, *rt = ut + (jpk + 2), *r2 = rt + (jpk + 2);  // pivots, 1/pivot(k-1), refined reciprocals
+    double *zbuf = ring + (size_t)CNB * CKL * NT;                                         // [jpk + 1][NT]: forward sweep
+    double *ut = zbuf + (size_t)(jpk + 1) * NT, *rt = ut + (jpk + 2), *r2 = rt + (jpk + 2);  // pivots, 1/pivot(k-1), refined reciprocals
     unsigned long long *full = reinterpret_cast<unsigned long long *>(r2 + (jpk + 2));
     const int tid = (int)threadIdx.x, tx = tid % CTX, ty = tid / CTX;
     const int X0 = (int)blockIdx.x * CTX, Y0 = 1 + (int)blockIdx.y * CTY;                 // 0-based origin of the tile (even in ji)
@@ -46,8 +39,7 @@ __global__ void __launch_bounds__(CTX * CTY) k_interp_4th_cpt_tiled(int jpi, int
     const bool valid = gi >= 2 && gi <= jpi - 1 && gj <= jpj - 1;
     const int ci = min(max(gi, 2), jpi - 1), cj = min(gj, jpj - 1);
     const size_t jpij = (size_t)jpi * jpj, c2 = (size_t)(cj - 1) * jpi + (ci - 1);
-    double *pt_out = pt_out_all + (size_t)jn * jpij * jpk;
-    double *pcol = pt_out + c2;                                                           // this column of pt_out (level k at pcol[(k-1)*jpij])
+    double *__restrict__ pt_out = pt_out_all + (size_t)jn * jpij * jpk;
     const int jpkm1 = jpk - 1;
     const int nbox = (jpkm1 + CKL - 1) / CKL;                                             // levels 1..jpkm1 of ptn
     const CUtensorMap *mp = &map.m;
@@ -93,7 +85,7 @@ __global__ void __launch_bounds__(CTX * CTY) k_interp_4th_cpt_tiled(int jpi, int
                     const double c = (k == 2 || k == ikb) ? 0.5 : (k < ikb ? 3.0 : 0.0);
                     const double rhs = c * (t_k + t_km1);
                     const double z = (k >= 3) ? rhs - (reg ? rt[k] : 0.0) * z_m : rhs;
-                    if (k <= ksplit) zp[k * NT] = z; else if (valid) pcol[(size_t)(k - 1) * jpij] = z;
+                    zp[k * NT] = z;
                     z_m = z;
                 }
                 t_km1 = t_k;
@@ -110,7 +102,7 @@ __global__ void __launch_bounds__(CTX * CTY) k_interp_4th_cpt_tiled(int jpi, int
                     else                      { rhs = 3.0 * wm * (t_k + t_km1); wi = wm; } // (:538-542)
                     double z = rhs;
                     if (k >= 3) z = rhs - div_rn(wi, zwt_m) * z_m;
-                    if (k <= ksplit) zp[k * NT] = z; else if (valid) pcol[(size_t)(k - 1) * jpij] = z;
+                    zp[k * NT] = z;
                     z_m = z;
                     zwt_m = zwt[c2 + (size_t)(k - 1) * jpij];
                 }
@@ -121,38 +113,26 @@ __global__ void __launch_bounds__(CTX * CTY) k_interp_4th_cpt_tiled(int jpi, int
     }
     // back substitution (:603-614): level jpkm1 is still in registers.  Simple columns: zws = 1 on the regular rows, else 0; the
     // pivot is utab(k) above the bottom row (division through the once-refined reciprocal) and 1 from there down (x / 1 = x)
-    // forward value of level k: shared memory, or parked in pt_out (a thread only reads what it wrote itself)
-    auto zfw = [&](int k) -> double { return k <= ksplit ? zp[k * NT] : (valid ? pcol[(size_t)(k - 1) * jpij] : 0.0); };
+    double *po = pt_out + c2 + (size_t)(jpkm1 - 1) * jpij;
     if (smp) {
         double x = (jpkm1 < ikb) ? div_by(z_m, ut[jpkm1], r2[jpkm1]) : z_m;
-        if (valid) pcol[(size_t)(jpkm1 - 1) * jpij] = x;
-        int k = jpk - 2;
-        for (; k - 3 >= 2; k -= 4) {                                                      // four levels per batch: their loads are in flight together
-            const double z0 = zfw(k), z1 = zfw(k - 1), z2 = zfw(k - 2), z3 = zfw(k - 3);
-            const double zz[4] = {z0, z1, z2, z3};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int kk = k - q;
-                const bool reg = kk >= 3 && kk < ikb;
-                const double num = zz[q] - (reg ? 1.0 : 0.0) * x;
-                x = (kk < ikb) ? div_by(num, ut[kk], r2[kk]) : num;
-                if (valid) pcol[(size_t)(kk - 1) * jpij] = x;
-            }
-        }
-        for (; k >= 2; --k) {
+        if (valid) *po = x;
+        for (int k = jpk - 2; k >= 2; --k) {
+            po -= jpij;
             const bool reg = k >= 3 && k < ikb;
-            const double num = zfw(k) - (reg ? 1.0 : 0.0) * x;
+            const double num = zp[k * NT] - (reg ? 1.0 : 0.0) * x;
             x = (k < ikb) ? div_by(num, ut[k], r2[k]) : num;
-            if (valid) pcol[(size_t)(k - 1) * jpij] = x;
+            if (valid) *po = x;
         }
     } else {
         double x = div_rn(z_m, zwt_m);
-        if (valid) pcol[(size_t)(jpkm1 - 1) * jpij] = x;
+        if (valid) *po = x;
         for (int k = jpk - 2; k >= 2; --k) {
+            po -= jpij;
             double d, s;
             cpt_row(k, ikt, ikb, wmask[c2 + (size_t)(k - 1) * jpij], d, s);
-            x = div_rn(zfw(k) - s * x, zwt[c2 + (size_t)(k - 1) * jpij]);
-            if (valid) pcol[(size_t)(k - 1) * jpij] = x;
+            x = div_rn(zp[k * NT] - s * x, zwt[c2 + (size_t)(k - 1) * jpij]);
+            if (valid) *po = x;
         }
     }
 }

@@ -473,14 +473,10 @@ void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wm
                            const double *pt_in, double *pt_out, cudaStream_t s, TmaMapCache *cache)
 {
     (void)ln_isfcav;
-    // tiled kernel: even jpi (16-byte global strides), 16-byte aligned input.  ksplit = levels whose forward sweep stays in shared
-    // memory (the rest is parked in pt_out).  Measured at ORCA025: the whole column in shared memory (8 warps / SM) 1.21 ms;
-    // ksplit 40 / 22 / 10 / 1 (12-20 warps / SM) 1.24 / 1.37 / 1.25 / 1.26 ms -- more resident warps do not pay for the extra global
-    // round trip, so the default keeps every level in shared memory when it fits
-    static const int ks_env = getenv("NEMO_CPT_KSPLIT") ? atoi(getenv("NEMO_CPT_KSPLIT")) : -1;
-    int ksplit = std::max(1, std::min(jpk, ks_env >= 0 ? ks_env : jpk));
-    while (ksplit > 1 && cpt_tiled_smem_bytes(jpk, ksplit) > 116224) --ksplit;     // deep grids: keep two blocks per SM
-    const size_t smem = cpt_tiled_smem_bytes(jpk, ksplit);
+    // tiled kernel: even jpi (16-byte global strides), 16-byte aligned input, the forward sweep of a tile fits in shared memory.
+    // (Tried: parking the upper levels of the forward sweep in pt_out for 12-20 resident warps per SM instead of 8 -- 1.24-1.37 ms
+    // against 1.21 ms at ORCA025; 64x2 and 128x1 tiles for longer DRAM bursts -- no gain.  Dropped.)
+    const size_t smem = cpt_tiled_smem_bytes(jpk);
     if (cache && !(jpi & 1) && jpk >= 3 && smem <= 200 * 1024 && utab && simple) {
         const void *key[12] = {pt_in};
         const int dims[4] = {jpi, jpj, jpk, nfld};
@@ -508,7 +504,7 @@ void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wm
             static bool done[kMaxDevices] = {};
             allow_dynamic_smem(k_interp_4th_cpt_tiled, 200 * 1024, done);
             const dim3 g((unsigned)((jpi - 1 + CTX - 1) / CTX), (unsigned)((jpj - 2 + CTY - 1) / CTY), (unsigned)nfld);
-            k_interp_4th_cpt_tiled<<<g, CTX * CTY, smem, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_out, m, ksplit);
+            k_interp_4th_cpt_tiled<<<g, CTX * CTY, smem, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_out, m);
             note_launch();
             return;
         }

@@ -67,11 +67,10 @@ int emu_fct_fused(int jpi, int jpj, int jpk, int kjpt, int h, int v, int ln_lins
 // interp_4th_cpt through the tiled kernel exactly as launch_interp_4th_cpt runs it: pivots, classification, TMA-fed solve.
 // Returns -1 where the product falls back to the column kernel (odd jpi), else the number of TMA rule violations (0 = fine).
 int emu_interp_4th_cpt_tiled(int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
-                             const double *pt_in, double *pt_out, int use_simple, int ksplit)
+                             const double *pt_in, double *pt_out, int use_simple)
 {
     using namespace nemo;
     if ((jpi & 1) || jpk < 3) return -1;
-    ksplit = ksplit < 1 ? 1 : (ksplit > jpk ? jpk : ksplit);
     const size_t jpij = (size_t)jpi * jpj;
     std::vector<double> zwt(jpij * jpk, 0.0), utab(jpk + 1, 1.0);
     std::vector<unsigned char> simple(jpij, 0);
@@ -89,8 +88,8 @@ int emu_interp_4th_cpt_tiled(int jpi, int jpj, int jpk, int nfld, const double *
     set_map(&m.m, pt_in, jpi, jpj, (long long)jpk * nfld, CTX, CTY * 1);
     emu_tma_violations = 0;
     emu_box_depth = CKL;
-    emu_run_blocks3((jpi - 1 + CTX - 1) / CTX, (jpj - 2 + CTY - 1) / CTY, nfld, CTX * CTY, cpt_tiled_smem_bytes(jpk, ksplit), k_interp_4th_cpt_tiled,
-                    jpi, jpj, jpk, wmask, mikt, mbkt, (const double *)zwt.data(), (const unsigned char *)simple.data(), (const double *)utab.data(), pt_out, m, ksplit);
+    emu_run_blocks3((jpi - 1 + CTX - 1) / CTX, (jpj - 2 + CTY - 1) / CTY, nfld, CTX * CTY, cpt_tiled_smem_bytes(jpk), k_interp_4th_cpt_tiled,
+                    jpi, jpj, jpk, wmask, mikt, mbkt, (const double *)zwt.data(), (const unsigned char *)simple.data(), (const double *)utab.data(), pt_out, m);
     emu_box_depth = 1;
     return emu_tma_violations;
 }

@@ -204,13 +204,13 @@ def interp_4th_cpt(L, f, pt_in, pt_out, isf, use_simple=True):
                                 int(use_simple))
 
 
-def interp_4th_cpt_tiled(L, f, pt_in, pt_out, use_simple=True, ksplit=22):
+def interp_4th_cpt_tiled(L, f, pt_in, pt_out, use_simple=True):
     """the TMA-tiled interp_4th_cpt kernel (k_interp_4th_cpt_tiled) on pt_in (nfld, jpk, jpj, jpi).  Returns -1 where the product
     falls back to the column kernel (odd jpi), else the number of violated TMA box rules: must be 0"""
     jpk, jpj, jpi = f["tmask"].shape
     L.emu_interp_4th_cpt_tiled.restype = C.c_int
     return L.emu_interp_4th_cpt_tiled(jpi, jpj, jpk, pt_in.shape[0], p(f["wmask"]), p(f["mikt"]), p(f["mbkt"]), p(pt_in), p(pt_out),
-                                      int(use_simple), int(ksplit))
+                                      int(use_simple))
 
 
 def fct_step(L, f, kjpt, h, v, lin, isf, nk, lbc, hooks=False):

@@ -452,9 +452,9 @@ def test_interp_4th_cpt_tiled_kernel(emu, G, GJ, K, isf, jperio):
         O.lib().interp_4th_cpt(d.h, gf["ptn"][jn].ctypes.data_as(C.c_void_p), ref[jn].ctypes.data_as(C.c_void_p))
     w.close()
     inner = (slice(None), slice(1, K - 1), slice(1, -1), slice(1, -1))
-    for simple, ksplit in ((True, 22), (False, 22), (True, 1), (True, 5), (False, 3), (True, 200)):
-        out = np.full_like(ref, -7.0)                                 # ksplit: levels kept in shared memory, the rest parked in pt_out
-        assert emu_api.interp_4th_cpt_tiled(emu, gf, gf["ptn"], out, simple, ksplit) == 0
-        assert np.array_equal(out[inner], ref[inner]), (simple, ksplit)
+    for simple in (True, False):
+        out = np.full_like(ref, -7.0)
+        assert emu_api.interp_4th_cpt_tiled(emu, gf, gf["ptn"], out, simple) == 0
+        assert np.array_equal(out[inner], ref[inner]), simple
         out[inner] = -7.0
         assert (out == -7.0).all()
