@@ -408,20 +408,23 @@ def main():
     achieved = b_alg / (ms_max * 1e-3) / 1e9
     # measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the committed `ncu --set full`
     # capture of this workload / schedule at N = 1 (profiles/ncu_traffic.json), summed over the kernels of one step
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as tf:
             key = "%s:schedule%d" % (args.workload, sched) if args.scheme == "fct" else "%s:%s:schedule%d" % (args.workload, args.scheme, sched)
             ent = json.load(tf).get(key)
-        if ent and world == 1:
+        # stale-file guard: the capture must hold exactly the big kernels this run launched
+        big = {k for k in kern if k in kbytes}
+        if ent and world == 1 and big and big <= set(ent["kernels"]):
             traffic = int(sum(ent["kernels"].values()))
+            traffic_src = "profiles/ncu_traffic.json (%s, git %s)" % (key, ent.get("git", "round 1"))
             for name in kern:
                 if name in ent["kernels"]:
                     kern[name]["traffic"] = int(ent["kernels"][name])
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "scope": scope,
                 "alg_bytes_per_step": b_alg, "dominant_kernel": dominant, "kernels": kern}
 
