@@ -459,7 +459,7 @@ def main():
         ems = float(te.item())
         e2e = {"value": round(npts_global / (ems * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": round(ems, 3), "steps": n_e2e,
-               "path": "nemo_fct_set_e3t + nemo_tra_adv_fct (host pointers, pinned), synchronous", "host_affinity": numa}
+               "path": "nemo_fct_set_e3t + nemo_tra_adv_fct (host pointers, pinned), synchronous call; inside it upload | step | download are pipelined over tracer batches on three streams", "host_affinity": numa}
         ctx.set_e3t(f["e3t_b"], f["e3t_n"], f["e3t_a"])
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------------

@@ -37,6 +37,8 @@
 #ifndef NEMO_FCT_H
 #define NEMO_FCT_H
 
+#include <stddef.h>   /* size_t */
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -241,6 +243,11 @@ const char *nemo_fct_last_error(void);
 int nemo_fct_abi_version(void);
 /* number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches)                */
 long long nemo_fct_launch_count(void);
+/* Page-lock host arrays the host-pointer entry points will be given (NEMO's module arrays are ALLOCATABLE, i.e. pageable: without
+ * this the copies are staged through the driver's bounce buffer at a fraction of the PCIe rate and cannot overlap the step).
+ * Call once after nemo_alloc for tsb, tsn, tsa, un, vn, wn, e3t_b/n/a ... (nemogcm.F90:659-664); unregister before deallocation. */
+int nemo_fct_host_register(void *ptr, size_t bytes);
+int nemo_fct_host_unregister(void *ptr);
 /* glob_sum (src/OCE/lib_fortran_generic.h90:32-65; DDPDD lib_fortran.F90:300-332; MPI_SUMDD lib_mpp.F90:1158-1186): for each of
  * the nfld device fields ptab[f](jpi,jpj,ipk), out[f] = REAL( SUM in double-double of ptab[f] [* pw3d] * tmask_i ) over this
  * subdomain and, through the communicator, over all ranks -- the same bits on every rank and for every decomposition.  pw3d

@@ -120,6 +120,8 @@ def lib():
         "nemo_fct_set_schedule": [vp, i],
         "nemo_fct_set_arithmetic": [vp, i],
         "nemo_fct_declare_transport_options": [vp, i, i, i, i],
+        "nemo_fct_host_register": [vp, C.c_size_t],
+        "nemo_fct_host_unregister": [vp],
         "nemo_glob_sum_dev": [vp, C.c_char_p, i, C.POINTER(vp), vp, vp, i, dp],
         "nemo_group_glob_sum_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.POINTER(vp), C.POINTER(vp), i, dp],
         "nemo_fct_set_profiling": [vp, i],
@@ -148,7 +150,8 @@ ABI_SYMBOLS = (
     "nemo_lbc_lnk_multi_dev nemo_group_lbc_lnk_multi_dev nemo_fct_last_error nemo_fct_abi_version "
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
     "nemo_fct_profile_read nemo_fct_selftest_division nemo_fct_set_arithmetic "
-    "nemo_glob_sum_dev nemo_group_glob_sum_dev nemo_fct_declare_transport_options").split()
+    "nemo_glob_sum_dev nemo_group_glob_sum_dev nemo_fct_declare_transport_options "
+    "nemo_fct_host_register nemo_fct_host_unregister").split()
 
 
 class NxtForcing(C.Structure):
@@ -206,6 +209,15 @@ def selftest_division(n=1 << 22, seed=1, device=0):
     nbad = C.c_longlong(-1)
     _check(lib().nemo_fct_selftest_division(device, n, seed, C.byref(nbad)))
     return int(nbad.value)
+
+
+def host_register(a):
+    """page-lock a host numpy array for the host-pointer entry points (cudaHostRegister)"""
+    _check(lib().nemo_fct_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+
+def host_unregister(a):
+    _check(lib().nemo_fct_host_unregister(a.ctypes.data_as(C.c_void_p)))
 
 
 def launch_count():

@@ -135,6 +135,8 @@ struct nemo_fct_ctx {
     bool have_zl = false;
     int masks_from_t = 0;                                              // bit 0: umask/vmask/wmask verified to be tmask products; bit 1: tmask holds only +0.0 / 1.0
     cudaStream_t side_stream = nullptr;                                // schedule 1: frame kernels + exchanges
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;                // host-pointer entry point: upload / download streams of the tracer pipeline
+    cudaEvent_t ev_up[4] = {}, ev_dn[4] = {}, ev_e3t = nullptr;
     cudaEvent_t ev_a = nullptr, ev_k1 = nullptr, ev_t = nullptr;
     // host-variant staging
     int stage_kjpt = 0;
@@ -929,6 +931,23 @@ const char *nemo_fct_last_error(void) { return g_err.c_str(); }
 int nemo_fct_abi_version(void) { return NEMO_FCT_ABI_VERSION; }
 long long nemo_fct_launch_count(void) { return kernel_launch_count(); }
 
+int nemo_fct_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return fail("nemo_fct_host_register: bad arguments");
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return fail("nemo_fct_host_register: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int nemo_fct_host_unregister(void *ptr)
+{
+    if (!ptr) return fail("nemo_fct_host_unregister: NULL pointer");
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail("nemo_fct_host_unregister: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
 int nemo_fct_selftest_division(int device, long long n, unsigned long long seed, long long *nbad)
 {
     if (!nbad || n < 1) return fail("nemo_fct_selftest_division: bad arguments");
@@ -1036,7 +1055,9 @@ int nemo_fct_destroy(nemo_fct_handle h)
     prof_collect(h);
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
-    for (cudaEvent_t e : {h->ev_a, h->ev_k1, h->ev_t}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_a, h->ev_k1, h->ev_t, h->ev_e3t, h->ev_up[0], h->ev_up[1], h->ev_up[2], h->ev_up[3], h->ev_dn[0], h->ev_dn[1], h->ev_dn[2], h->ev_dn[3]}) if (e) cudaEventDestroy(e);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -1280,16 +1301,44 @@ int nemo_tra_adv_fct(nemo_fct_handle h, int kt, int kit000, const char *cdtype, 
         if (h->s_pun.n != n3) { h->s_pun.alloc(n3); h->s_pvn.alloc(n3); h->s_pwn.alloc(n3); }
         if (h->stage_kjpt < kjpt) { h->s_ptb.alloc(n4); h->s_ptn.alloc(n4); h->s_pta.alloc(n4); h->stage_kjpt = kjpt; }
     } catch (const std::exception &e) { return fail("tra_adv_fct: staging buffers: %s", e.what()); }
+    // Tracers are independent given the transports: the call is pipelined over batches of tracers on three streams -- upload of
+    // batch b+1 (copy-in stream) | step of batch b (compute stream) | download of batch b-1 (copy-out stream) -- so the PCIe link
+    // runs in both directions at once and only the last batch's step and download are exposed.  Same kernels, same bits.
     cudaStream_t s = h->stream;
-    CU(cudaMemcpyAsync(h->s_pun.p, pun, n3 * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->s_pvn.p, pvn, n3 * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->s_pwn.p, pwn, n3 * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->s_ptb.p, ptb, n4 * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->s_ptn.p, ptn, n4 * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->s_pta.p, pta, n4 * 8, cudaMemcpyHostToDevice, s));
-    if (nemo_tra_adv_fct_dev(h, kt, kit000, cdtype, p2dt, h->s_pun.p, h->s_pvn.p, h->s_pwn.p, h->s_ptb.p, h->s_ptn.p,
-                             h->s_pta.p, kjpt, kn_fct_h, kn_fct_v)) return 1;
-    CU(cudaMemcpyAsync(pta, h->s_pta.p, n4 * 8, cudaMemcpyDeviceToHost, s));
+    try {
+        if (!h->copy_in) {
+            CUTHROW(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+            CUTHROW(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+            for (cudaEvent_t *e : {&h->ev_up[0], &h->ev_up[1], &h->ev_up[2], &h->ev_up[3], &h->ev_dn[0], &h->ev_dn[1], &h->ev_dn[2], &h->ev_dn[3], &h->ev_e3t})
+                CUTHROW(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
+    } catch (const std::exception &e) { return fail("tra_adv_fct: copy streams: %s", e.what()); }
+    const int nb = std::min(kjpt, 4);                                  // pipeline batches
+    CU(cudaEventRecord(h->ev_e3t, s));                                 // staging buffers are free once the previous work of the context is done
+    CU(cudaStreamWaitEvent(h->copy_in, h->ev_e3t, 0));
+    CU(cudaMemcpyAsync(h->s_pun.p, pun, n3 * 8, cudaMemcpyHostToDevice, h->copy_in));
+    CU(cudaMemcpyAsync(h->s_pvn.p, pvn, n3 * 8, cudaMemcpyHostToDevice, h->copy_in));
+    CU(cudaMemcpyAsync(h->s_pwn.p, pwn, n3 * 8, cudaMemcpyHostToDevice, h->copy_in));
+    int t0 = 0;
+    std::vector<std::pair<int, int>> batch;                            // [first tracer, count)
+    for (int b = 0; b < nb; ++b) { const int cnt = kjpt / nb + (b < kjpt % nb ? 1 : 0); batch.push_back({t0, cnt}); t0 += cnt; }
+    for (int b = 0; b < nb; ++b) {
+        const size_t off = (size_t)batch[b].first * n3, cnt = (size_t)batch[b].second * n3;
+        CU(cudaMemcpyAsync(h->s_ptb.p + off, ptb + off, cnt * 8, cudaMemcpyHostToDevice, h->copy_in));
+        CU(cudaMemcpyAsync(h->s_ptn.p + off, ptn + off, cnt * 8, cudaMemcpyHostToDevice, h->copy_in));
+        CU(cudaMemcpyAsync(h->s_pta.p + off, pta + off, cnt * 8, cudaMemcpyHostToDevice, h->copy_in));
+        CU(cudaEventRecord(h->ev_up[b], h->copy_in));
+    }
+    for (int b = 0; b < nb; ++b) {
+        const size_t off = (size_t)batch[b].first * n3, cnt = (size_t)batch[b].second * n3;
+        CU(cudaStreamWaitEvent(s, h->ev_up[b], 0));
+        if (nemo_tra_adv_fct_dev(h, kt, kit000, cdtype, p2dt, h->s_pun.p, h->s_pvn.p, h->s_pwn.p, h->s_ptb.p + off, h->s_ptn.p + off,
+                                 h->s_pta.p + off, batch[b].second, kn_fct_h, kn_fct_v)) { cudaStreamSynchronize(h->copy_in); return 1; }
+        CU(cudaEventRecord(h->ev_dn[b], s));
+        CU(cudaStreamWaitEvent(h->copy_out, h->ev_dn[b], 0));
+        CU(cudaMemcpyAsync(pta + off, h->s_pta.p + off, cnt * 8, cudaMemcpyDeviceToHost, h->copy_out));
+    }
+    CU(cudaStreamSynchronize(h->copy_out));
     CU(cudaStreamSynchronize(s));
     return 0;
 }

@@ -52,12 +52,25 @@ def test_bench128_closed_T_S(N, O):
 
 
 def test_host_pointer_entry_point(N, O):
-    """nemo_tra_adv_fct with HOST buffers (what the Fortran shim calls) == device-resident path == oracle"""
+    """nemo_tra_adv_fct with HOST buffers (what the Fortran shim calls) == device-resident path == oracle.  The call is
+    pipelined over batches of tracers (upload | step | download on three streams): 2, 5 and 7 tracers, pageable and
+    page-locked (nemo_fct_host_register) host arrays, the one-kernel schedule on a grid large enough for it"""
     g = SMALL
     gf = H.random_fields(O, g["jpiglo"], g["jpjglo"], g["jpk"], 6, kjpt=2, seed=5)
     ref, _, _ = H.oracle_fct(O, gf, g["jpiglo"], g["jpjglo"], g["jpk"], 6, 1, 1, 2, 4, 4)
     got, _ = H.device_fct(N, gf, g["jpiglo"], g["jpjglo"], g["jpk"], 6, 1, 1, 2, 4, 4, host_path=True)
     assert np.array_equal(got, ref)
+    for kjpt, G, GJ, K in ((5, 64, 50, 9), (7, 30, 22, 11)):
+        gf = H.random_fields(O, G, GJ, K, 4, kjpt=kjpt, seed=50 + kjpt)
+        ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, 4, 1, 1, kjpt, 4, 4)
+        got, _ = H.device_fct(N, gf, G, GJ, K, 4, 1, 1, kjpt, 4, 4, host_path=True, schedule=4)
+        assert np.array_equal(got, ref), kjpt
+        for k in ("pun", "pvn", "pwn", "ptb", "ptn"):
+            N.host_register(gf[k])
+        got, _ = H.device_fct(N, gf, G, GJ, K, 4, 1, 1, kjpt, 4, 4, host_path=True, schedule=4)
+        for k in ("pun", "pvn", "pwn", "ptb", "ptn"):
+            N.host_unregister(gf[k])
+        assert np.array_equal(got, ref), kjpt
 
 
 @pytest.mark.parametrize("layout", [(2, 1), (1, 2), (2, 2), (3, 2), (4, 2)])
