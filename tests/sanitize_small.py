@@ -17,14 +17,15 @@ ok = True
 for jperio, (h, v) in ((4, (4, 4)), (0, (2, 2))):
     gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=7)
     ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, 2, h, v)
-    for schedule in (0, 1, 2, 3):
+    for schedule in (0, 1, 2, 3, 4):
         got, _ = H.device_fct(N, gf, G, GJ, K, jperio, 1, 1, 2, h, v, schedule=schedule)
         same = bool(np.array_equal(got, ref))
         print("jperio", jperio, "h/v", h, v, "schedule", schedule, "bit-identical" if same else "MISMATCH", flush=True)
         ok = ok and same
-    got, _ = H.device_fct(N, gf, G, GJ, K, jperio, 2, 2, 2, h, v, schedule=2)
-    print("jperio", jperio, "2x2 in-process group", bool(np.array_equal(got, ref)), flush=True)
-    ok = ok and bool(np.array_equal(got, ref))
+    for schedule in (2, 4):                      # 4 in a group: persistent k_fct_fused beside the frame chain
+        got, _ = H.device_fct(N, gf, G, GJ, K, jperio, 2, 2, 2, h, v, schedule=schedule)
+        print("jperio", jperio, "2x2 in-process group schedule", schedule, bool(np.array_equal(got, ref)), flush=True)
+        ok = ok and bool(np.array_equal(got, ref))
 # widened rows: MUSCL (all three structures, in-process group), centred scheme, tra_nxt
 import golden_cases as GC    # noqa: E402
 for jperio in (4, 0):
