@@ -463,6 +463,10 @@ static int pick_fused_nkchunk(const Ctx *c, int kjpt, const Rect &out)
     return (int)std::max(1LL, std::min<long long>(n, kmax));
 }
 
+// jk chunks of the frame-band launches: thin bands are latency bound (one thread marches a column chunk).  Chunks stay >= 8 levels
+// long (the chunk-start logic of the band kernels is only exercised and tested down to that length)
+static int frame_nkchunk(int jpk) { return std::max(1, std::min(8, (jpk - 1) / 8)); }
+
 static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, double p2dt, int kjpt, int h, int v)
 {
     const int ng = (int)g.size();
@@ -557,7 +561,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         lap[m].reg = fp.lap; fin[m].reg = fp.fin; lim[m].reg = fp.lim; bet[m].reg = fp.bet;
         for (FctArgs *x : {&lim[m], &fin[m]}) { x->zlx = c->zlx.p; x->zly = c->zly.p; x->zlz = c->zlz.p; }
         // small launches: one jk chunk is enough for the bands
-        for (FctArgs *x : {&lap[m], &lowf[m], &bet[m], &lim[m], &fin[m]}) x->nkchunk = std::max(1, std::min(8, (c->dom.jpk - 1) / 8));
+        for (FctArgs *x : {&lap[m], &lowf[m], &bet[m], &lim[m], &fin[m]}) x->nkchunk = frame_nkchunk(c->dom.jpk);
     }
     cudaStream_t side = g[0]->side_stream;
     std::vector<cudaStream_t> mainst(ng);
@@ -590,7 +594,7 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
         const FctFusedPlan fp = fct_fused_plan(g[m]->dom.jpi, g[m]->dom.jpj, g[m]->dom.npolj != 0, true);
         if (!fp.split) { split = false; break; }                                // all subdomains or none
         k1b[m].reg = fp.k1_band;
-        k1b[m].nkchunk = std::max(1, std::min(8, (g[m]->dom.jpk - 1) / 8));
+        k1b[m].nkchunk = frame_nkchunk(g[m]->dom.jpk);
         k1c[m].reg = fp.k1_centre;
         if (one_kernel) k1b[m].out = fp.k2_out;
     }
