@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kThreads) k_cen(const CenArgs a)
     const int kmax = a.jpk - 1;
     const int per = (kmax + a.nkchunk - 1) / a.nkchunk;
     const int ka = 1 + (int)blockIdx.y * per, kb = min(kmax, ka + per - 1);
+    if (ka > kb) return;                                 // an empty trailing chunk
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *ptn = a.ptn + toff, *ztu = a.ztu + toff, *ztv = a.ztv + toff, *ztw = a.ztw + toff;
     double *pta = a.pta + toff;

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kThreads) k_fct_laplacian(const FctArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *ptn = a.ptn + toff;
     double *zltu = a.zltu + toff, *zltv = a.zltv + toff;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff(const FctArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *ptb = a.ptb + toff, *ptn = a.ptn + toff;
     double *pta = a.pta + toff, *zwi = a.zwi + toff, *zwx = a.zwx + toff, *zwy = a.zwy + toff, *zwz = a.zwz + toff;
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(kThreads) k_fct_betas(const FctArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *pbef = a.ptb + toff, *paft = a.zwi + toff;
     const double *paa = a.zwx + toff, *pbb = a.zwy + toff, *pcc = a.zwz + toff;
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(kThreads) k_fct_limit(const FctArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *paa = a.zwx + toff, *pbb = a.zwy + toff, *pcc = a.zwz + toff;
     // in place (reference structure) or into separate arrays (schedule 1: the inner kernels still read zwx/zwy/zwz)
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(kThreads) k_fct_final(const FctArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *zwx = (a.zlx ? a.zlx : a.zwx) + toff, *zwy = (a.zly ? a.zly : a.zwy) + toff, *zwz = (a.zlz ? a.zlz : a.zwz) + toff;
     double *pta = a.pta + toff;

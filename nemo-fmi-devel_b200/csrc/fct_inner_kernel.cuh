@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kThreads) k_fct_low_antidiff_inner(const FctAr
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *__restrict__ ptb = a.ptb + toff;
     const double *__restrict__ ptn = a.ptn + toff;

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(TTX * TTY) k_fct_low_antidiff_tma(const FctArg
     const size_t jpij = a.jpij;
     int ka, kb;
     { const int per = (jpk - 1 + a.nkchunk - 1) / a.nkchunk; ka = 1 + chunk * per; kb = min(jpk - 1, ka + per - 1); }
+    if (ka > kb) return;                                 // an empty trailing chunk
     const int gi = ox + lx + 1, gj = oy + ly + 1;                                 // 1-based column of this thread
     const bool active = gi <= rc.i1 && gj <= rc.j1;
     const int ci = min(gi, jpi - 2), cj = min(gj, a.jpj - 2);                     // clamped: addresses of inactive threads stay legal

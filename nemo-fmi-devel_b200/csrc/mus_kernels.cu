@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(kThreads) k_mus_grad(const MusArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *ptb = a.ptb + toff;
     double *zwx = a.zwx + toff, *zwy = a.zwy + toff;
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(kThreads) k_mus_hflux(const MusArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *ptb = a.ptb + toff, *zwx = a.zwx + toff, *zwy = a.zwy + toff;
     double *fx = a.fx + toff, *fy = a.fy + toff;
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(kThreads) k_mus_trend(const MusArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *fx = a.fx + toff, *fy = a.fy + toff;
     double *pta = a.pta + toff;
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(kThreads) k_mus_inner(const MusArgs a)
     int ji, jj, ka, kb;
     if (!region_column(a.reg, ji, jj)) return;
     k_chunk(a.jpk - 1, a.nkchunk, ka, kb);
+    if (ka > kb) return;                                 // an empty trailing chunk (nkchunk does not divide jpk-1 evenly)
     const size_t toff = (size_t)blockIdx.z * a.n3;
     const double *ptb = a.ptb + toff;
     double *pta = a.pta + toff;
