@@ -465,7 +465,12 @@ static int pick_fused_nkchunk(const Ctx *c, int kjpt, const Rect &out)
 
 // jk chunks of the frame-band launches: thin bands are latency bound (one thread marches a column chunk).  Chunks stay >= 8 levels
 // long (the chunk-start logic of the band kernels is only exercised and tested down to that length)
-static int frame_nkchunk(int jpk) { return std::max(1, std::min(8, (jpk - 1) / 8)); }
+static int frame_nkchunk(int jpk)
+{
+    static const int env = getenv("NEMO_FCT_FRAME_NKCHUNK") ? atoi(getenv("NEMO_FCT_FRAME_NKCHUNK")) : 0;   // experiment knob: chunks of >= 3 levels
+    if (env > 0) return std::max(1, std::min(env, (jpk - 1) / 3));
+    return std::max(1, std::min(8, (jpk - 1) / 8));
+}
 
 static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, double p2dt, int kjpt, int h, int v)
 {

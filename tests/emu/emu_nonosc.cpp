@@ -4,12 +4,12 @@
 
 namespace nemo { namespace {
 #include "../../nemo-fmi-devel_b200/csrc/nonosc_final.cuh"
-#include "../../nemo-fmi-devel_b200/csrc/dev/nonosc_final_v3.cuh"      // experimental variant, not in the product library
+#include "../../experiments/nonosc_final_v3.cuh"      // experimental variant, not in the product library
 } }
 
 extern "C" {
 
-// out = i0, i1, j0, j1 (1-based output rectangle); variant 0 = the product kernel, 3 = csrc/dev/nonosc_final_v3.cuh
+// out = i0, i1, j0, j1 (1-based output rectangle); variant 0 = the product kernel, 3 = experiments/nonosc_final_v3.cuh
 int emu_nonosc_final_variant(int variant, int jpi, int jpj, int jpk, int kjpt, const int *out, double p2dt, const double *tmask,
                              const double *e3t_n, const double *e1e2t, const double *r1_e1e2t, const double *ptb, const double *zwi,
                              const double *zwx, const double *zwy, const double *zwz, double *pta);

@@ -166,7 +166,7 @@ def test_fused_limiter_kernel_emulated(emu, jperio, h):
     sl = (slice(None), slice(0, K - 1), slice(out[2] - 1, out[3]), slice(out[0] - 1, out[1]))
     assert np.array_equal(pta[sl], final[sl])
     assert not np.array_equal(pta[sl], stack("pta")[sl])
-    # the experimental variant of csrc/dev/nonosc_final_v3.cuh (loads consumed behind the barrier): same bits
+    # the experimental variant of experiments/nonosc_final_v3.cuh (loads consumed behind the barrier): same bits
     pta3 = stack("pta")
     emu.emu_nonosc_final_variant.restype = C.c_int
     rc = emu.emu_nonosc_final_variant(3, G, GJ, K, kjpt, _rect(*out), C.c_double(gf["p2dt"]), _p(gf["tmask"]), _p(gf["e3t_n"]),
