@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(CTX * CTY) k_interp_4th_cpt_tiled(int jpi, int
                                                                     const int *__restrict__ mikt, const int *__restrict__ mbkt,
                                                                     const double *__restrict__ zwt, const unsigned char *__restrict__ simple,
                                                                     const double *__restrict__ utab, double *__restrict__ pt_out_all,
-                                                                    const __grid_constant__ CptMap map)
+                                                                    const __grid_constant__ CptMap map, int jlo, int jhi)
 {
     NEMO_DYN_SMEM_ALIGNED(unsigned char, cpt_smem, 128);
     constexpr int NT = CTX * CTY;
@@ -33,10 +33,10 @@ __global__ void __launch_bounds__(CTX * CTY) k_interp_4th_cpt_tiled(int jpi, int
     double *ut = zbuf + (size_t)(jpk + 1) * NT, *rt = ut + (jpk + 2), *r2 = rt + (jpk + 2);  // pivots, 1/pivot(k-1), refined reciprocals
     unsigned long long *full = reinterpret_cast<unsigned long long *>(r2 + (jpk + 2));
     const int tid = (int)threadIdx.x, tx = tid % CTX, ty = tid / CTX;
-    const int X0 = (int)blockIdx.x * CTX, Y0 = 1 + (int)blockIdx.y * CTY;                 // 0-based origin of the tile (even in ji)
+    const int X0 = (int)blockIdx.x * CTX, Y0 = jlo - 1 + (int)blockIdx.y * CTY;           // 0-based origin of the tile (even in ji); rows jlo..jhi
     const int jn = (int)blockIdx.z;
     const int gi = X0 + tx + 1, gj = Y0 + ty + 1;                                         // 1-based column
-    const bool valid = gi >= 2 && gi <= jpi - 1 && gj <= jpj - 1;
+    const bool valid = gi >= 2 && gi <= jpi - 1 && gj <= jhi;
     const int ci = min(max(gi, 2), jpi - 1), cj = min(gj, jpj - 1);
     const size_t jpij = (size_t)jpi * jpj, c2 = (size_t)(cj - 1) * jpi + (ci - 1);
     double *__restrict__ pt_out = pt_out_all + (size_t)jn * jpij * jpk;

@@ -470,8 +470,9 @@ void launch_cpt_classify(int jpi, int jpj, int jpk, const double *wmask, const i
 
 void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
                            int ln_isfcav, const double *zwt, const unsigned char *simple, const double *utab,
-                           const double *pt_in, double *pt_out, cudaStream_t s, TmaMapCache *cache)
+                           const double *pt_in, double *pt_out, cudaStream_t s, TmaMapCache *cache, int jlo, int jhi)
 {
+    if (jlo < 2 || jhi > jpj - 1 || jhi < jlo) { jlo = 2; jhi = jpj - 1; }                // rows to solve (1-based); default: the whole interior
     (void)ln_isfcav;
     // tiled kernel: even jpi (16-byte global strides), 16-byte aligned input, the forward sweep of a tile fits in shared memory.
     // (Tried: parking the upper levels of the forward sweep in pt_out for 12-20 resident warps per SM instead of 8 -- 1.24-1.37 ms
@@ -503,8 +504,8 @@ void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wm
             memcpy(&m, cache->maps, sizeof m);
             static bool done[kMaxDevices] = {};
             allow_dynamic_smem(k_interp_4th_cpt_tiled, 200 * 1024, done);
-            const dim3 g((unsigned)((jpi - 1 + CTX - 1) / CTX), (unsigned)((jpj - 2 + CTY - 1) / CTY), (unsigned)nfld);
-            k_interp_4th_cpt_tiled<<<g, CTX * CTY, smem, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_out, m);
+            const dim3 g((unsigned)((jpi - 1 + CTX - 1) / CTX), (unsigned)((jhi - jlo + 1 + CTY - 1) / CTY), (unsigned)nfld);
+            k_interp_4th_cpt_tiled<<<g, CTX * CTY, smem, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_out, m, jlo, jhi);
             note_launch();
             return;
         }

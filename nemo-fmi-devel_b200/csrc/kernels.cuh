@@ -88,7 +88,7 @@ void launch_cpt_classify(int jpi, int jpj, int jpk, const double *wmask, const i
                          const double *utab, unsigned char *simple, cudaStream_t s);
 void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,
                            int ln_isfcav, const double *zwt, const unsigned char *simple, const double *utab,
-                           const double *pt_in, double *pt_out, cudaStream_t s, struct TmaMapCache *cache = nullptr);
+                           const double *pt_in, double *pt_out, cudaStream_t s, struct TmaMapCache *cache = nullptr, int jlo = 0, int jhi = 0);   // jlo..jhi: rows to solve (tiled kernel; 0 = all)
 // the same on the columns of `reg` only (the frame bands of schedule 4), column kernel.  The forward sweep is parked in
 // `scratch` (same shape), never in pt_out: another stream may be reading pt_out on these columns (same final values)
 void launch_interp_4th_cpt_region(const Region &reg, int jpi, int jpj, int jpk, int nfld, const double *wmask, const int *mikt, const int *mbkt,

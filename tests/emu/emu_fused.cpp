@@ -89,7 +89,7 @@ int emu_interp_4th_cpt_tiled(int jpi, int jpj, int jpk, int nfld, const double *
     emu_tma_violations = 0;
     emu_box_depth = CKL;
     emu_run_blocks3((jpi - 1 + CTX - 1) / CTX, (jpj - 2 + CTY - 1) / CTY, nfld, CTX * CTY, cpt_tiled_smem_bytes(jpk), k_interp_4th_cpt_tiled,
-                    jpi, jpj, jpk, wmask, mikt, mbkt, (const double *)zwt.data(), (const unsigned char *)simple.data(), (const double *)utab.data(), pt_out, m);
+                    jpi, jpj, jpk, wmask, mikt, mbkt, (const double *)zwt.data(), (const unsigned char *)simple.data(), (const double *)utab.data(), pt_out, m, 2, jpj - 1);
     emu_box_depth = 1;
     return emu_tma_violations;
 }

@@ -60,7 +60,8 @@ def test_host_pointer_entry_point(N, O):
     ref, _, _ = H.oracle_fct(O, gf, g["jpiglo"], g["jpjglo"], g["jpk"], 6, 1, 1, 2, 4, 4)
     got, _ = H.device_fct(N, gf, g["jpiglo"], g["jpjglo"], g["jpk"], 6, 1, 1, 2, 4, 4, host_path=True)
     assert np.array_equal(got, ref)
-    for kjpt, G, GJ, K in ((5, 64, 50, 9), (7, 30, 22, 11)):
+    # (96 x 130 and 76 x 214: K2 has >= 96 rows, so every batch is further pipelined over 2 / 4 row slabs of the one-kernel step)
+    for kjpt, G, GJ, K in ((5, 64, 50, 9), (7, 30, 22, 11), (3, 96, 130, 9), (2, 76, 214, 7)):
         gf = H.random_fields(O, G, GJ, K, 4, kjpt=kjpt, seed=50 + kjpt)
         ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, 4, 1, 1, kjpt, 4, 4)
         got, _ = H.device_fct(N, gf, G, GJ, K, 4, 1, 1, kjpt, 4, 4, host_path=True, schedule=4)
@@ -71,6 +72,10 @@ def test_host_pointer_entry_point(N, O):
         for k in ("pun", "pvn", "pwn", "ptb", "ptn"):
             N.host_unregister(gf[k])
         assert np.array_equal(got, ref), kjpt
+    gf = H.random_fields(O, 90, 150, 8, 0, kjpt=2, seed=61)                          # closed domain, 2nd order, slabs
+    ref, _, _ = H.oracle_fct(O, gf, 90, 150, 8, 0, 1, 1, 2, 2, 2)
+    got, _ = H.device_fct(N, gf, 90, 150, 8, 0, 1, 1, 2, 2, 2, host_path=True, schedule=4)
+    assert np.array_equal(got, ref)
 
 
 @pytest.mark.parametrize("layout", [(2, 1), (1, 2), (2, 2), (3, 2), (4, 2)])
