@@ -647,7 +647,25 @@ static int run_fct(std::vector<Ctx *> &g, const std::vector<FctCall> &args, doub
     // left free for that chain's small kernels and the NCCL transfers: otherwise each of their ~25 launches waits for whole-SM
     // blocks to retire (measured at 4x2 ORCA025: the chain, not the inner kernel, set the step time).
     static const int reserve_env = getenv("NEMO_FCT_RESERVE_SMS") ? atoi(getenv("NEMO_FCT_RESERVE_SMS")) : -1;
-    const int reserve = (one_kernel && frame_order == 0) ? (reserve_env >= 0 ? reserve_env : 16) : 0;
+    // How many SMs to leave: the chain is latency bound (~1 ms of launches and four exchanges + what its kernels need, which shrinks
+    // with the SMs they get: ~2.0 ms on 16 SMs at 4x2 ORCA025, 1.7 ms on 24), the one-kernel step scales with the SMs it keeps and
+    // proceeds in rounds of one work item (~0.13 ms at jpk = 75) per block.  Pick the reservation that balances the two estimates.
+    int reserve = 0;
+    if (one_kernel && frame_order == 0) {
+        if (reserve_env >= 0) reserve = reserve_env;
+        else {
+            const Rect &o = k2[0].out;
+            const long long items = (long long)((o.i1 - o.i0 + 28) / 28) * ((o.j1 - o.j0 + 12) / 12) * kjpt * std::max(1, k2[0].nkchunk);
+            const double t_item = 0.134 * 1.05 * g[0]->dom.jpk / 75.0 / std::max(1, k2[0].nkchunk);
+            double best = 1e30;
+            for (int r = 8; r <= 40 && r < g[0]->nsm - 8; r += 2) {          // NCCL alone wants a handful of SMs: 4 left the exchanges at 0.85 ms each (2x1, measured)
+                const bool remote = g[0]->nccl_nranks > 1;                  // four NCCL round trips in the chain, or local copies only
+                const double fused_ms = (double)((items + g[0]->nsm - r - 1) / (g[0]->nsm - r)) * t_item, chain_ms = remote ? 1.0 + 16.0 / r : 0.25 + 6.0 / r;
+                const double t = std::max(fused_ms, chain_ms);
+                if (t < best - 1e-9) { best = t; reserve = r; }
+            }
+        }
+    }
     // Without a reservation every work item is its own block (the hardware scheduler staggers them: measured 5 % faster and
     // 30 % less DRAM traffic than 148 persistent blocks marching in lockstep, whose tracer pairs miss each other in L2)
     static const int force_pers = getenv("NEMO_FCT_FORCE_PERSISTENT") ? atoi(getenv("NEMO_FCT_FORCE_PERSISTENT")) : 0;   // experiment knob
