@@ -21,6 +21,8 @@
  *   l_trd/l_hst/l_ptr     src/OCE/TRA/traadv_fct.F90:96-112,172-176,299-316 -> nemo_fct_set_trend_diag
  *   lbc_lnk_multi         src/OCE/LBC/lbc_lnk_multi_generic.h90:16-29 -> nemo_lbc_lnk_multi[_dev]
  *   mynode / MPI_Init     src/OCE/LBC/lib_mpp.F90:197-331         ->  nemo_fct_comm_unique_id / nemo_fct_comm_init
+ *   glob_sum              src/OCE/lib_fortran_generic.h90:32-65    ->  nemo_glob_sum_dev
+ *   stp_ctl (extrema)     src/OCE/stpctl.F90:115-186               ->  nemo_stp_ctl_dev
  *   ctl_stop              src/OCE/LBC/lib_mpp.F90:1868-1907       ->  non-zero return + nemo_fct_last_error
  *
  * Conventions
@@ -257,6 +259,25 @@ int nemo_glob_sum_dev(nemo_fct_handle h, const char *cdname, int nfld, const dou
                       const double *tmask_i, int ipk, double *out);
 int nemo_group_glob_sum_dev(nemo_fct_handle *hs, int n, const char *cdname, int nfld, const double *const *const *ptab,
                             const double *const *pw3d, const double *const *tmask_i, int ipk, double *out);
+/* stp_ctl's extrema test on device-resident state (src/OCE/stpctl.F90:115-124 zmax(1:6), :149-156 the condition, :162-165 the
+ * locations, :184 kindic).  sshn (jpi,jpj), un (jpi,jpj,jpk), tsn (jpi,jpj,jpk,2) with jp_tem = 1, jp_sal = 2: device pointers;
+ * tmask is the one given to nemo_fct_set_domain_arrays.  zmax = max|sshn|, max|un|, max(-S), max(S), max(-T), max(T), the tracer
+ * ones where tmask == 1 (MAXVAL of an empty set: -HUGE); ih, iu, is1, is2 = MAXLOC|sshn|, MAXLOC|un|, MINLOC S, MAXLOC S as 1-based
+ * GLOBAL indices (first occurrence in array order).  kindic = -3 when the reference's condition holds (the ctl_stop text is
+ * then what nemo_fct_last_error returns), else 0; the return value is 0 unless the call itself failed.  A NaN never wins a
+ * comparison (MAXVAL over NaN is processor dependent in Fortran); nan_found reports one in sshn, un or the masked S, which is what
+ * the reference's ISNAN( zmax(1)+zmax(2)+zmax(3) ) tests for.  collective != 0 (ln_ctl / sn_cfctl%l_runstat, :126-129, 157-160):
+ * maxima and locations over all ranks of the communicator, identical on every rank, ties to the lowest rank as MPI_MAXLOC (the
+ * locations are the unmasked ones of the local branch; mpp_maxloc's ssmask / umask change nothing while land values are zero).
+ * The files stp_ctl writes (time.step, run.stat, output.abort) and zmax(8:9) (ln_zad_Aimp) stay with the host.               */
+typedef struct nemo_stp_ctl_result {
+    double zmax[6];
+    int ih[2], iu[3], is1[3], is2[3];
+    int nan_found;
+    int kindic;
+} nemo_stp_ctl_result;
+int nemo_stp_ctl_dev(nemo_fct_handle h, int kt, const double *sshn, const double *un, const double *tsn, int collective,
+                     nemo_stp_ctl_result *res);
 /* Self-test of the inlined IEEE division of the fused kernel (csrc/fct_fused_kernel.cuh: div_rn): n pseudo-random operand
  * pairs per class (ordinary magnitudes, the FCT ranges 1e-15 .. 1e40, zeros, subnormals, huge, Inf/NaN) are divided on device
  * `device` by div_rn and by the compiler's x / y; *nbad = number of pairs whose bit patterns differ (NaN payloads aside).

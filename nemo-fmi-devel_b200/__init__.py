@@ -124,6 +124,7 @@ def lib():
         "nemo_fct_host_unregister": [vp],
         "nemo_glob_sum_dev": [vp, C.c_char_p, i, C.POINTER(vp), vp, vp, i, dp],
         "nemo_group_glob_sum_dev": [C.POINTER(vp), i, C.c_char_p, i, C.POINTER(C.POINTER(vp)), C.POINTER(vp), C.POINTER(vp), i, dp],
+        "nemo_stp_ctl_dev": [vp, i, vp, vp, vp, i, vp],
         "nemo_fct_set_profiling": [vp, i],
         "nemo_fct_profile_read": [vp, i, C.c_char_p, i, dp, C.POINTER(C.c_longlong)],
         "nemo_fct_abi_version": [],
@@ -151,7 +152,13 @@ ABI_SYMBOLS = (
     "nemo_fct_launch_count nemo_fct_comm_report nemo_fct_set_schedule nemo_fct_set_profiling "
     "nemo_fct_profile_read nemo_fct_selftest_division nemo_fct_set_arithmetic "
     "nemo_glob_sum_dev nemo_group_glob_sum_dev nemo_fct_declare_transport_options "
-    "nemo_fct_host_register nemo_fct_host_unregister").split()
+    "nemo_fct_host_register nemo_fct_host_unregister nemo_stp_ctl_dev").split()
+
+
+class StpCtlResult(C.Structure):
+    """nemo_stp_ctl_result: zmax(1:6) and the locations of stp_ctl (stpctl.F90:115-124, 162-165), kindic (:184)"""
+    _fields_ = [("zmax", C.c_double * 6), ("ih", C.c_int * 2), ("iu", C.c_int * 3), ("is1", C.c_int * 3), ("is2", C.c_int * 3),
+                ("nan_found", C.c_int), ("kindic", C.c_int)]
 
 
 class NxtForcing(C.Structure):
@@ -501,6 +508,16 @@ class FctContext:
         out = (C.c_double * nfld)()
         _check(lib().nemo_glob_sum_dev(self._h, cdname.encode(), nfld, tab, None if w3d is None else _ptr(w3d), _ptr(tmask_i), ipk, out))
         return list(out)
+
+    def stp_ctl(self, kt, sshn, un, tsn, collective=False):
+        """stp_ctl( kt, kindic ) (stpctl.F90:115-186) on device tensors sshn (jpj,jpi), un (jpk,jpj,jpi), tsn (2,jpk,jpj,jpi) = (tem, sal).
+        Returns dict(zmax, ih, iu, is1, is2, nan_found, kindic, message)."""
+        for a in (sshn, un, tsn):
+            _f64(a, "stp_ctl")
+        r = StpCtlResult()
+        _check(lib().nemo_stp_ctl_dev(self._h, int(kt), _ptr(sshn), _ptr(un), _ptr(tsn), int(bool(collective)), C.byref(r)))
+        return dict(zmax=list(r.zmax), ih=list(r.ih), iu=list(r.iu), is1=list(r.is1), is2=list(r.is2), nan_found=r.nan_found,
+                    kindic=r.kindic, message=lib().nemo_fct_last_error().decode() if r.kindic else "")
 
     def lbc_lnk(self, cdname, pt, cd_nat, psgn, pval=None):
         """lbc_lnk( cdname, ptab, cd_nat, psgn [, pval] ) (lbclnk.F90:21-29)"""

@@ -248,7 +248,7 @@ inline dim3 column_grid(const FctArgs &a)
 // is remembered per device: contexts of several GPUs may live in one process.
 constexpr int kMaxDevices = 64;
 template <typename Kernel>
-static void allow_dynamic_smem(Kernel kernel, size_t smem, bool (&done)[kMaxDevices])
+static void allow_dynamic_smem(Kernel kernel, size_t smem, std::atomic<bool> (&done)[kMaxDevices])
 {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -342,7 +342,7 @@ bool launch_fct_low_antidiff_tma(const FctArgs &a, cudaStream_t s)
     const size_t smem = (size_t)TSTAGES * kTileStageBytes + 64;
     const dim3 g((unsigned)(((rc.i1 - rc.i0 + 1 + TTX - 1) / TTX) * a.kjpt), (unsigned)((rc.j1 - rc.j0 + 1 + TTY - 1) / TTY), (unsigned)a.nkchunk);
     const bool ft = (a.masks_from_t & 1) != 0;
-#define LAT(H, V, F) do { static bool done[kMaxDevices] = {}; allow_dynamic_smem(k_fct_low_antidiff_tma<H, V, F>, smem, done); \
+#define LAT(H, V, F) do { static std::atomic<bool> done[kMaxDevices]; allow_dynamic_smem(k_fct_low_antidiff_tma<H, V, F>, smem, done); \
                           k_fct_low_antidiff_tma<H, V, F><<<g, TTX * TTY, smem, s>>>(a, tm, rc); } while (0)
 #define LAT2(H, V) do { if (ft) LAT(H, V, true); else LAT(H, V, false); } while (0)
     if (a.kn_fct_h == 2 && a.kn_fct_v == 2) LAT2(2, 2);
@@ -366,7 +366,7 @@ bool launch_fct_nonosc_final_tma(const FctArgs &a, cudaStream_t s)
                     make_tile_map(&tm.m[NQ_TM], a.tmask, a.jpi, a.jpj, n3, NX, NY) && make_tile_map(&tm.m[NQ_PCC], a.zwz, a.jpi, a.jpj, n4, NX, NY) &&
                     make_tile_map(&tm.m[NQ_PAA], a.zwx, a.jpi, a.jpj, n4, NX, NY) && make_tile_map(&tm.m[NQ_PBB], a.zwy, a.jpi, a.jpj, n4, NX, NY);
     if (!ok) return false;
-    static bool done[kMaxDevices] = {};
+    static std::atomic<bool> done[kMaxDevices];
     const size_t smem = (size_t)2 * kNqStageBytes + 6 * kNqBoxBytes + 64;
     allow_dynamic_smem(k_fct_nonosc_final_tma, smem, done);
     const int ox = NX - 2 * NHALO, oy = NY - 2 * NHALO;
@@ -412,7 +412,7 @@ void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache
     const int nblk = std::max(1, std::min(nwork, max_blocks));
     static const int skew_env = getenv("NEMO_FCT_SKEW_NS") ? atoi(getenv("NEMO_FCT_SKEW_NS")) : 0;   // experiment knob: measured to hurt
     const int skew_ns = nblk < nwork ? skew_env : 0;                  // persistent blocks only
-#define LFU(H, V, A) do { static bool done[kMaxDevices] = {}, donep[kMaxDevices] = {}; \
+#define LFU(H, V, A) do { static std::atomic<bool> done[kMaxDevices], donep[kMaxDevices]; \
                           if (nblk < nwork) { allow_dynamic_smem(k_fct_fused<H, V, A, true>, kFusedSmemBytes, donep); \
                                               k_fct_fused<H, V, A, true><<<nblk, FX * FY, kFusedSmemBytes, s>>>(a, tm, gx, gy, nwork, skew_ns); } \
                           else              { allow_dynamic_smem(k_fct_fused<H, V, A, false>, kFusedSmemBytes, done); \
@@ -429,7 +429,7 @@ void launch_fct_fused(const FctArgs &a, cudaStream_t s, const TmaMapCache *cache
 
 void launch_fct_nonosc_final(const FctArgs &a, cudaStream_t s)
 {
-    static bool done[kMaxDevices] = {};
+    static std::atomic<bool> done[kMaxDevices];
     const size_t smem = (size_t)(3 * 4 + 2 * 2) * NY * NX * sizeof(double);
     allow_dynamic_smem(k_fct_nonosc_final, smem, done);
     const int ox = NX - 2 * NHALO, oy = NY - 2 * NHALO;
@@ -502,7 +502,7 @@ void launch_interp_4th_cpt(int jpi, int jpj, int jpk, int nfld, const double *wm
         if (ok) {
             CptMap m;
             memcpy(&m, cache->maps, sizeof m);
-            static bool done[kMaxDevices] = {};
+            static std::atomic<bool> done[kMaxDevices];
             allow_dynamic_smem(k_interp_4th_cpt_tiled, 200 * 1024, done);
             const dim3 g((unsigned)((jpi - 1 + CTX - 1) / CTX), (unsigned)((jhi - jlo + 1 + CTY - 1) / CTY), (unsigned)nfld);
             k_interp_4th_cpt_tiled<<<g, CTX * CTY, smem, s>>>(jpi, jpj, jpk, wmask, mikt, mbkt, zwt, simple, utab, pt_out, m, jlo, jhi);

@@ -173,6 +173,12 @@ constexpr int kGlobSumBlocks = 148 * 4;
 void launch_glob_sum(const double *const *ptab_dev, int nfld, const double *pw3d, const double *tmask_i, size_t jpij, int ipk, double *partial,
                      double *out_pairs, cudaStream_t s);
 
+// ---- stp_ctl (stpctl.F90:115-124, 162-165): extrema of |sshn|, |un|, S, T (tracers where tmask == 1) with the linear index of
+// the first occurrence (-1: no operand), flags bit 0 = NaN met in sshn / un / masked S, bit 1 = some tmask == 1
+struct StpCtlRec { double z1, z2, smin, smax, tmin, tmax; long long l1, l2, ls1, ls2, lt1, lt2; int flags, pad; };
+void launch_stp_ctl(const double *sshn, const double *un, const double *tem, const double *sal, const double *tmask, size_t jpij, size_t n3,
+                    StpCtlRec *partial, StpCtlRec *out, cudaStream_t s);
+
 long long kernel_launch_count();
 // div_rn (fct_fused_kernel.cuh) against x / y on n operand pairs per class; returns the number of differing results, < 0 on error
 long long division_selftest(long long n, unsigned long long seed, cudaStream_t s);

@@ -14,8 +14,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <limits>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -63,13 +65,19 @@ const int kNcclFloat64 = 8;   // ncclDouble, nccl.h
 
 int load_nccl()
 {
-    if (g_nccl.lib) return 0;
+    static std::mutex mu;                                              // contexts may be created from several host threads
+    static bool ready = false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (ready) return 0;
+    NcclApi api;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char *n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
-    if (!g_nccl.lib) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
-#define SYM(f) *(void **)(&g_nccl.f) = dlsym(g_nccl.lib, "nccl" #f); if (!g_nccl.f) return fail("libnccl: missing symbol nccl" #f)
+    for (const char *n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+    if (!api.lib) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(f) *(void **)(&api.f) = dlsym(api.lib, "nccl" #f); if (!api.f) return fail("libnccl: missing symbol nccl" #f)
     SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllGather); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
+    g_nccl = api;                                                      // published complete, under the lock
+    ready = true;
     return 0;
 }
 #define NC(call) do { int r_ = (call); if (r_ != 0) return fail("%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); } while (0)
@@ -155,6 +163,7 @@ struct nemo_fct_ctx {
     int nsm = 148;                                                     // SMs of the device (persistent k_fct_fused: one block per SM it occupies)
     TmaMapCache fused_maps;                                            // schedule 4: tensor maps of k_fct_fused, encoded once per (pointers, shape)
     DevBuf<double> gs_partial, gs_pairs, gs_gather; DevBuf<const double *> gs_ptrs;     // glob_sum scratch
+    DevBuf<StpCtlRec> sc_partial, sc_out; DevBuf<double> sc_send, sc_gather;            // stp_ctl scratch
     TmaMapCache cpt_maps[3];                                           // tensor map of k_interp_4th_cpt_tiled: tra_adv_fct, tra_adv_cen, interp_4th_cpt entry
     // per-kernel CUDA-event timing (bench.py's roofline): off by default
     bool profiling = false;
@@ -1811,6 +1820,74 @@ int nemo_group_glob_sum_dev(nemo_fct_handle *hs, int n, const char *cdname, int 
     std::vector<Ctx *> g;
     if (group_of(hs, n, "nemo_group_glob_sum_dev", g)) return 1;
     return glob_sum_common(g, nfld, ptab, pw3d, tmask_i, ipk, out);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stp_ctl (stpctl.F90:115-124, 149-166, 184): extrema / NaN guard on device-resident state
+// ------------------------------------------------------------------------------------------------------------
+int nemo_stp_ctl_dev(nemo_fct_handle h, int kt, const double *sshn, const double *un, const double *tsn, int collective, nemo_stp_ctl_result *res)
+{
+    if (need_single(h, "nemo_stp_ctl_dev")) return 1;
+    if (!sshn || !un || !tsn || !res) return fail("nemo_stp_ctl_dev: NULL argument");
+    if (!h->have_dom) return fail("nemo_stp_ctl_dev: nemo_fct_set_domain_arrays has not been called (tmask is needed)");
+    Ctx *c = h;
+    CU(cudaSetDevice(c->device));
+    try { if (!c->sc_partial.n) { c->sc_partial.alloc(kGlobSumBlocks); c->sc_out.alloc(1); } }
+    catch (const std::exception &e) { return fail("nemo_stp_ctl_dev: %s", e.what()); }
+    launch_stp_ctl(sshn, un, tsn, tsn + c->n3, c->tmask.p, c->jpij, c->n3, c->sc_partial.p, c->sc_out.p, c->stream);   // jp_tem = 1, jp_sal = 2
+    CU(cudaGetLastError());
+    StpCtlRec r;
+    CU(cudaMemcpyAsync(&r, c->sc_out.p, sizeof r, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const nemo_fct_domain &d = c->dom;
+    // one record per rank: zmax(1:6), flags, ih(2), iu(3), is1(3), is2(3) (global indices: MAXLOC + (/ nimpp-1, njmpp-1, 0 /), :162-165)
+    enum { NREC = 18 };
+    double rec[NREC];
+    const double none = -std::numeric_limits<double>::max();           // MAXVAL of an empty set = -HUGE
+    rec[0] = r.l1 < 0 ? none : r.z1;     rec[1] = r.l2 < 0 ? none : r.z2;
+    rec[2] = r.ls1 < 0 ? none : -r.smin; rec[3] = r.ls2 < 0 ? none : r.smax;
+    rec[4] = r.lt1 < 0 ? none : -r.tmin; rec[5] = r.lt2 < 0 ? none : r.tmax;
+    rec[6] = (double)r.flags;
+    auto loc3 = [&](long long l, double *o) {
+        if (l < 0) { o[0] = d.nimpp - 1; o[1] = d.njmpp - 1; o[2] = 0; return; }
+        o[0] = (double)(l % d.jpi + 1 + d.nimpp - 1); o[1] = (double)((l / d.jpi) % d.jpj + 1 + d.njmpp - 1); o[2] = (double)(l / (long long)c->jpij + 1);
+    };
+    { double t3[3]; loc3(r.l1, t3); rec[7] = t3[0]; rec[8] = t3[1]; }
+    loc3(r.l2, &rec[9]); loc3(r.ls1, &rec[12]); loc3(r.ls2, &rec[15]);
+    std::vector<double> all(rec, rec + NREC);
+    if (collective && c->nccl_nranks > 1) {                            // ll_colruns: mpp_max + mpp_maxloc / mpp_minloc over the ranks (:126-129, 157-160)
+        const int nr = c->nccl_nranks;
+        try { if (c->sc_gather.n < (size_t)nr * NREC) { c->sc_gather.alloc((size_t)nr * NREC); c->sc_send.alloc(NREC); } }
+        catch (const std::exception &e) { return fail("nemo_stp_ctl_dev: %s", e.what()); }
+        CU(cudaMemcpyAsync(c->sc_send.p, rec, sizeof rec, cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllGather(c->sc_send.p, c->sc_gather.p, (size_t)NREC, kNcclFloat64, c->nccl_comm, c->stream));
+        all.assign((size_t)nr * NREC, 0.0);
+        CU(cudaMemcpyAsync(all.data(), c->sc_gather.p, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    const int nparts = (int)(all.size() / NREC);
+    int win[4] = {0, 0, 0, 0}, flags = 0;                              // rank holding zmax(1:4): the lowest on a tie, as MPI_MAXLOC
+    for (int q = 0; q < 6; ++q) res->zmax[q] = all[q];
+    for (int m = 0; m < nparts; ++m) {
+        const double *a = &all[(size_t)m * NREC];
+        for (int q = 0; q < 6; ++q) if (a[q] > res->zmax[q]) { res->zmax[q] = a[q]; if (q < 4) win[q] = m; }
+        flags |= (int)a[6];
+    }
+    const double *w0 = &all[(size_t)win[0] * NREC], *w1 = &all[(size_t)win[1] * NREC], *w2 = &all[(size_t)win[2] * NREC], *w3 = &all[(size_t)win[3] * NREC];
+    res->ih[0] = (int)w0[7]; res->ih[1] = (int)w0[8];
+    for (int q = 0; q < 3; ++q) { res->iu[q] = (int)w1[9 + q]; res->is1[q] = (int)w2[12 + q]; res->is2[q] = (int)w3[15 + q]; }
+    res->nan_found = flags & 1;
+    res->kindic = 0;
+    const double *z = res->zmax;
+    if ((collective || (flags & 2)) && (z[0] > 20.0 || z[1] > 10.0 || z[2] >= 0.0 || z[3] >= 100.0 || z[3] < 0.0 || (flags & 1))) {   // :149-156
+        res->kindic = -3;                                              // :184; the text is ctl_stop's (:167-171), kept for nemo_fct_last_error
+        fail(" stp_ctl: |ssh| > 20 m  or  |U| > 10 m/s  or  S <= 0  or  S >= 100  or  NaN encounter in the tests\n"
+             " kt=%8d   |ssh| max: %11.4g, at  i j  : %5d%5d\n kt=%8d   |U|   max: %11.4g, at  i j k: %5d%5d%5d\n"
+             " kt=%8d   S     min: %11.4g, at  i j k: %5d%5d%5d\n kt=%8d   S     max: %11.4g, at  i j k: %5d%5d%5d",
+             kt, z[0], res->ih[0], res->ih[1], kt, z[1], res->iu[0], res->iu[1], res->iu[2], kt, -z[2], res->is1[0], res->is1[1], res->is1[2],
+             kt, z[3], res->is2[0], res->is2[1], res->is2[2]);
+    }
+    return 0;
 }
 
 int nemo_group_lbc_lnk_multi_dev(nemo_fct_handle *hs, int n, const char *cdname, int nfld, double *const *const *ptab,

@@ -170,6 +170,11 @@ void   ddpdd(const double ydda[2], double yddb[2]);                             
  * into ctmp (caller zero-inits); the cross-rank MPI_SUMDD (lib_mpp.F90:1158-1186) is ddpdd over ranks.       */
 void   glob_sum_local(const double *ptab, const double *tmask_i, int jpi, int jpj, int ipk, double ctmp[2]);
 
+/* ---- stpctl.c ---- */
+/* extrema test + error condition of stp_ctl (stpctl.F90:115-124, 149-166, 184), local domain, branch without ln_ctl */
+void   stp_ctl_local(const oce_dom *d, const double *sshn, const double *un, const double *tsn, const double *tmask,
+                     double zmax[6], int ih[2], int iu[3], int is1[3], int is2[3], int *nan_found, int *kindic);
+
 #ifdef __cplusplus
 }
 #endif

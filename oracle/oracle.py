@@ -53,6 +53,7 @@ def lib():
         L.oracle_poison_workspace.argtypes = [C.c_int]
         L.glob_sum_local.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, DP]
         L.ddpdd.argtypes = [DP, DP]
+        L.stp_ctl_local.argtypes = [C.c_void_p] * 5 + [DP, IP, IP, IP, IP, IP, IP]
         L.sign_nosignedzero.restype = C.c_double
         L.sign_nosignedzero.argtypes = [C.c_double, C.c_double]
         L.tra_adv_transports.argtypes = [C.c_void_p] * 11
@@ -225,6 +226,16 @@ class World:
             _ptr_table([r[n] for r in res]) for n in ("tmask", "umask", "vmask", "wmask", "tmask_i", "mikt", "mbkt")]
         lib().oce_world_dom_msk(self.h, *tabs)
         return res
+
+
+def stp_ctl(dom, sshn, un, tsn, tmask):
+    """Extrema test of stp_ctl (stpctl.F90:115-124, 149-166, 184) on one subdomain.  tsn: (2, jpk, jpj, jpi) = (tem, sal).
+    Returns dict(zmax[6], ih, iu, is1, is2, nan_found, kindic)."""
+    zmax = (C.c_double * 6)()
+    ih, iu, is1, is2 = (C.c_int * 2)(), (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)()
+    nanf, kindic = C.c_int(0), C.c_int(0)
+    lib().stp_ctl_local(dom.h, _ptr(sshn), _ptr(un), _ptr(tsn), _ptr(tmask), zmax, ih, iu, is1, is2, C.byref(nanf), C.byref(kindic))
+    return dict(zmax=list(zmax), ih=list(ih), iu=list(iu), is1=list(is1), is2=list(is2), nan_found=nanf.value, kindic=kindic.value)
 
 
 def glob_sum(world, locs, tmask_i):

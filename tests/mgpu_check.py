@@ -27,7 +27,8 @@ def main():
     G, GJ, K, kjpt = 130, 96, 12, 2
     ok_all = True
     only_fct = os.environ.get("MGPU_ONLY_FCT", "0") == "1"          # tests/test_gpu_multi.py: the tra_adv_fct matrix only
-    for jperio in (0, 1, 4, 6):
+    only_diag = os.environ.get("MGPU_ONLY_DIAG", "0") == "1"        # the collective diagnostics only (glob_sum, stp_ctl)
+    for jperio in (() if only_diag else (0, 1, 4, 6)):
         gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=50 + jperio)
         for (h, v) in ((2, 2), (4, 4)):
             ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v)
@@ -87,7 +88,41 @@ def main():
             print("%s %dx%d: %s" % (what, part[0], part[1], "BIT-IDENTICAL" if flag.item() else "MISMATCH"), flush=True)
         return bool(flag.item())
 
-    for jperio in (() if only_fct else (0, 1, 4, 6)):
+    # ---- collective diagnostics over NCCL: glob_sum (MPI_SUMDD) and stp_ctl with ln_ctl (mpp_max / mpp_maxloc) ---------
+    from test_gpu_glob_sum import _tmask_i
+    for jperio in (() if only_fct else (0, 4, 6)):
+        gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=90 + jperio)
+        rng = np.random.default_rng(11)
+        big = np.ascontiguousarray(gf["ptb"][0] * (1.0 + 1e8 * rng.standard_normal(gf["ptb"][0].shape)))    # heavy cancellation
+        cvol = np.ascontiguousarray(gf["e1e2t"][None] * gf["e3t_n"] * gf["tmask"])
+        sshn = np.ascontiguousarray(0.5 * rng.standard_normal((GJ, G)) * gf["tmask"][0])
+        un = np.ascontiguousarray(0.3 * rng.standard_normal((K, GJ, G)) * gf["umask"])
+        tem = (10.0 + rng.standard_normal((K, GJ, G))) * gf["tmask"]
+        sal = (35.0 + rng.standard_normal((K, GJ, G))) * gf["tmask"]
+        wet = np.argwhere(gf["tmask"][:, 2:-2, 2:-2] == 1.0)
+        kk, jj, ii = wet[len(wet) // 2]
+        un[kk, jj + 2, ii + 2] = -12.0                                  # one rank holds it, every rank must report it
+        tsn = np.ascontiguousarray(np.stack([tem, sal]))
+        w1 = O.World(G, GJ, K, jperio)
+        want_sum = O.glob_sum(w1, [np.ascontiguousarray(big * cvol)], [np.ascontiguousarray(gf["tmask_i"])])[0]
+        want_ctl = O.stp_ctl(w1.doms[0], sshn, un, tsn, gf["tmask"])
+        w1.close()
+        w = O.World(G, GJ, K, jperio, part[0], part[1])
+        loc = {k: w.scatter(gf[k])[rank] for k in H.DOM_KEYS}
+        ctx = make_ctx(jperio, loc, 4)
+        ti = _tmask_i(ctx.dom, loc["tmask"])
+        td = lambda a: torch.from_numpy(np.ascontiguousarray(w.scatter(a)[rank])).to(dev)   # noqa: E731
+        got_sum = ctx.glob_sum("mgpu", [td(big)], torch.from_numpy(ti).to(dev), w3d=td(cvol))[0]
+        ok_all = agree(got_sum == want_sum, "glob_sum over NCCL jperio=%d (%r)" % (jperio, got_sum)) and ok_all
+        l_ts = torch.from_numpy(np.ascontiguousarray(np.stack([w.scatter(tsn[0])[rank], w.scatter(tsn[1])[rank]]))).to(dev)
+        got = ctx.stp_ctl(5, td(sshn), td(un), l_ts, collective=True)
+        ok = (got["zmax"] == want_ctl["zmax"] and got["iu"] == want_ctl["iu"] and got["kindic"] == -3 and got["nan_found"] == 0
+              and got["is1"] == want_ctl["is1"] and got["is2"] == want_ctl["is2"] and got["ih"] == want_ctl["ih"])
+        ok_all = agree(ok, "stp_ctl (ln_ctl) over NCCL jperio=%d |U|max=%g at %s" % (jperio, got["zmax"][1], got["iu"])) and ok_all
+        ctx.close()
+        w.close()
+
+    for jperio in (() if (only_fct or only_diag) else (0, 1, 4, 6)):
         gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=70 + jperio)
         mx = H.mus_extra_fields(O, gf, G, GJ, K, jperio, seed=70 + jperio)
         _, refl = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, part[0], part[1], kjpt)

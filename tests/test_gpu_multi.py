@@ -39,3 +39,16 @@ def test_widened_rows_over_nccl():
     r = _run(n, {}, 2400)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU_CHECK PASS" in r.stdout and "MISMATCH" not in r.stdout
+
+
+def test_collective_diagnostics_over_nccl():
+    """glob_sum (MPI_SUMDD, lib_mpp.F90:1158-1186) and stp_ctl with ln_ctl (mpp_max / mpp_maxloc, stpctl.F90:126-129, 157-160)
+    through the NCCL communicator: the same numbers on every rank as the mono-domain oracle"""
+    n = torch.cuda.device_count()
+    n = 8 if n >= 8 else 4 if n >= 4 else 2 if n >= 2 else 1
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    r = _run(n, {"MGPU_ONLY_DIAG": "1"}, 600)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MGPU_CHECK PASS" in r.stdout and "MISMATCH" not in r.stdout and "glob_sum over NCCL" in r.stdout
