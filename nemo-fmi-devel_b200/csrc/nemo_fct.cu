@@ -1373,6 +1373,9 @@ int nemo_tra_adv_fct(nemo_fct_handle h, int kt, int kit000, const char *cdtype, 
             CUTHROW(cudaEventCreateWithFlags(&h->ev_e3t, cudaEventDisableTiming));
         }
     } catch (const std::exception &e) { return fail("tra_adv_fct: copy streams: %s", e.what()); }
+    // The copies below read and write the CALLER's arrays asynchronously: whatever way this function is left (a failed launch or
+    // copy included), nothing may still be in flight on them when it returns
+    struct Drain { cudaStream_t a, b, c; ~Drain() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); cudaStreamSynchronize(c); } } drain{h->copy_in, h->copy_out, s};
     size_t nev = 0;
     auto event = [&]() -> cudaEvent_t {                                // pooled, timing disabled
         if (nev == h->ev_pool.size()) { cudaEvent_t e = nullptr; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr; h->ev_pool.push_back(e); }
