@@ -13,10 +13,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+_port = [29533]
+
+
 def _run(nproc, env_extra, timeout):
     env = dict(os.environ, **env_extra)
+    _port[0] += 1                                                      # a fresh rendezvous port per launch
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_check.py")]
+           "--master-port", str(_port[0]), os.path.join(ROOT, "tests", "mgpu_check.py")]
     return subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
 
 
