@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) k_glob_sum_final(const double *partial, i
 
 }  // namespace
 
+#ifndef NEMO_EMU_KERNELS_ONLY          // the launcher (CUDA launch syntax) is left out of the host emulation build of tests/emu
 void launch_glob_sum(const double *const *ptab_dev, int nfld, const double *pw3d, const double *tmask_i, size_t jpij, int ipk, double *partial,
                      double *out_pairs, cudaStream_t s)
 {
@@ -83,5 +84,7 @@ void launch_glob_sum(const double *const *ptab_dev, int nfld, const double *pw3d
     k_glob_sum_final<<<nfld, 256, 0, s>>>(partial, nblk, out_pairs);
     note_launch();
 }
+
+#endif  // NEMO_EMU_KERNELS_ONLY
 
 }  // namespace nemo

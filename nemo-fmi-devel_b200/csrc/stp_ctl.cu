@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) k_stp_ctl_final(const StpCtlRec *partial,
 
 }  // namespace
 
+#ifndef NEMO_EMU_KERNELS_ONLY          // the launcher (CUDA launch syntax) is left out of the host emulation build of tests/emu
 void launch_stp_ctl(const double *sshn, const double *un, const double *tem, const double *sal, const double *tmask, size_t jpij, size_t n3,
                     StpCtlRec *partial, StpCtlRec *out, cudaStream_t s)
 {
@@ -134,5 +135,7 @@ void launch_stp_ctl(const double *sshn, const double *un, const double *tem, con
     k_stp_ctl_final<<<1, 256, 0, s>>>(partial, kGlobSumBlocks, out);
     note_launch();
 }
+
+#endif  // NEMO_EMU_KERNELS_ONLY
 
 }  // namespace nemo

@@ -239,3 +239,25 @@ def fct_step(L, f, kjpt, h, v, lin, isf, nk, lbc, hooks=False):
             work[k] = np.full(shp, -7.0e77)
         fct(L, 5, interior, 1, f, work, kjpt, h, v, lin, isf)
     return work["pta"], work
+
+
+def glob_sum(L, fields, tmask_i, w3d=None, nblk=4):
+    """k_glob_sum_partial + k_glob_sum_final (csrc/glob_sum.cu) on a grid of nblk blocks: [(hi, lo)] per field"""
+    import numpy as np
+    nfld = len(fields)
+    ipk = int(np.prod(fields[0].shape[:-2])) if fields[0].ndim > 2 else 1
+    jpij = fields[0].shape[-1] * fields[0].shape[-2]
+    tab = (C.c_void_p * nfld)(*[a.ctypes.data for a in fields])
+    out = np.zeros(2 * nfld)
+    L.emu_glob_sum.restype = C.c_int
+    L.emu_glob_sum(tab, nfld, p(w3d), p(tmask_i), C.c_longlong(jpij), ipk, nblk, p(out))
+    return [(out[2 * f], out[2 * f + 1]) for f in range(nfld)]
+
+
+def stp_ctl(L, sshn, un, tem, sal, tmask, nblk=4):
+    """k_stp_ctl_partial + k_stp_ctl_final (csrc/stp_ctl.cu): (values[6], first linear indices[6], flags)"""
+    import numpy as np
+    vals, idx, flags = np.zeros(6), np.zeros(6, np.int64), C.c_int(0)
+    L.emu_stp_ctl.restype = C.c_int
+    L.emu_stp_ctl(p(sshn), p(un), p(tem), p(sal), p(tmask), C.c_longlong(sshn.size), C.c_longlong(un.size), nblk, p(vals), p(idx), C.byref(flags))
+    return vals, idx, flags.value
