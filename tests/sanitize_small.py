@@ -55,4 +55,27 @@ for name in ("nxt_vvl_jperio4", "nxt_fix_jperio1"):
     same = all(bool(np.array_equal(got[k], ref[k])) for k in ref)
     print("tra_nxt", name, "bit-identical" if same else "MISMATCH", flush=True)
     ok = ok and same
+# diagnostic reductions: glob_sum (double-double) and stp_ctl (extrema + locations): warp shuffles + shared memory
+import torch                 # noqa: E402
+gf = H.random_fields(O, G, GJ, K, 4, kjpt=2, seed=9)
+rng = np.random.default_rng(9)
+sshn = np.ascontiguousarray(rng.standard_normal((GJ, G)))
+un = np.ascontiguousarray(rng.standard_normal((K, GJ, G)))
+tsn = np.ascontiguousarray(np.stack([10.0 + rng.standard_normal((K, GJ, G)), 35.0 + rng.standard_normal((K, GJ, G))]))
+w = O.World(G, GJ, K, 4)
+ref_ctl = O.stp_ctl(w.doms[0], sshn, un, tsn, gf["tmask"])
+ref_sum = O.glob_sum(w, [np.ascontiguousarray(gf["ptb"][0] * gf["e3t_n"])], [np.ascontiguousarray(gf["tmask_i"])])[0]
+w.close()
+ctx = N.FctContext(N.mpp_init(G, GJ, K, 4, 1, 1, 1), 0)
+ctx.set_domain_arrays(gf["tmask"], gf["umask"], gf["vmask"], gf["wmask"], gf["e1e2t"], gf["r1_e1e2t"], gf["mikt"], gf["mbkt"])
+dev = torch.device("cuda:0")
+got = ctx.stp_ctl(1, torch.from_numpy(sshn).to(dev), torch.from_numpy(un).to(dev), torch.from_numpy(tsn).to(dev))
+same = all(got[k] == ref_ctl[k] for k in ("zmax", "ih", "iu", "is1", "is2", "nan_found", "kindic"))
+print("stp_ctl", "bit-identical" if same else "MISMATCH", flush=True)
+ok = ok and same
+gsum = ctx.glob_sum("san", [torch.from_numpy(np.ascontiguousarray(gf["ptb"][0])).to(dev)], torch.from_numpy(np.ascontiguousarray(gf["tmask_i"])).to(dev),
+                    w3d=torch.from_numpy(np.ascontiguousarray(gf["e3t_n"])).to(dev))[0]
+print("glob_sum", "bit-identical" if gsum == ref_sum else "MISMATCH", flush=True)
+ok = ok and gsum == ref_sum
+ctx.close()
 sys.exit(0 if ok else 1)
