@@ -5,7 +5,7 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 SRC=${NEMO_SRC:-/root/reference}
 FC=${FC:-gfortran}
 OUT=$HERE/../_ref
-if ! command -v "$FC" >/dev/null 2>&1; then echo "_ref_recipe: no Fortran compiler ($FC) on this machine -- nothing built, parity stays unpinned"; exit 0; fi
+if ! command -v "$FC" >/dev/null 2>&1; then echo "_ref_recipe: no Fortran compiler ($FC) on this machine -- nothing built: no compiled-binary pin (the source-text pin is tests/test_cpu_reference_exec.py)"; exit 0; fi
 if [ ! -f "$SRC/src/OCE/TRA/traadv_fct.F90" ]; then echo "_ref_recipe: no NEMO source tree at $SRC -- nothing built"; exit 0; fi
 mkdir -p "$OUT/build" && cd "$OUT/build"
 O=$SRC/src/OCE

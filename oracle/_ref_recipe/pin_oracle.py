@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     exe = os.path.join(ROOT, "oracle", "_ref", "fct_ref_driver")
     if not os.path.exists(exe):
-        print("pin_oracle: %s not built (no gfortran or no NEMO tree): parity stays unpinned" % exe)
+        print("pin_oracle: %s not built (no gfortran or no NEMO tree): no compiled-binary pin (the source-text pin is tests/test_cpu_reference_exec.py)" % exe)
         return 0
     import helpers as H
     from oracle import oracle as O

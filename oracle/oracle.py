@@ -3,7 +3,7 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 The oracle is a loop-for-loop C restatement of the reference's tra_adv_fct / nonosc / interp_4th_cpt
 (src/OCE/TRA/traadv_fct.F90), lbc_lnk / mpp_lnk / lbc_nfd / mpp_nfd (src/OCE/LBC/*.h90) and mpp_init
-(src/OCE/LBC/mppini.F90).  PARITY UNPINNED: the reference holds no golden vectors for this path.
+(src/OCE/LBC/mppini.F90).  PARITY PIN: see nemo_oracle.h (the reference's source text executed by translation, oracle/f90exec.py + ref_exec.py).
 
 Arrays are numpy float64 in Fortran layout seen from C order: shape (jpk, jpj, jpi) [or (kjpt, jpk, jpj, jpi)],
 i.e. ji fastest, exactly the memory image of REAL(wp) a(jpi,jpj,jpk[,kjpt]).

@@ -1,0 +1,182 @@
+"""ref_exec -- ORACLE-SIDE TEST INFRASTRUCTURE: runs the reference's own tra_adv_fct / nonosc / interp_4th_cpt source
+(src/OCE/TRA/traadv_fct.F90, read from the reference tree at run time, never copied) through oracle/f90exec.py on numpy arrays.
+Only usable where the reference tree exists (this container); the GPU box sees the golden vectors generated from it
+(tests/golden/ref_exec_*.npz, oracle/_ref_recipe/make_ref_exec_golden.py)."""
+import os
+
+import numpy as np
+
+from . import f90exec
+
+REF_ROOT = os.environ.get("NEMO_REFERENCE_ROOT", "/root/reference")
+DOM_ARRAYS = ("tmask", "umask", "vmask", "wmask", "e3t_b", "e3t_n", "e3t_a", "e1e2t", "r1_e1e2t")
+DOM_INT_ARRAYS = ("mikt", "mbkt")
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_ROOT, "src", "OCE", "TRA", "traadv_fct.F90"))
+
+
+def _read(*rel):
+    with open(os.path.join(REF_ROOT, *rel)) as f:
+        return f.read()
+
+
+def F(a):
+    """Fortran view a(jpi,jpj[,jpk[,kjpt]]) of a C-ordered array [kjpt][jpk][jpj][jpi]: same memory"""
+    return np.transpose(a)
+
+
+class RefDomain:
+    """the module variables the tracer routines read (dom_oce, par_oce, in_out_manager, trd_oce, diaptr) for ONE mono-processor
+    domain, plus lbc_lnk / lbc_lnk_multi.  `lbc` = callable(list of (C-ordered array, nature, sign)) doing the exchange in place:
+    reference_lbc() below, i.e. the reference's own lbc_lnk / lbc_nfd text (lbc_lnk_multi is a loop over its fields,
+    lbc_lnk_multi_generic.h90)."""
+
+    def __init__(self, gf, jpi, jpj, jpk, ln_linssh, ln_isfcav, lbc, sign_mode="nosignedzero", undef=np.nan):
+        ns = {}
+        # what an automatic (stack) array holds before it is defined: NaN shows every read of an undefined element that reaches
+        # the result; 0.0 is one value the memory may hold (what the oracle's calloc'ed work arrays hold)
+        ns["f_alloc"] = lambda shape, integer=False: (np.zeros(tuple(int(n) for n in shape), dtype=np.int32, order="F") if integer
+                                                      else np.full(tuple(int(n) for n in shape), undef, order="F"))
+        ns.update(jpi=jpi, jpj=jpj, jpk=jpk, jpim1=jpi - 1, jpjm1=jpj - 1, jpkm1=jpk - 1, ln_linssh=bool(ln_linssh), ln_isfcav=bool(ln_isfcav),
+                  lwp=False, numout=6, l_trdtra=False, l_trdtrc=False, ln_diaptr=False, iom_use=lambda name: False)
+        for k in DOM_ARRAYS:
+            ns[k] = F(np.ascontiguousarray(gf[k]))
+        for k in DOM_INT_ARRAYS:
+            ns[k] = F(np.ascontiguousarray(gf[k], dtype=np.int32))
+
+        def lbc_lnk_multi(cdname, *triples):
+            assert len(triples) % 3 == 0
+            lbc([(np.transpose(triples[i]), triples[i + 1], float(triples[i + 2])) for i in range(0, len(triples), 3)])
+
+        def lbc_lnk(cdname, a, nat, sgn):
+            lbc([(np.transpose(a), nat, float(sgn))])
+        ns.update(lbc_lnk_multi=lbc_lnk_multi, lbc_lnk=lbc_lnk)
+        self.ns = ns
+        self.defines = f90exec.cpp_defines(_read("src", "OCE", "vectopt_loop_substitute.h90"))      # fs_2, fs_jpim1 (no key_vectopt_loop)
+        if sign_mode == "nosignedzero":
+            # the reference's gfortran arch file builds with -Dkey_nosignedzero (arch/arch-linux_gfortran.fcm:46): SIGN is then
+            # lib_fortran's SIGN_SCALAR (lib_fortran.F90:339-351), taken here from the reference's own text
+            f90exec.load(_read("src", "OCE", "lib_fortran.F90"), ns, only=("sign_scalar",), defined=("key_nosignedzero",))
+            scalar = ns["sign_scalar"]
+            ns["f_sign"] = lambda a, b: (np.where(np.asarray(b) >= 0.0, np.abs(a), -np.abs(a))
+                                         if isinstance(a, np.ndarray) or isinstance(b, np.ndarray) else scalar(a, b))
+        else:
+            assert sign_mode == "ieee"
+
+    def load(self, *rel, only=None):
+        text = _read(*rel)
+        f90exec.module_parameters(text, self.ns, self.defines)
+        return f90exec.load(text, self.ns, arrays=DOM_ARRAYS, int_arrays=DOM_INT_ARRAYS, defines=self.defines, only=only)
+
+
+def reference_lbc(jperio, jpi, jpj):
+    """lbc_lnk of the reference itself for ONE mono-processor domain, from its text: lbc_lnk_generic.h90 (the build without
+    key_mpp_mpi, lbclnk.F90:59-170, 3-D variant) calling lbc_nfd_generic.h90 (lbcnfd.F90, 3-D variant) for the north folds.  The
+    scalars it reads are those mpp_init sets for jpni = jpnj = 1 (mppini.F90:88-101: npolj = jperio for the folds, l_Iperio /
+    l_Jperio from the cyclic types)."""
+    ns = dict(jpi=jpi, jpj=jpj, jpim1=jpi - 1, jpjm1=jpj - 1, jpiglo=jpi, jpjglo=jpj, jpni=1, jpnj=1, nlci=jpi, nlcj=jpj, jperio=jperio,
+              npolj=jperio if jperio in (3, 4, 5, 6) else 0, l_iperio=jperio in (1, 4, 6, 7), l_jperio=jperio in (2, 7))
+    nfd = f90exec.cpp(_read("src", "OCE", "LBC", "lbc_nfd_generic.h90"), defined=("DIM_3d",), macros={"ROUTINE_NFD": "lbc_nfd_3d"})
+    lnk = f90exec.cpp(_read("src", "OCE", "LBC", "lbc_lnk_generic.h90"), defined=("DIM_3d",), macros={"ROUTINE_LNK": "lbc_lnk_3d"})
+    f90exec.load(nfd, ns)
+    f90exec.load(lnk, ns)
+    ns["lbc_nfd"] = ns["lbc_nfd_3d"]                                   # INTERFACE lbc_nfd (lbcnfd.F90:27-31)
+
+    def lbc(items):
+        for a, nat, sgn in items:                                      # a: C-ordered [jpk][jpj][jpi] (or [jpj][jpi])
+            a3 = a if a.ndim == 3 else a.reshape((1,) + a.shape)
+            ns["lbc_lnk_3d"]("ref_exec", np.transpose(a3), nat, float(sgn))
+    return lbc
+
+
+def tra_adv_fct(gf, jpi, jpj, jpk, kjpt, kn_fct_h, kn_fct_v, ln_linssh, ln_isfcav, lbc, cdtype="TRA", sign_mode="nosignedzero"):
+    """the reference's tra_adv_fct on the C-ordered fields of `gf` (helpers.random_fields); returns the new pta"""
+    dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, ln_isfcav, lbc, sign_mode)
+    dom.load("src", "OCE", "TRA", "traadv_fct.F90", only=("tra_adv_fct", "nonosc", "interp_4th_cpt"))
+    pta = np.array(gf["pta"], copy=True)
+    args = [F(np.ascontiguousarray(gf[k])) for k in ("pun", "pvn", "pwn", "ptb", "ptn")]
+    dom.ns["tra_adv_fct"](1, 1, cdtype, float(gf["p2dt"]), args[0], args[1], args[2], args[3], args[4], F(pta), kjpt, kn_fct_h, kn_fct_v)
+    return pta
+
+
+MUS_ARRAYS = ("r1_e1e2u", "r1_e1e2v", "e3u_n", "e3v_n", "e3w_n", "rnfmsk", "rnfmsk_z")
+NXT_ARRAYS = ("tsb", "tsn", "tsa", "emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf", "h_rnf", "qsr_hc", "qsr_hc_b", "rnf_tsc", "rnf_tsc_b",
+              "risf_tsc", "risf_tsc_b", "r1_hisf_tbl", "ralpha", "sbc_tsc", "sbc_tsc_b")
+NXT_INT_ARRAYS = ("nk_rnf", "misfkt", "misfkb")
+
+
+def tra_adv_mus(gf, mx, jpi, jpj, jpk, kjpt, ln_linssh, ln_isfcav, ld_msc_ups, lbc, cdtype="TRA"):
+    """the reference's tra_adv_mus (src/OCE/TRA/traadv_mus.F90) called at kt = kit000, so that it builds its own upstream
+    indicator xind from rnfmsk / rnfmsk_z (:98-113); returns the new pta"""
+    dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, ln_isfcav, lbc)
+    for k in ("r1_e1e2u", "r1_e1e2v", "e3u_n", "e3v_n", "e3w_n"):
+        dom.ns[k] = F(np.ascontiguousarray(mx[k]))
+    if ld_msc_ups:
+        dom.ns["rnfmsk"] = F(np.ascontiguousarray(mx["rnfmsk"]))
+        dom.ns["rnfmsk_z"] = np.ascontiguousarray(mx["rnfmsk_z"])
+    text = _read("src", "OCE", "TRA", "traadv_mus.F90")
+    f90exec.module_parameters(text, dom.ns, dom.defines)
+    f90exec.load(text, dom.ns, arrays=DOM_ARRAYS + MUS_ARRAYS, int_arrays=DOM_INT_ARRAYS, defines=dom.defines, only=("tra_adv_mus",))
+    pta = np.array(gf["pta"], copy=True)
+    args = [F(np.ascontiguousarray(gf[k])) for k in ("pun", "pvn", "pwn", "ptb")]
+    dom.ns["tra_adv_mus"](1, 1, cdtype, float(gf["p2dt"]), args[0], args[1], args[2], args[3], F(pta), kjpt, bool(ld_msc_ups))
+    return pta
+
+
+def tra_adv_cen(gf, jpi, jpj, jpk, kjpt, kn_cen_h, kn_cen_v, ln_linssh, ln_isfcav, lbc, cdtype="TRA", undef=np.nan):
+    """the reference's tra_adv_cen (src/OCE/TRA/traadv_cen.F90; its compact vertical scheme calls the reference's
+    interp_4th_cpt of traadv_fct.F90); returns the new pta"""
+    dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, ln_isfcav, lbc, undef=undef)
+    dom.load("src", "OCE", "TRA", "traadv_fct.F90", only=("interp_4th_cpt",))
+    dom.load("src", "OCE", "TRA", "traadv_cen.F90", only=("tra_adv_cen",))
+    pta = np.array(gf["pta"], copy=True)
+    args = [F(np.ascontiguousarray(gf[k])) for k in ("pun", "pvn", "pwn", "ptn")]
+    dom.ns["tra_adv_cen"](1, 1, cdtype, args[0], args[1], args[2], args[3], F(pta), kjpt, kn_cen_h, kn_cen_v)
+    return pta
+
+
+def tra_nxt(gf, extra, jpi, jpj, jpk, kt, nit000, neuler, rdt, atfp, r1_rau0, ln_linssh, lbc):
+    """the reference's tra_nxt driver (src/OCE/TRA/tranxt.F90:65-177: lbc_lnk on tsa, tra_nxt_fix or tra_nxt_vvl, lbc_lnk on tsb, tsn,
+    tsa) on tsb / tsn / tsa = the case's ptb / ptn / pta (jpts = 2), without solar penetration, runoffs, ice shelves, BDY, AGRIF
+    or trend diagnostics; returns (tsb, tsn, tsa)"""
+    dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, False, lbc)
+    ts = {k: np.array(gf[s], copy=True) for k, s in (("tsb", "ptb"), ("tsn", "ptn"), ("tsa", "pta"))}
+    ns = dom.ns
+    for k, a in ts.items():
+        ns[k] = F(a)
+    ns.update(jpts=2, jp_tem=1, jp_sal=2, nit000=nit000, neuler=neuler, rdt=float(rdt), r2dt=0.0, atfp=float(atfp), r1_rau0=float(r1_rau0),
+              ln_timing=False, ln_bdy=False, ln_traldf_iso=False, ln_ctl=False, ln_traqsr=False, ln_rnf=False, ln_isf=False,
+              ln_rnf_depth=False, nksr=0)
+    for k in ("emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf"):
+        ns[k] = F(np.ascontiguousarray(extra[k]))
+    ns["sbc_tsc"], ns["sbc_tsc_b"] = F(np.ascontiguousarray(extra["sbc"])), F(np.ascontiguousarray(extra["sbc_b"]))
+    text = _read("src", "OCE", "TRA", "tranxt.F90")
+    f90exec.load(text, ns, arrays=DOM_ARRAYS + NXT_ARRAYS, int_arrays=DOM_INT_ARRAYS + NXT_INT_ARRAYS, defines=dom.defines, module_vars=("r2dt",))
+    ns["tra_nxt"](kt)
+    return ts["tsb"], ts["tsn"], ts["tsa"]
+
+
+def tra_adv(gf, vel, jpi, jpj, jpk, kt, nit000, neuler, rdt, nn_fct_h, nn_fct_v, ln_linssh, ln_isfcav, lbc):
+    """the reference's tra_adv driver (src/OCE/TRA/traadv.F90:77-175) on the FCT branch: r2dt rule (:88-90), effective transports
+    from un, vn, wn (:93-118; no Stokes drift, z-tilde, eiv or mle additions), then ITS call of tra_adv_fct (:150) on tsb, tsn, tsa =
+    the case's ptb, ptn, pta.  vel = dict(e2u, e1v, e3u_n, e3v_n, un, vn, wn).  Returns (tsa, r2dt)."""
+    dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, ln_isfcav, lbc)
+    ns = dom.ns
+    ts = {k: np.array(gf[s], copy=True) for k, s in (("tsb", "ptb"), ("tsn", "ptn"), ("tsa", "pta"))}
+    for k, a in ts.items():
+        ns[k] = F(a)
+    for k in ("e2u", "e1v", "e3u_n", "e3v_n", "un", "vn", "wn"):
+        ns[k] = F(np.ascontiguousarray(vel[k]))
+    ns.update(jpts=ts["tsa"].shape[0], jp_tem=1, jp_sal=2, nit000=nit000, neuler=neuler, rdt=float(rdt), r2dt=0.0, ln_timing=False,
+              ln_wave=False, ln_sdw=False, ln_vvl_ztilde=False, ln_vvl_layer=False, ln_ldfeiv=False, ln_traldf_triad=False, ln_mle=False,
+              ln_ctl=False, nn_fct_h=nn_fct_h, nn_fct_v=nn_fct_v, iom_put=lambda *a: None)
+    dom.load("src", "OCE", "TRA", "traadv_fct.F90", only=("tra_adv_fct", "nonosc", "interp_4th_cpt"))
+    text = _read("src", "OCE", "TRA", "traadv.F90")
+    f90exec.module_parameters(text, ns, dom.defines)                   # np_CEN, np_FCT, ... (traadv.F90:58-63)
+    f90exec.load(text, ns, arrays=DOM_ARRAYS + NXT_ARRAYS + ("e2u", "e1v", "e3u_n", "e3v_n", "un", "vn", "wn"), int_arrays=DOM_INT_ARRAYS,
+                 defines=dom.defines, only=("tra_adv",), module_vars=("r2dt",))
+    ns["nadv"] = ns["np_fct"]
+    ns["tra_adv"](kt)
+    return ts["tsa"], ns["r2dt"]

@@ -1,7 +1,7 @@
 /*
  * traadv_cen.c -- ORACLE (test infrastructure only; see nemo_oracle.h).
  * Loop-for-loop C restatement of src/OCE/TRA/traadv_cen.F90:46-204 (tra_adv_cen, 2nd / 4th order centred scheme,
- * 2nd order or 4th-order COMPACT in the vertical).  PARITY UNPINNED by reference golden vectors (none exist).
+ * 2nd order or 4th-order COMPACT in the vertical).  PARITY PIN: bit-identical to the reference's own source executed by translation (oracle/f90exec.py); see nemo_oracle.h.
  *
  * REFERENCE DEFECT kept visible (kn_cen_h = 4 only, traadv_cen.F90:124-137): the flux loop runs ji = 1..jpim1,
  * jj = 2..jpjm1, so (i) at ji = 1 it reads ztu(0,jj,jk), one element before the row -- in the contiguous automatic

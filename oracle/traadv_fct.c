@@ -2,7 +2,7 @@
  * traadv_fct.c -- ORACLE (test infrastructure only; see nemo_oracle.h).
  * Loop-for-loop C restatement of src/OCE/TRA/traadv_fct.F90 (tra_adv_fct :54-327, nonosc :330-428,
  * interp_4th_cpt :517-616).  Same loop bounds, same operation order, same automatic work arrays living
- * across the tracer loop.  PARITY UNPINNED by reference golden vectors (none exist); see nemo_oracle.h.
+ * across the tracer loop.  PARITY PIN: bit-identical to the reference's own source executed by translation (oracle/f90exec.py); see nemo_oracle.h.
  *
  * The l_trd / l_hst / l_ptr hooks (:96-112, :172-176, :299-316) are restated up to the point where the reference hands
  * ztrdx / ztrdy / ztrdz (zptry = ztrdy) to trd_tra, dia_ar5_hst and dia_ptr_hst: d->diag_trd* receive those arrays.

@@ -2,7 +2,7 @@
  * traadv_mus.c -- ORACLE (test infrastructure only; see nemo_oracle.h).
  * Loop-for-loop C restatement of src/OCE/TRA/traadv_mus.F90:55-273 (tra_adv_mus, MUSCL scheme): same loop
  * bounds, same operation order, the two automatic pairs zwx/zslpx, zwy/zslpy reused as in the reference.
- * PARITY UNPINNED by reference golden vectors (none exist); see nemo_oracle.h.
+ * PARITY PIN: bit-identical to the reference's own source executed by translation (oracle/f90exec.py); see nemo_oracle.h.
  *
  * Not restated: l_trd / l_hst / l_ptr diagnostics (:117-124, :207-214, :268), off by default.
  * Module arrays read besides those of tra_adv_fct: r1_e1e2u, r1_e1e2v (dom_oce.F90:118), e3u_n, e3v_n, e3w_n

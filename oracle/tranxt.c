@@ -2,7 +2,7 @@
  * tranxt.c -- ORACLE (test infrastructure only; see nemo_oracle.h).
  * Loop-for-loop C restatement of src/OCE/TRA/tranxt.F90 (tra_nxt :65-187, tra_nxt_fix :190-234,
  * tra_nxt_vvl :237-380) and of the swap part of src/TOP/TRP/trcnxt.F90:56-183 (trc_nxt).
- * PARITY UNPINNED by reference golden vectors (none exist); see nemo_oracle.h.
+ * PARITY PIN: bit-identical to the reference's own source executed by translation (oracle/f90exec.py); see nemo_oracle.h.
  *
  * Not restated (optional hooks, off by default in the reference): AGRIF, ln_bdy, l_trdtra / l_trdtrc trends
  * (:121-146, :169-178, :278-281, :359-378), prt_ctl, trc_nxt_off (l_offline).

@@ -1,0 +1,72 @@
+"""Regenerate tests/golden/ref_exec_pins.json: sha256 of the outputs of the REFERENCE'S OWN SOURCE (tra_adv_fct / nonosc /
+interp_4th_cpt, tra_adv_mus, tra_adv_cen, tra_nxt + tra_nxt_fix / tra_nxt_vvl of /root/reference/src/OCE/TRA/*.F90, with the lateral
+boundary conditions of src/OCE/LBC/lbc_lnk_generic.h90 + lbc_nfd_generic.h90 and SIGN of src/OCE/lib_fortran.F90), executed through
+oracle/f90exec.py on the seeded cases of tests/golden_cases.py -- the same cases whose oracle outputs are tests/golden/vectors.json
+and against which the GPU suite checks the CUDA path.  Needs the reference tree (this container); run from the repository root:
+
+    python tests/golden/make_ref_exec_pins.py
+
+Every entry records the sha256 of the reference files it executed, so a pin can be traced to the exact source text."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import oracle as O              # noqa: E402
+from oracle import ref_exec as R            # noqa: E402
+import golden_cases as GC                   # noqa: E402
+
+FILES = {"fct": ["src/OCE/TRA/traadv_fct.F90"], "mus": ["src/OCE/TRA/traadv_mus.F90"],
+         "cen": ["src/OCE/TRA/traadv_cen.F90", "src/OCE/TRA/traadv_fct.F90"], "nxt": ["src/OCE/TRA/tranxt.F90"]}
+COMMON = ["src/OCE/lib_fortran.F90", "src/OCE/vectopt_loop_substitute.h90", "arch/arch-linux_gfortran.fcm",
+          "src/OCE/LBC/lbc_lnk_generic.h90", "src/OCE/LBC/lbc_nfd_generic.h90"]
+
+
+def file_sha(rel):
+    return hashlib.sha256(open(os.path.join(R.REF_ROOT, rel), "rb").read()).hexdigest()
+
+
+def run_reference(name, undef=np.nan):
+    """outputs of the reference source for one golden case (dict of arrays, as golden_cases.run_oracle)"""
+    kind, jperio, opt = GC.CASES[name]
+    gf, extra = GC.inputs(O, name)
+    lbc = R.reference_lbc(jperio, GC.G, GC.GJ)        # the reference's own lbc_lnk_generic.h90 + lbc_nfd_generic.h90
+    lin, isf = opt.get("ln_linssh", False), opt.get("ln_isfcav", False)
+    if True:
+        if kind == "fct":
+            return {"pta": R.tra_adv_fct(gf, GC.G, GC.GJ, GC.K, GC.KJPT, opt["h"], opt["v"], lin, isf, lbc)}, gf, extra
+        if kind == "mus":
+            return {"pta": R.tra_adv_mus(gf, extra, GC.G, GC.GJ, GC.K, GC.KJPT, lin, isf, opt.get("ld_msc_ups", False), lbc)}, gf, extra
+        if kind == "cen":
+            return {"pta": R.tra_adv_cen(gf, GC.G, GC.GJ, GC.K, GC.KJPT, opt["h"], opt["v"], lin, isf, lbc, undef=undef)}, gf, extra
+        tb, tn, ta = R.tra_nxt(gf, extra, GC.G, GC.GJ, GC.K, 5, 1, 1, GC.NXT["rdt"], GC.NXT["atfp"], GC.NXT["r1_rau0"], opt["ln_linssh"], lbc)
+        return {"ptb": tb, "ptn": tn, "pta": ta}, gf, extra
+
+
+#: cases whose reference result depends on UNDEFINED memory (see tests/test_cpu_reference_exec.py): pinned with automatic arrays
+#: that start as 0.0, and flagged
+UNDEFINED_READS = {"cen_h4v2_jperio0": "tra_adv_cen with nn_cen_h = 4 reads zwy(:,1,:), which it never defines (traadv_cen.F90:127-140, 181-190)"}
+
+if __name__ == "__main__":
+    pins = {"_about": "sha256 of the outputs of the reference's own Fortran source executed through oracle/f90exec.py "
+                      "(tests/golden/make_ref_exec_pins.py); compare with tests/golden/vectors.json",
+            "_sign": "key_nosignedzero, as arch/arch-linux_gfortran.fcm:46 builds (SIGN = lib_fortran.F90:339-351, from the reference's text)",
+            "_common_files": {f: file_sha(f) for f in COMMON}, "cases": {}}
+    for name in sorted(GC.CASES):
+        kind = GC.CASES[name][0]
+        out, gf, extra = run_reference(name, undef=0.0 if name in UNDEFINED_READS else np.nan)
+        ent = {"input_sha256": GC.input_hash(gf, extra), "outputs": {k: GC.digest(v) for k, v in sorted(out.items())},
+               "reference_files": {f: file_sha(f) for f in FILES[kind]}}
+        if name in UNDEFINED_READS:
+            ent["undefined_read"] = UNDEFINED_READS[name]
+        pins["cases"][name] = ent
+        print(name, ent["outputs"])
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_exec_pins.json")
+    with open(path, "w") as f:
+        json.dump(pins, f, indent=1, sort_keys=True)
+    print(path, os.path.getsize(path), "bytes")

@@ -1,9 +1,10 @@
 """Small seeded cases whose ORACLE outputs are committed as golden vectors (tests/golden/vectors.json: sha256 of every
 output array + a block of sample values).
 
-The reference holds no golden vectors for this path and cannot be built here, so these are regression pins of the oracle
-itself (generated by tests/golden/make_vectors.py, script committed): the CPU suite checks that the oracle still reproduces
-them bit for bit, the GPU suite compares the CUDA path with the committed arrays directly, with no oracle in the loop.
+The reference holds no golden vectors for this path and cannot be compiled here; these vectors are generated from the oracle
+(tests/golden/make_vectors.py, script committed) AND are what the reference's own source text produces when executed by
+translation (tests/golden/ref_exec_pins.json, tests/test_cpu_reference_exec.py).  The CPU suite checks that the oracle still
+reproduces them bit for bit, the GPU suite compares the CUDA path with the committed arrays directly, with no oracle in the loop.
 Every case records a sha256 of its inputs so that a change of the input generator (numpy RNG stream) is told apart from a
 change of the arithmetic."""
 import hashlib

@@ -1,0 +1,362 @@
+"""The oracle pinned against the REFERENCE'S OWN SOURCE TEXT.
+
+No Fortran compiler exists in this image or on the GPU box (oracle/_ref_recipe/), so the reference cannot be compiled; instead
+oracle/f90exec.py translates the reference's routines line by line (DO / IF / SELECT CASE, array elements and sections, MAX / MIN /
+ABS / SIGN, CALL) into Python and executes them on numpy arrays (IEEE binary64, one rounding per operation).  Loop bounds, statement
+order and every arithmetic expression are the reference's, character for character.
+
+  * everywhere (GPU box included): tests/golden/vectors.json (what the oracle produces, and what `pytest -m gpu` holds the CUDA path
+    to) carries the same sha256 as tests/golden/ref_exec_pins.json (what the reference's source produced when executed here);
+  * where the reference tree exists (this container): the pins are regenerated and compared, and the reference's tra_adv_fct /
+    nonosc / interp_4th_cpt, tra_adv (driver + transports), tra_adv_mus, tra_adv_cen and tra_nxt run against the oracle on a
+    matrix of boundary types, orders, ln_linssh / ln_isfcav -- bit for bit -- with the lateral boundary conditions ALSO taken from
+    the reference's text (lbc_lnk_generic.h90 + lbc_nfd_generic.h90 through a small cpp: nothing of the oracle is in that loop),
+    and that lbc_lnk is compared with the oracle's for every boundary type, grid-point nature and sign;
+  * the translator itself is unit-tested on Fortran snippets written here.
+
+Two findings are pinned as tests: (1) SIGN -- the reference's gfortran arch file defines key_nosignedzero, under which SIGN is
+lib_fortran's "pb >= 0" function: that is what the oracle and the kernels implement, and with the IEEE intrinsic only the signs
+of exact zeros change; (2) tra_adv_cen with nn_cen_h = 4 reads an element it never defines."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from oracle import oracle as O
+from oracle import f90exec
+from oracle import ref_exec as R
+import helpers as H
+import golden_cases as GC
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+VECTORS = json.load(open(os.path.join(GOLD, "vectors.json")))
+PINS = json.load(open(os.path.join(GOLD, "ref_exec_pins.json")))
+needs_reference = pytest.mark.skipif(not R.available(), reason="the reference tree is not on this machine")
+
+
+# ---- everywhere ---------------------------------------------------------------------------------------------------------------
+def test_golden_vectors_are_what_the_reference_source_produced():
+    assert sorted(PINS["cases"]) == sorted(VECTORS) == sorted(GC.CASES)
+    for name, pin in PINS["cases"].items():
+        assert pin["input_sha256"] == VECTORS[name]["input_sha256"], name
+        assert pin["outputs"] == {k: v["sha256"] for k, v in VECTORS[name]["outputs"].items()}, name
+    assert [n for n, p in PINS["cases"].items() if "undefined_read" in p] == ["cen_h4v2_jperio0"]
+
+
+# ---- the translator, on snippets written here ------------------------------------------------------------------------------------
+def _run(src, **ns):
+    f90exec.load(src, ns, arrays=ns.pop("_arrays", ()), int_arrays=ns.pop("_int_arrays", ()))
+    return ns
+
+
+def test_translator_expressions_and_control_flow():
+    src = """
+    SUBROUTINE t( a, n, res )
+       REAL(wp), DIMENSION(n), INTENT(inout) ::   a      ! comment with ( and '
+       INTEGER , INTENT(in) :: n
+       REAL(wp), DIMENSION(8) :: res
+       INTEGER :: ji, ik
+       REAL(wp) :: zx
+       res(:) = 0._wp
+       res(1) = 7 / 2 + 1                      ! integer division truncates
+       res(2) = -7 / 2
+       res(3) = 2._wp * 3._wp / 4._wp * 5._wp  ! left to right
+       res(4) = - 2._wp ** 2                   ! -(2**2)
+       zx = 1.e-3_wp   ;   res(5) = zx * 1.d3
+       DO ji = n, 2, -1
+          a(ji) = a(ji) + a(ji-1)
+       END DO
+       ik = 0
+       DO ji = 1, n
+          IF( a(ji) > 2.5_wp .AND. .NOT. a(ji) >= 100. ) THEN   ;   ik = ik + 1
+          ELSEIF( a(ji) == 1._wp ) THEN ; ik = ik + 10
+          ELSE ; ik = ik + 100
+          ENDIF
+       END DO
+       res(6) = ik
+       SELECT CASE( n )
+       CASE( 1 , 2 )
+          res(7) = -1._wp
+       CASE( 4 )
+          res(7) = MAX( 0., a(1), a(n) ) - MIN( 3._wp, a(2) )
+       CASE DEFAULT
+          res(7) = -2._wp
+       END SELECT
+       IF( n /= 4 )   res(8) = 1._wp
+       IF( n == 4 )   res(8) = SIGN( 2._wp, -0._wp ) + ABS( -1.5_wp )
+    END SUBROUTINE t
+    """
+    a, res = np.array([1.0, 2.0, 3.0, 4.0]), np.full(8, np.nan)
+    _run(src, _arrays=())["t"](a, 4, res)
+    assert a.tolist() == [1.0, 3.0, 5.0, 7.0]                         # the descending loop sees the old neighbours
+    assert res.tolist() == [4.0, -3.0, 2.0 * 3.0 / 4.0 * 5.0, -4.0, 1.0e-3 * 1.0e3, 3 + 10, 7.0 - 3.0, -2.0 + 1.5]
+
+
+def test_translator_sections_whole_arrays_module_variables_and_functions():
+    src = """
+    MODULE m
+       REAL(wp) ::   r1_3 = 1._wp / 3._wp
+       REAL(wp), ALLOCATABLE, SAVE, DIMENSION(:,:) ::   keep
+    CONTAINS
+       SUBROUTINE s( pa, pb )
+          REAL(wp), DIMENSION(jpi,jpj,jpk), INTENT(inout) ::   pa
+          REAL(wp), DIMENSION(jpi,jpj    ), INTENT(in   ) ::   pb
+          REAL(wp), DIMENSION(jpi,jpj,jpk) ::   zw
+          INTEGER ::   jk
+          ALLOCATE( keep(jpi,jpj), STAT=jk )
+          keep(:,:) = pb(:,:) * r1_3
+          zw(:,:,jpk) = 0._wp
+          DO jk = 1, jpk-1
+             zw(:,:,jk) = pa(:,:,jk+1) - pa(:,:,jk) * msk(:,:)
+          END DO
+          pa = MAX( pa * 2._wp , zw ) + half( pb(2,3) )
+          pa(2:3,1,1) = -1._wp
+          CALL other( pa(:,:,2), 'T', 1. )
+       END SUBROUTINE s
+       FUNCTION half( px )
+          REAL(wp) :: px, half
+          half = 0.5_wp * px
+       END FUNCTION half
+    END MODULE m
+    """
+    jpi, jpj, jpk = 4, 3, 3
+    rng = np.random.default_rng(0)
+    pa, pb, msk = rng.standard_normal((jpi, jpj, jpk)), rng.standard_normal((jpi, jpj)), rng.random((jpi, jpj))
+    seen = []
+    ns = dict(jpi=jpi, jpj=jpj, jpk=jpk, msk=msk, other=lambda a, nat, sgn: seen.append((a.shape, nat, sgn, np.shares_memory(a, pa))))
+    f90exec.module_parameters(src, ns)
+    f90exec.load(src, ns, arrays=("msk",))
+    want = pa.copy()
+    zw = np.zeros_like(pa)
+    zw[:, :, :2] = pa[:, :, 1:] - pa[:, :, :2] * msk[:, :, None]
+    want = np.where(zw > want * 2.0, zw, want * 2.0) + 0.5 * pb[1, 2]
+    want[1:3, 0, 0] = -1.0
+    ns["s"](pa, pb)
+    assert np.array_equal(pa, want)
+    assert np.array_equal(ns["keep"], pb * (1.0 / 3.0))                # the module array was assigned, not a local
+    assert seen == [((jpi, jpj), "T", 1.0, True)]                     # a section argument is a view of the caller's array
+
+
+def test_translator_resolves_cpp_conditionals_and_flags_literals():
+    src = """
+    SUBROUTINE c( res )
+       REAL(wp), DIMENSION(2) :: res
+    #if defined key_a
+       res(1) = 1._wp
+    #else
+       res(1) = 2._wp
+    #endif
+    #if ! defined key_b
+       res(2) = 0.1
+    #endif
+    END SUBROUTINE c
+    """.replace("\n    #", "\n#")
+    for defined, want in (((), [2.0, 0.1]), (("key_a", "key_b"), [1.0, -1.0])):
+        ns, res = {}, np.array([-1.0, -1.0])
+        f90exec.load(src, ns, defined=defined)
+        ns["c"](res)
+        assert res.tolist() == want
+    assert f90exec.literal_report(src) == ["0.1"]                     # a default-kind literal that is not exact in single precision
+
+
+def test_cpp_function_like_macros_as_in_the_generic_h90_files():
+    src = """
+#if defined MULTI
+#   define ARRAY_IN(i,j,k,l,f)   ptab(f)%pt3d(i,j,k)
+#else
+#   define NAT_IN(k)             cd_nat
+#   if defined DIM_3d
+#      define ARRAY_IN(i,j,k,l,f)   ptab(i,j,k)
+#      define K_SIZE(ptab)          SIZE(ptab,3)
+#   endif
+#   define ARRAY_TYPE(i,j,k,l,f)    REAL(wp),INTENT(inout)::ARRAY_IN(i,j,k,l,f)
+#endif
+   SUBROUTINE ROUTINE_X( ptab, cd_nat )
+      ARRAY_TYPE(:,:,:,:,:)
+      CHARACTER(len=1) , INTENT(in   ) ::   NAT_IN(:)
+      INTEGER :: ji
+      DO ji = 1, K_SIZE(ptab)
+         IF( NAT_IN(jf) == 'T' )   ARRAY_IN(1,2,ji,:,jf) = -ARRAY_IN(2, 2 ,ji,:,jf)
+      END DO
+   END SUBROUTINE ROUTINE_X
+#undef ARRAY_IN
+"""
+    txt = f90exec.cpp(src, defined=("DIM_3d",), macros={"ROUTINE_X": "flip_3d"})
+    assert "#" not in txt and "ptab(1,2,ji) = -ptab(2,2,ji)" in txt and "REAL(wp),INTENT(inout)::ptab(:,:,:)" in txt
+    ns = {}
+    f90exec.load(txt, ns)
+    a = np.arange(24, dtype=np.float64).reshape(2, 3, 4)
+    want = a.copy(); want[0, 1, :] = -a[1, 1, :]
+    ns["flip_3d"](a, "T")
+    assert np.array_equal(a, want)
+
+
+# ---- against the reference tree ------------------------------------------------------------------------------------------------------
+@needs_reference
+@pytest.mark.parametrize("jperio", range(8))
+def test_reference_lbc_lnk_equals_the_oracle(jperio):
+    """lbc_lnk + lbc_nfd of the reference (no-MPI build, 3-D variant, from its text) vs the oracle's lbc_lnk on one domain, in both
+    of the oracle's builds (mpp_lnk with jpni = jpnj = 1, and the key_mpp_mpi-less lbc_lnk): every nature, both signs, even and odd
+    jpiglo"""
+    rng = np.random.default_rng(jperio)
+    for G, GJ, K in ((18, 13, 3), (19, 12, 2)):
+        lbc = R.reference_lbc(jperio, G, GJ)
+        for mpi in (True, False):
+            w = O.World(G, GJ, K, jperio, 1, 1, key_mpp_mpi=mpi)
+            for nat in "TUVWF":
+                for sgn in (1.0, -1.0):
+                    a = rng.standard_normal((K, GJ, G))
+                    b = a.copy()
+                    w.lbc_lnk([[a]], nat, [sgn])
+                    lbc([(b, nat, sgn)])
+                    assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (G, mpi, nat, sgn)
+            w.close()
+
+
+@needs_reference
+def test_the_reference_files_hold_no_kindless_inexact_literals():
+    """under -fdefault-real-8 (arch-linux_gfortran.fcm:48) such literals are doubles anyway; none exists in the routines executed,
+    so the results do not depend on that flag"""
+    for rel in ("traadv_fct.F90", "traadv_mus.F90", "traadv_cen.F90", "tranxt.F90"):
+        assert f90exec.literal_report(R._read("src", "OCE", "TRA", rel)) == [], rel
+    arch = R._read("arch", "arch-linux_gfortran.fcm")
+    assert "-Dkey_nosignedzero" in arch and "-fdefault-real-8" in arch and "-ffast-math" not in arch
+
+
+@needs_reference
+def test_pins_are_reproduced_from_the_reference_tree():
+    import make_ref_exec_pins as M
+    for name in sorted(GC.CASES):
+        out, gf, extra = M.run_reference(name, undef=0.0 if name in M.UNDEFINED_READS else np.nan)
+        pin = PINS["cases"][name]
+        assert GC.input_hash(gf, extra) == pin["input_sha256"], name
+        assert {k: GC.digest(v) for k, v in out.items()} == pin["outputs"], name
+        for f, sha in pin["reference_files"].items():
+            assert M.file_sha(f) == sha, (name, f, "the reference file changed since the pins were made")
+
+
+def _lbc(jperio, jpi, jpj):
+    return R.reference_lbc(jperio, jpi, jpj)          # the reference's own lbc_lnk + lbc_nfd text
+
+
+@needs_reference
+@pytest.mark.parametrize("jperio", [0, 1, 4, 6])
+@pytest.mark.parametrize("h,v", [(2, 2), (4, 4), (4, 2), (2, 4)])
+def test_reference_tra_adv_fct_equals_the_oracle(jperio, h, v):
+    G, GJ, K, kjpt = 19, 15, 8, 3
+    for lin, isf in ((False, False), (True, False), (True, True), (False, True)):
+        gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=400 + 10 * jperio + h + v, ln_linssh=lin, ln_isfcav=isf)
+        ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v, ln_linssh=lin, ln_isfcav=isf)
+        got = R.tra_adv_fct(gf, G, GJ, K, kjpt, h, v, lin, isf, _lbc(jperio, G, GJ), cdtype="TRC" if isf else "TRA")
+        assert np.isfinite(got).all()                                 # NaN-poisoned work arrays: no undefined value reaches pta
+        assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), (jperio, h, v, lin, isf)
+        assert not np.array_equal(got, gf["pta"])
+
+
+@needs_reference
+def test_sign_of_zero_is_the_only_trace_of_the_ieee_sign_intrinsic():
+    """Without key_nosignedzero the intrinsic SIGN(0.5, -0.0) is -0.5: the limiter then picks the other beta for fluxes that are
+    exactly -0.0, which changes nothing but the sign of zeros (on land and where every flux vanishes)."""
+    G, GJ, K, jperio = 24, 18, 7, 0
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=77)
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, 2, 2, 2)
+    ieee = R.tra_adv_fct(gf, G, GJ, K, 2, 2, 2, False, False, _lbc(jperio, G, GJ), sign_mode="ieee")
+    nosz = R.tra_adv_fct(gf, G, GJ, K, 2, 2, 2, False, False, _lbc(jperio, G, GJ))
+    assert np.array_equal(nosz.view(np.uint64), ref.view(np.uint64))
+    assert np.array_equal(ieee, ref)                                  # every VALUE is the same ...
+    differ = ieee.view(np.uint64) != ref.view(np.uint64)
+    assert differ.any() and (ref[differ] == 0.0).all()                # ... some zeros carry the other sign
+
+
+@needs_reference
+@pytest.mark.parametrize("jperio", [0, 4])
+def test_reference_tra_adv_driver_equals_transports_plus_fct_of_the_oracle(jperio):
+    G, GJ, K = 22, 17, 7
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=12)
+    rng = np.random.default_rng(5)
+    vel = dict(e2u=1e5 * (1 + 0.05 * rng.random((GJ, G))), e1v=1e5 * (1 + 0.05 * rng.random((GJ, G))),
+               e3u_n=gf["e3t_n"] * (1 + 0.01 * rng.random((K, GJ, G))), e3v_n=gf["e3t_n"] * (1 + 0.01 * rng.random((K, GJ, G))),
+               un=0.3 * 1e5 / 7200 * rng.uniform(-1, 1, (K, GJ, G)) * gf["umask"], vn=0.3 * 1e5 / 7200 * rng.uniform(-1, 1, (K, GJ, G)) * gf["vmask"],
+               wn=1e-4 * rng.uniform(-1, 1, (K, GJ, G)) * gf["wmask"])
+    w = O.World(G, GJ, K, jperio)
+    w.lbc_lnk([[vel["un"]], [vel["vn"]], [vel["wn"]]], "UVW", [-1.0, -1.0, 1.0])
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS])
+    zu, zv, zw = (np.zeros((K, GJ, G)) for _ in range(3))
+    O.lib().tra_adv_transports(d.h, *[vel[k].ctypes.data for k in ("e2u", "e1v", "e3u_n", "e3v_n", "un", "vn", "wn")],
+                               zu.ctypes.data, zv.ctypes.data, zw.ctypes.data)
+    for kt, neuler, want in ((11, 0, 3600.0), (12, 0, 7200.0), (11, 1, 7200.0)):     # r2dt rule of traadv.F90:88-90
+        g2 = dict(gf, pun=zu, pvn=zv, pwn=zw, p2dt=want)
+        ref, _, _ = H.oracle_fct(O, g2, G, GJ, K, jperio, 1, 1, 2, 4, 4)
+        tsa, r2dt = R.tra_adv(gf, vel, G, GJ, K, kt, 11, neuler, 3600.0, 4, 4, False, False, _lbc(jperio, G, GJ))
+        assert r2dt == want
+        assert np.array_equal(tsa.view(np.uint64), ref.view(np.uint64)), (kt, neuler)
+    w.close()
+
+
+@needs_reference
+@pytest.mark.parametrize("jperio,ups,lin,isf", [(0, False, False, False), (1, True, True, False), (4, True, False, False), (6, False, True, True)])
+def test_reference_tra_adv_mus_equals_the_oracle(jperio, ups, lin, isf):
+    G, GJ, K, kjpt = 21, 16, 7, 2
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=500 + jperio, ln_linssh=lin, ln_isfcav=isf)
+    mx = H.mus_extra_fields(O, gf, G, GJ, K, jperio, seed=500 + jperio, runoff=True)
+    ref, _ = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, 1, 1, kjpt, ln_linssh=lin, ln_isfcav=isf, ld_msc_ups=ups)
+    got = R.tra_adv_mus(gf, mx, G, GJ, K, kjpt, lin, isf, ups, _lbc(jperio, G, GJ))
+    assert np.isfinite(got).all()
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
+@needs_reference
+@pytest.mark.parametrize("jperio,h,v", [(0, 2, 2), (4, 2, 4), (6, 2, 2), (1, 2, 4)])
+def test_reference_tra_adv_cen_equals_the_oracle(jperio, h, v):
+    G, GJ, K, kjpt = 21, 16, 7, 2
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=600 + jperio)
+    ref, _ = H.oracle_cen(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v)
+    got = R.tra_adv_cen(gf, G, GJ, K, kjpt, h, v, False, False, _lbc(jperio, G, GJ))
+    assert np.isfinite(got).all()
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
+@needs_reference
+def test_reference_tra_adv_cen_4th_order_reads_an_undefined_row():
+    """tra_adv_cen, nn_cen_h = 4: the flux loop runs jj = 2, jpjm1 (traadv_cen.F90:127-140) but the divergence reads zwy(ji,jj-1,jk)
+    at jj = 2 (:181-190): zwy(:,1,:) is never defined.  With NaN in undefined memory exactly the second row is NaN; with zeros
+    there (what the oracle's work arrays hold) the result is the oracle's, bit for bit.  Not on the FCT path."""
+    G, GJ, K, kjpt, jperio = 21, 16, 7, 2, 0
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=601)
+    ref, _ = H.oracle_cen(O, gf, G, GJ, K, jperio, 1, 1, kjpt, 4, 2)
+    poisoned = R.tra_adv_cen(gf, G, GJ, K, kjpt, 4, 2, False, False, _lbc(jperio, G, GJ))
+    zeroed = R.tra_adv_cen(gf, G, GJ, K, kjpt, 4, 2, False, False, _lbc(jperio, G, GJ), undef=0.0)
+    bad = np.isnan(poisoned)
+    assert bad.any() and np.unique(np.argwhere(bad)[:, 2]).tolist() == [1]        # local row jj = 2 only
+    assert np.array_equal(zeroed.view(np.uint64), ref.view(np.uint64))
+    assert np.array_equal(poisoned[~bad].view(np.uint64), ref[~bad].view(np.uint64))
+
+
+@needs_reference
+@pytest.mark.parametrize("jperio,lin,kt,neuler", [(1, True, 5, 1), (4, False, 5, 1), (6, False, 1, 0), (0, True, 1, 0)])
+def test_reference_tra_nxt_equals_the_oracle(jperio, lin, kt, neuler):
+    """the whole tra_nxt driver: lbc_lnk on tsa, Euler swap at nit000 (neuler = 0) or tra_nxt_fix / tra_nxt_vvl + lbc_lnk on all three"""
+    G, GJ, K = GC.G // 2, GC.GJ // 2, GC.K
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=700 + jperio, ln_linssh=lin)
+    rng = np.random.default_rng(3)
+    w = O.World(G, GJ, K, jperio)
+    f2 = {k: rng.standard_normal((1, GJ, G)) * 1e-4 for k in ("emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf")}
+    w.lbc_lnk([[a] for a in f2.values()], "T" * 6, [1.0] * 6)
+    sbc, sbc_b = rng.standard_normal((2, GJ, G)) * 1e-5, rng.standard_normal((2, GJ, G)) * 1e-5
+    w.lbc_lnk([[sbc], [sbc_b]], "TT", [1.0, 1.0])
+    extra = {k: np.ascontiguousarray(v[0]) for k, v in f2.items()}
+    extra["sbc"], extra["sbc_b"] = sbc, sbc_b
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS], ln_linssh=lin)
+    tb, tn, ta = gf["ptb"].copy(), gf["ptn"].copy(), gf["pta"].copy()
+    forc = O.NxtForcing(atfp=0.1, r1_rau0=1.0 / 1026.0, **{k: extra[k] for k in f2})
+    w.tra_nxt(kt, 1, neuler == 0 and kt == 1, 900.0, "TRA", [forc], [tb], [tn], [ta], 2, [sbc], [sbc_b])
+    got = R.tra_nxt(gf, extra, G, GJ, K, kt, 1, neuler, 900.0, 0.1, 1.0 / 1026.0, lin, _lbc(jperio, G, GJ))
+    w.close()
+    for a, b, nm in zip(got, (tb, tn, ta), ("tsb", "tsn", "tsa")):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), nm
