@@ -31,7 +31,7 @@ import numpy as np
 
 INTRINSICS = {"max": "f_max", "min": "f_min", "abs": "f_abs", "sign": "f_sign", "real": "f_real", "mod": "f_mod", "int": "f_int",
               "nint": "f_nint", "sqrt": "f_sqrt", "sum": "f_sum", "maxval": "f_maxval", "minval": "f_minval", "present": "f_present",
-              "trim": "f_trim", "size": "f_size"}
+              "trim": "f_trim", "size": "f_size", "cmplx": "f_cmplx", "aimag": "f_aimag"}
 
 
 # ---- run-time support (the namespace translated code runs in) ---------------------------------------------------------------
@@ -66,6 +66,8 @@ def f_sign(a, b):
 
 
 def f_real(a, kind=None):
+    if isinstance(a, complex):
+        return a.real                                     # REAL( z ): the first component of the (sum, error) pair of DDPDD
     return a.astype(np.float64) if isinstance(a, np.ndarray) else float(a)
 
 
@@ -97,10 +99,11 @@ def f_alloc(shape, integer=False):
     return np.zeros(shape, dtype=np.int32, order="F") if integer else np.full(shape, np.nan, order="F")
 
 
-RUNTIME = dict(f_max=f_max, f_min=f_min, f_abs=f_abs, f_sign=f_sign, f_real=f_real, f_mod=f_mod, f_int=f_int, f_nint=f_nint,
+RUNTIME = dict(wp=8, f_max=f_max, f_min=f_min, f_abs=f_abs, f_sign=f_sign, f_real=f_real, f_mod=f_mod, f_int=f_int, f_nint=f_nint,
                f_sqrt=math.sqrt, f_sum=np.sum, f_maxval=np.max, f_minval=np.min, f_div=f_div, f_alloc=f_alloc, np=np,
                f_trim=lambda s: s.rstrip(), f_present=lambda a: a is not None,
-               f_size=lambda a, dim=None: a.size if dim is None else a.shape[dim - 1])
+               f_size=lambda a, dim=None: a.size if dim is None else a.shape[dim - 1],
+               f_cmplx=lambda re_, im=0.0, kind=None: complex(float(re_), float(im)), f_aimag=lambda z: z.imag)
 
 
 # ---- source preparation --------------------------------------------------------------------------------------------------------
@@ -484,6 +487,7 @@ class Translator:
                 ent, init = [x.strip() for x in ent.split("=", 1)]
             m = re.match(r"([a-z_]\w*)\s*(\(.*\))?$", ent)
             name, own = m.group(1), m.group(2)
+            self.local_names.add(name)
             if optional:
                 self.optional.add(name)
             shape = own or (dim[dim.index("("):] if dim else None)
@@ -495,6 +499,11 @@ class Translator:
             elif init is not None:
                 body.append("%s%s = %s" % (ind, name, self.expr(init, arrays)))
 
+    def outs(self, arrays):
+        """what a translated SUBROUTINE returns: its scalar dummy arguments by name (INTENT(out) scalars cannot be passed back
+        through Python arguments; arrays are modified in place)"""
+        return "{%s}" % ", ".join("'%s': %s, %d: %s" % (d, d, i, d) for i, d in enumerate(self.dummies) if d not in arrays)
+
     # -- one subroutine --
     def subroutine(self, sts):
         head = re.match(r"(subroutine|function)\s+(\w+)\s*(?:\((.*)\))?\s*$", sts[0])
@@ -502,6 +511,8 @@ class Translator:
         name, dummies = head.group(2), [a.strip() for a in (head.group(3) or "").split(",") if a.strip()]
         arrays = set(self.global_arrays)
         self.optional = set()
+        self.dummies = dummies
+        self.local_names = set(dummies)
         body, depth, sel = [], 1, []
         ind = lambda: "    " * depth                      # noqa: E731
         mod = sorted(self.module_names - set(dummies))
@@ -510,7 +521,7 @@ class Translator:
         for st in sts[1:]:
             if re.match(r"end\s*(subroutine|function)", st):
                 break
-            if re.match(r"(integer|real|logical|character|type\s*\()", st) and "::" in st:
+            if re.match(r"(integer|real|logical|character|complex|type\s*\()", st) and "::" in st:
                 self.declaration(st, dummies, arrays, body, ind())
                 continue
             if re.match(r"(use |implicit |intent|external )", st):
@@ -518,6 +529,8 @@ class Translator:
             depth = self.statement(st, arrays, body, depth, sel)
         if is_function:
             body.append("    return " + name)                          # the result variable carries the function's name
+        else:
+            body.append("    return " + self.outs(arrays))
         src = "def %s(%s):\n" % (name, ", ".join(d + "=None" if d in self.optional else d for d in dummies)) + \
             ("\n".join(body) if body else "    pass") + "\n"
         if is_function:                                                # ... and must not shadow the function inside its own body
@@ -594,7 +607,14 @@ class Translator:
                 a = a.strip()
                 km = re.match(r"(\w+)\s*=\s*(?!=)(.*)$", a)
                 conv.append("%s=%s" % (km.group(1), self.expr(km.group(2), arrays)) if km else self.expr(a, arrays))
-            body.append("%s%s(%s)" % (ind, m.group(1), ", ".join(conv)))
+            body.append("%s_r = %s(%s)" % (ind, m.group(1), ", ".join(conv)))
+            # scalar INTENT(out / inout) dummies come back by position (see outs): copy them into the caller's own scalars
+            back = [(i, a.strip()) for i, a in enumerate(args) if re.fullmatch(r"[a-z_]\w*", a.strip()) and a.strip() not in arrays
+                    and (a.strip() in self.local_names or a.strip() in self.module_names)]
+            if back:
+                body.append("%sif isinstance(_r, dict):" % ind)
+                for i, a in back:
+                    body.append("%s    %s = _r.get(%d, %s)" % (ind, a, i, a))
             return depth
         m = re.match(r"allocate\s*\((.*)\)$", st)
         if m:
@@ -609,7 +629,7 @@ class Translator:
             body.append(ind + "pass")
             return depth
         if st == "return":
-            body.append(ind + "return")
+            body.append(ind + "return " + self.outs(arrays))
             return depth
         # assignment
         parts = self._split_assignment(st)

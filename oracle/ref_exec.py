@@ -180,3 +180,50 @@ def tra_adv(gf, vel, jpi, jpj, jpk, kt, nit000, neuler, rdt, nn_fct_h, nn_fct_v,
     ns["nadv"] = ns["np_fct"]
     ns["tra_adv"](kt)
     return ts["tsa"], ns["r2dt"]
+
+
+def trc_adv(gf, vel, trb, trn, tra, jpi, jpj, jpk, kt, nittrc000, r2dttrc, nn_fct_h, nn_fct_v, ln_linssh, ln_isfcav, lbc):
+    """the reference's trc_adv driver (src/TOP/TRP/trcadv.F90:70-145) on the FCT branch: effective transports (:88-101), then ITS call
+    tra_adv_fct( kt, nittrc000, 'TRC', r2dttrc, zun, zvn, zwn, trb, trn, tra, jptra, nn_fct_h, nn_fct_v ) (:127).  trb, trn, tra:
+    C-ordered [jptra][jpk][jpj][jpi]; returns the new tra."""
+    dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, ln_isfcav, lbc)
+    ns = dom.ns
+    out = np.array(tra, copy=True)
+    ns.update(trb=F(np.ascontiguousarray(trb)), trn=F(np.ascontiguousarray(trn)), tra=F(out), jptra=out.shape[0])
+    for k in ("e2u", "e1v", "e3u_n", "e3v_n", "un", "vn", "wn"):
+        ns[k] = F(np.ascontiguousarray(vel[k]))
+    ns.update(nittrc000=nittrc000, r2dttrc=float(r2dttrc), ln_timing=False, l_offline=False, ln_wave=False, ln_sdw=False, ln_vvl_ztilde=False,
+              ln_vvl_layer=False, ln_ldfeiv=False, ln_traldf_triad=False, ln_mle=False, ln_ctl=False, nn_fct_h=nn_fct_h, nn_fct_v=nn_fct_v)
+    dom.load("src", "OCE", "TRA", "traadv_fct.F90", only=("tra_adv_fct", "nonosc", "interp_4th_cpt"))
+    text = _read("src", "TOP", "TRP", "trcadv.F90")
+    f90exec.module_parameters(text, ns, dom.defines, defined=("key_top",))        # np_CEN, np_FCT, ... (trcadv.F90:52-57)
+    f90exec.load(text, ns, arrays=DOM_ARRAYS + ("trb", "trn", "tra", "e2u", "e1v", "e3u_n", "e3v_n", "un", "vn", "wn"), int_arrays=DOM_INT_ARRAYS,
+                 defines=dom.defines, only=("trc_adv",), defined=("key_top",))
+    ns["nadv"] = ns["np_fct"]
+    ns["trc_adv"](kt)
+    return out
+
+
+def mpp_basic_decomposition(jpiglo, jpjglo, jperio, knbi, knbj):
+    """the reference's mpp_basic_decomposition (src/OCE/LBC/mppini.F90:695-798, nn_hls = 1) from its text:
+    (kimax, kjmax, kimppt, kjmppt, klci, klcj), tables shaped (knbj, knbi) like the product's; raises if the reference calls ctl_stop"""
+    def stop(*a):
+        raise ValueError("ctl_stop: " + " ".join(str(x) for x in a))
+    ns = dict(jpiglo=jpiglo, jpjglo=jpjglo, jperio=jperio, nn_hls=1, ctmp1="", ctmp2="", ctl_stop=stop)
+    f90exec.load(_read("src", "OCE", "LBC", "mppini.F90"), ns, only=("mpp_basic_decomposition",), defined=("key_mpp_mpi",))
+    tabs = [np.zeros((knbi, knbj), np.int32, order="F") for _ in range(4)]
+    out = ns["mpp_basic_decomposition"](knbi, knbj, 0, 0, *tabs)
+    return (out["kimax"], out["kjmax"]) + tuple(np.ascontiguousarray(t.T) for t in tabs)
+
+
+def glob_sum_3d(ptab, tmask_i):
+    """the reference's glob_sum for a 3-D field on ONE domain, from its text: lib_fortran_generic.h90:30-65 (GLOBSUM_CODE, DIM_3d,
+    OPERATION_GLOBSUM => masked by tmask_i) accumulating with DDPDD (lib_fortran.F90:300-332; the (sum, error) pair is a COMPLEX);
+    mpp_sum is the identity on one rank.  ptab: C-ordered [jpk][jpj][jpi]; returns (REAL(ctmp), AIMAG(ctmp) is not returned by the
+    reference) -- here the fp64 result only."""
+    ns = dict(tmask_i=F(np.ascontiguousarray(tmask_i)), mpp_sum=lambda cdname, c: None)
+    f90exec.load(_read("src", "OCE", "lib_fortran.F90"), ns, only=("ddpdd",))
+    gen = f90exec.cpp(_read("src", "OCE", "lib_fortran_generic.h90"), defined=("GLOBSUM_CODE", "DIM_3d", "OPERATION_GLOBSUM"),
+                      macros={"FUNCTION_GLOBSUM": "glob_sum_3d"})
+    f90exec.load(gen, ns, arrays=("tmask_i",), only=("glob_sum_3d",))
+    return ns["glob_sum_3d"]("ref_exec", F(np.ascontiguousarray(ptab)))

@@ -299,6 +299,81 @@ def test_reference_tra_adv_driver_equals_transports_plus_fct_of_the_oracle(jperi
 
 
 @needs_reference
+def test_reference_mpp_basic_decomposition_equals_oracle_and_product(N):
+    """the decomposition of the PRODUCT (host code of libnemo_fct.so, csrc/layout.cpp) and of the oracle against the reference's
+    mpp_basic_decomposition text: sizes, first global indices, the shrunk last row of subdomains under a north fold"""
+    import ctypes as C
+    L = O.lib()
+    for (gi, gj) in ((1442, 1207), (362, 332), (182, 149), (30, 24), (31, 23)):
+        for jperio in (0, 1, 4, 6, 7):
+            for (ni, nj) in ((1, 1), (2, 1), (2, 2), (4, 2), (3, 5), (8, 4), (7, 3)):
+                try:
+                    want = R.mpp_basic_decomposition(gi, gj, jperio, ni, nj)
+                except ValueError:
+                    with pytest.raises(N.NemoFctError):            # the reference stops (jpi < 3 or jpj too small): so must the product
+                        N.mpp_basic_decomposition(gi, gj, jperio, ni, nj)
+                    continue
+                got = N.mpp_basic_decomposition(gi, gj, jperio, ni, nj)
+                assert got[:2] == tuple(int(x) for x in want[:2]), (gi, gj, jperio, ni, nj)
+                for a, b in zip(got[2:], want[2:]):
+                    assert np.array_equal(a, b), (gi, gj, jperio, ni, nj)
+                ki, kj = C.c_int(), C.c_int()
+                tabs = [np.zeros(ni * nj, np.int32) for _ in range(4)]
+                L.mpp_basic_decomposition(gi, gj, jperio, ni, nj, C.byref(ki), C.byref(kj), *[t.ctypes.data_as(C.POINTER(C.c_int)) for t in tabs])
+                assert (ki.value, kj.value) == got[:2]
+                for a, b in zip(tabs, want[2:]):
+                    assert np.array_equal(a.reshape(nj, ni), b)
+
+
+@needs_reference
+@pytest.mark.parametrize("jperio", [0, 4, 6])
+def test_reference_glob_sum_and_ddpdd_equal_the_oracle(jperio):
+    """glob_sum (lib_fortran_generic.h90:30-65) accumulating with DDPDD (lib_fortran.F90:300-332), the conservation metric: the
+    reference's text on one domain == the oracle's double-double sum (which the device glob_sum is held to), on a field with heavy
+    cancellation where the plain fp64 sum goes wrong"""
+    G, GJ, K = 17, 12, 5
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=1, seed=3 + jperio)
+    rng = np.random.default_rng(1)
+    big = np.ascontiguousarray(gf["ptb"][0] * gf["e3t_n"] * (1 + 1e8 * rng.standard_normal((K, GJ, G))))
+    ti = np.ascontiguousarray(gf["tmask_i"])
+    w = O.World(G, GJ, K, jperio)
+    want = O.glob_sum(w, [big], [ti])[0]
+    w.close()
+    assert R.glob_sum_3d(big, ti) == want
+    naive = 0.0
+    for x in (big * ti[None]).ravel(order="C"):           # the same order, plain fp64: the compensation matters on this field
+        naive += x
+    assert naive != want
+
+
+@needs_reference
+def test_reference_trc_adv_with_many_passive_tracers_equals_the_oracle():
+    """trc_adv -> tra_adv_fct(..., 'TRC', r2dttrc, ..., jptra, ...) (trcadv.F90:127): the batched-tracer call of BASELINE config 5"""
+    G, GJ, K, jperio, jptra = 20, 15, 6, 4, 7
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=1, seed=31)
+    rng = np.random.default_rng(6)
+    vel = dict(e2u=1e5 * (1 + 0.05 * rng.random((GJ, G))), e1v=1e5 * (1 + 0.05 * rng.random((GJ, G))),
+               e3u_n=gf["e3t_n"] * (1 + 0.01 * rng.random((K, GJ, G))), e3v_n=gf["e3t_n"] * (1 + 0.01 * rng.random((K, GJ, G))),
+               un=0.3 * 1e5 / 7200 * rng.uniform(-1, 1, (K, GJ, G)) * gf["umask"], vn=0.3 * 1e5 / 7200 * rng.uniform(-1, 1, (K, GJ, G)) * gf["vmask"],
+               wn=1e-4 * rng.uniform(-1, 1, (K, GJ, G)) * gf["wmask"])
+    w = O.World(G, GJ, K, jperio)
+    w.lbc_lnk([[vel["un"]], [vel["vn"]], [vel["wn"]]], "UVW", [-1.0, -1.0, 1.0])
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS])
+    zu, zv, zw = (np.zeros((K, GJ, G)) for _ in range(3))
+    O.lib().tra_adv_transports(d.h, *[vel[k].ctypes.data for k in ("e2u", "e1v", "e3u_n", "e3v_n", "un", "vn", "wn")],
+                               zu.ctypes.data, zv.ctypes.data, zw.ctypes.data)
+    w.close()
+    trb = np.ascontiguousarray(np.stack([gf["ptb"][0] * (1 + 0.1 * n) for n in range(jptra)]))
+    trn = np.ascontiguousarray(np.stack([gf["ptn"][0] * (1 + 0.1 * n) for n in range(jptra)]))
+    tra = np.ascontiguousarray(np.stack([gf["pta"][0] * (1 + 0.2 * n) for n in range(jptra)]))
+    g2 = dict(gf, pun=zu, pvn=zv, pwn=zw, p2dt=7200.0, ptb=trb, ptn=trn, pta=tra)
+    ref, _, _ = H.oracle_fct(O, g2, G, GJ, K, jperio, 1, 1, jptra, 2, 2)
+    got = R.trc_adv(gf, vel, trb, trn, tra, G, GJ, K, 3, 1, 7200.0, 2, 2, False, False, _lbc(jperio, G, GJ))
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
+@needs_reference
 @pytest.mark.parametrize("jperio,ups,lin,isf", [(0, False, False, False), (1, True, True, False), (4, True, False, False), (6, False, True, True)])
 def test_reference_tra_adv_mus_equals_the_oracle(jperio, ups, lin, isf):
     G, GJ, K, kjpt = 21, 16, 7, 2
