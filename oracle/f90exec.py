@@ -94,12 +94,19 @@ def f_div(a, b):
         return np.float64(a) / np.float64(b)
 
 
+def f_ref(a, idx):
+    """the storage of the Fortran-ordered array `a` from element `idx` (0-based) on, as a flat view: what a routine receives
+    when it is handed an array element as the start of a buffer"""
+    assert a.flags["F_CONTIGUOUS"]
+    return a.reshape(-1, order="F")[int(np.ravel_multi_index(tuple(int(i) for i in idx), a.shape, order="F")):]
+
+
 def f_alloc(shape, integer=False):
     shape = tuple(int(n) for n in shape)
     return np.zeros(shape, dtype=np.int32, order="F") if integer else np.full(shape, np.nan, order="F")
 
 
-RUNTIME = dict(wp=8, f_max=f_max, f_min=f_min, f_abs=f_abs, f_sign=f_sign, f_real=f_real, f_mod=f_mod, f_int=f_int, f_nint=f_nint,
+RUNTIME = dict(wp=8, f_ref=f_ref, f_max=f_max, f_min=f_min, f_abs=f_abs, f_sign=f_sign, f_real=f_real, f_mod=f_mod, f_int=f_int, f_nint=f_nint,
                f_sqrt=math.sqrt, f_sum=np.sum, f_maxval=np.max, f_minval=np.min, f_div=f_div, f_alloc=f_alloc, np=np,
                f_trim=lambda s: s.rstrip(), f_present=lambda a: a is not None,
                f_size=lambda a, dim=None: a.size if dim is None else a.shape[dim - 1],
@@ -206,8 +213,8 @@ def cpp(text, defined=(), macros=None):
     (nested), `#define NAME body`, `#define NAME(a,b) body`, `#undef`, and expansion of those macros in the code lines (repeated
     until nothing changes, as cpp rescans).  `defined`: keys defined from outside; `macros`: {name: body} object-like macros defined
     from outside (e.g. ROUTINE_NFD).  `#include` lines are dropped.  Returns the preprocessed text (no `#` lines left)."""
-    defined = set(defined)
     obj = dict(macros or {})
+    defined = set(defined) | set(obj)
     fun = {}
     out, take = [], [True]
 
@@ -241,7 +248,7 @@ def cpp(text, defined=(), macros=None):
             d = st[1:].strip()
             m = re.match(r"if\s*(!)?\s*defined\s*\(?\s*(\w+)\s*\)?\s*$", d) or re.match(r"if(n)?def\s+(\w+)\s*$", d)
             if m:
-                take.append(all(take) and ((m.group(2) in defined or m.group(2) in obj) != bool(m.group(1))))
+                take.append(all(take) and ((m.group(2) in defined) != bool(m.group(1))))
             elif d.startswith("if"):
                 raise SyntaxError("cpp condition not understood: " + raw)
             elif d.startswith("else"):
@@ -254,10 +261,8 @@ def cpp(text, defined=(), macros=None):
                     fun[m.group(1)] = ([a.strip() for a in m.group(2).split(",")], m.group(3).strip())
                 else:
                     m = re.match(r"define\s+(\w+)\s*(.*)$", d)
-                    if m.group(2).strip():
-                        obj[m.group(1)] = m.group(2).strip()
-                    else:
-                        defined.add(m.group(1))
+                    obj[m.group(1)] = m.group(2).strip()                 # an empty body (e.g. LBC_ARG) expands to nothing
+                    defined.add(m.group(1))
             elif all(take) and d.startswith("undef"):
                 nm = d.split()[1]
                 fun.pop(nm, None); obj.pop(nm, None); defined.discard(nm)
@@ -304,6 +309,10 @@ def literal_report(text):
 
 # ---- the translator ------------------------------------------------------------------------------------------------------------
 class Translator:
+    #: external routines that receive a message buffer by its FIRST ELEMENT (sequence association), e.g.
+    #: CALL mppsend( 2, zt3we(1,1,1,1,1,1), imigr, noea, ml_req1 ): the element is passed as a flat view of the array from there on
+    BYREF_CALLEES = {"mppsend": (1,), "mpprecv": (1,), "mpi_allgather": (0, 3)}        # name -> positions of the buffer arguments
+
     def __init__(self, arrays=(), int_arrays=()):
         self.global_arrays = set(a.lower() for a in arrays) | set(a.lower() for a in int_arrays)
         self.module_names = set()                         # variables declared at module level: `global` inside the routines
@@ -474,6 +483,7 @@ class Translator:
 
     # -- declarations --
     def declaration(self, st, dummies, arrays, body, ind):
+        is_result_of = lambda n: n == getattr(self, "function_name", None)      # noqa: E731
         left, right = st.split("::", 1)
         attrs = [a.strip() for a in _split_top(left, ",")]
         integer = attrs[0].startswith("integer")
@@ -488,6 +498,8 @@ class Translator:
             m = re.match(r"([a-z_]\w*)\s*(\(.*\))?$", ent)
             name, own = m.group(1), m.group(2)
             self.local_names.add(name)
+            if integer:
+                self.int_names.add(name)
             if optional:
                 self.optional.add(name)
             shape = own or (dim[dim.index("("):] if dim else None)
@@ -498,6 +510,12 @@ class Translator:
                     body.append("%s%s = f_alloc((%s,), %s)" % (ind, name, ", ".join(dims), integer))
             elif init is not None:
                 body.append("%s%s = %s" % (ind, name, self.expr(init, arrays)))
+            elif name not in dummies and name not in self.module_names and not is_result_of(name):
+                # an undefined local scalar: it may legally be handed to a routine that sets it (e.g. an MPI request handle)
+                kind = attrs[0]
+                body.append("%s%s = %s" % (ind, name, "0" if kind.startswith("integer") else "False" if kind.startswith("logical")
+                                           else "''" if kind.startswith("character") else "complex(float('nan'), float('nan'))"
+                                           if kind.startswith("complex") else "float('nan')"))
 
     def outs(self, arrays):
         """what a translated SUBROUTINE returns: its scalar dummy arguments by name (INTENT(out) scalars cannot be passed back
@@ -508,11 +526,13 @@ class Translator:
     def subroutine(self, sts):
         head = re.match(r"(subroutine|function)\s+(\w+)\s*(?:\((.*)\))?\s*$", sts[0])
         is_function = head.group(1) == "function"
+        self.function_name = head.group(2) if is_function else None
         name, dummies = head.group(2), [a.strip() for a in (head.group(3) or "").split(",") if a.strip()]
         arrays = set(self.global_arrays)
         self.optional = set()
         self.dummies = dummies
         self.local_names = set(dummies)
+        self.int_names = set()
         body, depth, sel = [], 1, []
         ind = lambda: "    " * depth                      # noqa: E731
         mod = sorted(self.module_names - set(dummies))
@@ -603,9 +623,14 @@ class Translator:
         if m:
             args = _split_top(m.group(2)[1:-1], ",") if m.group(2) else []
             conv = []
-            for a in args:
+            for pos, a in enumerate(args):
                 a = a.strip()
                 km = re.match(r"(\w+)\s*=\s*(?!=)(.*)$", a)
+                em = re.fullmatch(r"([a-z_]\w*)\s*\((.*)\)", a)
+                if pos in self.BYREF_CALLEES.get(m.group(1), ()) and em and em.group(1) in arrays and ":" not in em.group(2):
+                    idx = ", ".join("(%s)-1" % self.expr(x, arrays) for x in _split_top(em.group(2), ","))
+                    conv.append("f_ref(%s, (%s,))" % (em.group(1), idx))
+                    continue
                 conv.append("%s=%s" % (km.group(1), self.expr(km.group(2), arrays)) if km else self.expr(a, arrays))
             body.append("%s_r = %s(%s)" % (ind, m.group(1), ", ".join(conv)))
             # scalar INTENT(out / inout) dummies come back by position (see outs): copy them into the caller's own scalars
@@ -623,13 +648,16 @@ class Translator:
                 if em:
                     arrays.add(em.group(1))
                     dims = [self.expr(d, arrays) for d in _split_top(em.group(2), ",")]
-                    body.append("%s%s = f_alloc((%s,))" % (ind, em.group(1), ", ".join(dims)))
+                    body.append("%s%s = f_alloc((%s,), %s)" % (ind, em.group(1), ", ".join(dims), em.group(1) in self.int_names))
             return depth
         if re.match(r"(deallocate|write|print|format)\b", st) or st == "continue":
             body.append(ind + "pass")
             return depth
         if st == "return":
             body.append(ind + "return " + self.outs(arrays))
+            return depth
+        if st == "stop" or st.startswith("stop "):
+            body.append(ind + "raise RuntimeError('STOP')")
             return depth
         # assignment
         parts = self._split_assignment(st)

@@ -227,3 +227,137 @@ def glob_sum_3d(ptab, tmask_i):
                       macros={"FUNCTION_GLOBSUM": "glob_sum_3d"})
     f90exec.load(gen, ns, arrays=("tmask_i",), only=("glob_sum_3d",))
     return ns["glob_sum_3d"]("ref_exec", F(np.ascontiguousarray(ptab)))
+
+
+def decomposition_tables(jpiglo, jpjglo, jperio, jpni, jpnj):
+    """the per-rank tables mpp_init derives from mpp_basic_decomposition for an all-ocean layout (mppini.F90:255-300: rank r holds
+    subdomain (ii, ij) with r = (ij-1)*jpni + ii - 1), built from the REFERENCE's mpp_basic_decomposition text: dict of Fortran-
+    shaped arrays nimppt, njmppt, nlcit, nlcjt (jpnij) and nfiimpp, nfilcit, nfipproc (jpni, jpnj)"""
+    kimax, kjmax, kimppt, kjmppt, klci, klcj = mpp_basic_decomposition(jpiglo, jpjglo, jperio, jpni, jpnj)
+    t = dict(jpimax=int(kimax), jpjmax=int(kjmax))
+    for name, tab in (("nimppt", kimppt), ("njmppt", kjmppt), ("nlcit", klci), ("nlcjt", klcj)):
+        t[name] = np.ascontiguousarray(tab.reshape(-1), dtype=np.int32)            # (knbj, knbi) C order == rank order
+    t["nfiimpp"] = np.asfortranarray(kimppt.T.astype(np.int32))
+    t["nfilcit"] = np.asfortranarray(klci.T.astype(np.int32))
+    t["nfipproc"] = np.asfortranarray(np.arange(jpni * jpnj, dtype=np.int32).reshape(jpnj, jpni).T)
+    return t
+
+
+def mpp_init_nfdcom(jpiglo, jpjglo, jperio, jpni, jpnj, narea, nlci, nldi, nlei):
+    """the reference's mpp_init_nfdcom (src/OCE/LBC/mppini.F90:1180-1240) for rank `narea` (1-based) from its text: the no-gather
+    fold partners (nsndto, isendto) and nfsloop / nfeloop"""
+    t = decomposition_tables(jpiglo, jpjglo, jperio, jpni, jpnj)
+    ns = dict(t, jpiglo=jpiglo, jpni=jpni, jpnj=jpnj, narea=narea, njmpp=int(t["njmppt"][narea - 1]), nlci=nlci, nldi=nldi, nlei=nlei,
+              isendto=np.zeros(3, np.int32), nsndto=0, nfsloop=0, nfeloop=0, l_north_nogather=False)
+    f90exec.load(_read("src", "OCE", "LBC", "mppini.F90"), ns, arrays=("nimppt", "njmppt", "nlcit", "nfiimpp", "nfilcit", "nfipproc", "isendto"),
+                 only=("mpp_init_nfdcom",), defined=("key_mpp_mpi",), module_vars=("nsndto", "nfsloop", "nfeloop", "l_north_nogather"))
+    ns["mpp_init_nfdcom"]()
+    return ns["nsndto"], [int(x) for x in ns["isendto"][:ns["nsndto"]]], ns["nfsloop"], ns["nfeloop"]
+
+
+# ---- the multi-rank exchange: mpp_lnk / mpp_nfd of the reference, one thread per MPI rank --------------------------------------------
+import queue
+import threading
+
+
+class _Mpi:
+    """two-sided messages between rank threads: a FIFO per (source, destination, tag); MPI_ALLGATHER over the northern ranks"""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.box = {}
+        self.gather = {}
+
+    def _q(self, key):
+        with self.lock:
+            return self.box.setdefault(key, queue.Queue())
+
+    def send(self, src, dst, tag, data):
+        self._q((src, dst, tag)).put(np.array(data, copy=True))
+
+    def recv(self, src, dst, tag):
+        return self._q((src, dst, tag)).get(timeout=10)
+
+
+class MppWorld:
+    """jpni x jpnj ranks running the REFERENCE's mpp_lnk_3d (mpp_lnk_generic.h90) with its north fold (mpp_nfd_generic.h90 ->
+    lbc_nfd_generic.h90 on the gathered rows, or lbc_nfd_nogather_generic.h90), each in its own thread and namespace; mppsend / mpprecv /
+    MPI_ALLGATHER are emulated.  The decomposition scalars of every rank (what mpp_init leaves in dom_oce / lib_mpp) are taken from the
+    oracle's mpp_init (`doms`: sizes and fold partners are pinned to the reference separately, see mpp_basic_decomposition and
+    mpp_init_nfdcom above); nothing of the oracle's exchange code is involved."""
+
+    def __init__(self, doms, ln_nnogather):
+        self.doms, self.n = doms, len(doms)
+        d0 = doms[0]
+        self.mpi = _Mpi()
+        top = [r for r, d in enumerate(doms) if d.njmpp == max(x.njmpp for x in doms)]
+        tabs = dict(nimppt=np.array([d.nimpp for d in doms], np.int32), nlcit=np.array([d.nlci for d in doms], np.int32),
+                    nldit=np.array([d.nldi for d in doms], np.int32), nleit=np.array([d.nlei for d in doms], np.int32))
+        nfipproc = np.asfortranarray(np.arange(self.n, dtype=np.int32).reshape(d0.jpnj, d0.jpni).T)
+        nfiimpp = np.asfortranarray(tabs["nimppt"].reshape(d0.jpnj, d0.jpni).T)
+        lnk = f90exec.cpp(_read("src", "OCE", "LBC", "mpp_lnk_generic.h90"), defined=("DIM_3d",), macros={"ROUTINE_LNK": "mpp_lnk_3d"})
+        nfd = f90exec.cpp(_read("src", "OCE", "LBC", "mpp_nfd_generic.h90"), defined=("DIM_3d",), macros={"ROUTINE_NFD": "mpp_nfd_3d"})
+        fold = {nd: f90exec.cpp(_read("src", "OCE", "LBC", "lbc_nfd_generic.h90"), defined=("DIM_%dd" % nd,), macros={"ROUTINE_NFD": "lbc_nfd_%dd" % nd})
+                for nd in (3, 4)}
+        nog = f90exec.cpp(_read("src", "OCE", "LBC", "lbc_nfd_nogather_generic.h90"), defined=("DIM_3d",), macros={"ROUTINE_NFD": "lbc_nfd_nogather_3d"})
+        self.ns = []
+        for r, d in enumerate(doms):
+            ns = dict(jpi=d.jpi, jpj=d.jpj, jpim1=d.jpi - 1, jpjm1=d.jpj - 1, jpiglo=d.jpiglo, jpjglo=d.jpjglo, jpni=d.jpni, jpnj=d.jpnj,
+                      jpnij=d.jpnij, jpimax=d.jpimax, jpjmax=d.jpjmax, jperio=d.jperio, narea=d.narea, nproc=d.nproc, nimpp=d.nimpp,
+                      njmpp=d.njmpp, nlci=d.nlci, nlcj=d.nlcj, nldi=d.nldi, nlei=d.nlei, nldj=d.nldj, nlej=d.nlej, nbondi=d.nbondi,
+                      nbondj=d.nbondj, noea=d.noea, nowe=d.nowe, noso=d.noso, nono=d.nono, npolj=d.npolj, l_iperio=bool(d.l_Iperio),
+                      l_jperio=bool(d.l_Jperio), nsndto=d.nsndto, isendto=np.array(list(d.isendto) + [0, 0, 0], np.int32)[:3],
+                      nfsloop=d.nfsloop, nfeloop=d.nfeloop, nn_hls=1, nreci=2, nrecj=2, numcom=0, ln_timing=False, l_isend=False,
+                      jpmaxngh=3, mpi_status_size=1, mpi_double_precision=0, l_north_nogather=bool(ln_nnogather), ncom_stp=1, nit000=1,
+                      ln_rstart=False, l_full_nf_update=True, ndim_rank_north=len(top), nrank_north=np.array(top, np.int32), ncomm_north=0,
+                      nfipproc=nfipproc, nfiimpp=nfiimpp, **tabs)
+            me = r
+
+            def mppsend(ktyp, pmess, kbytes, kdest, md_req=None, me=me):
+                self.mpi.send(me, int(kdest), int(ktyp), np.asarray(pmess).reshape(-1, order="F")[:int(kbytes)])
+
+            def mpprecv(ktyp, pmess, kbytes, ksource, me=me):
+                data = self.mpi.recv(int(ksource), me, int(ktyp))
+                assert data.size == int(kbytes)
+                flat = pmess if pmess.ndim == 1 else pmess.reshape(-1, order="F")
+                assert np.shares_memory(flat, pmess)
+                flat[:int(kbytes)] = data
+
+            def mpi_allgather(sbuf, scount, stype, rbuf, rcount, rtype, comm, ierr, me=me, top=top):
+                for q in top:                                          # every northern rank sends its rows to every northern rank
+                    self.mpi.send(me, q, 99, np.asarray(sbuf).reshape(-1, order="F")[:int(scount)])
+                flat = rbuf.reshape(-1, order="F")
+                assert np.shares_memory(flat, rbuf)
+                for n, q in enumerate(top):
+                    flat[n * int(rcount):(n + 1) * int(rcount)] = self.mpi.recv(q, me, 99)
+
+            ns.update(mppsend=mppsend, mpprecv=mpprecv, mpi_allgather=mpi_allgather, mpi_wait=lambda *a: None, tic_tac=lambda *a: None,
+                      mpp_report=lambda *a, **k: None)
+            arrs = ("nimppt", "nlcit", "nldit", "nleit", "nfipproc", "nfiimpp", "isendto", "nrank_north")
+            for nd in (3, 4):
+                f90exec.load(fold[nd], ns, int_arrays=arrs)
+            f90exec.load(nog, ns, int_arrays=arrs)
+            f90exec.load(nfd, ns, int_arrays=arrs, module_vars=("l_full_nf_update",))
+            f90exec.load(lnk, ns, int_arrays=arrs)
+            ns["lbc_nfd"] = lambda ptab, nat, sgn, ns=ns: ns["lbc_nfd_%dd" % ptab.ndim](ptab, nat, sgn)      # INTERFACE lbc_nfd
+            ns["lbc_nfd_nogather"] = lambda ptab, ptab2, nat, sgn, ns=ns: ns["lbc_nfd_nogather_3d"](ptab, ptab2, nat, sgn)
+            ns["mpp_nfd"] = ns["mpp_nfd_3d"]
+            self.ns.append(ns)
+
+    def lbc_lnk(self, locs, nat, sgn):
+        """mpp_lnk_3d on every rank at once; locs: list over ranks of C-ordered [jpk][jpj][jpi] arrays, updated in place"""
+        err = []
+
+        def run(r):
+            try:
+                self.ns[r]["mpp_lnk_3d"]("ref_exec", np.transpose(locs[r]), nat, float(sgn))
+            except Exception as e:        # noqa: BLE001
+                import traceback
+                err.append((r, traceback.format_exc()))
+        th = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(self.n)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=25)
+        if err or any(t.is_alive() for t in th):
+            raise RuntimeError("mpp_lnk failed or hung: %s" % (err[:1] or "timeout"))

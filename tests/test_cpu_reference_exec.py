@@ -11,7 +11,8 @@ order and every arithmetic expression are the reference's, character for charact
     nonosc / interp_4th_cpt, tra_adv (driver + transports), tra_adv_mus, tra_adv_cen and tra_nxt run against the oracle on a
     matrix of boundary types, orders, ln_linssh / ln_isfcav -- bit for bit -- with the lateral boundary conditions ALSO taken from
     the reference's text (lbc_lnk_generic.h90 + lbc_nfd_generic.h90 through a small cpp: nothing of the oracle is in that loop),
-    and that lbc_lnk is compared with the oracle's for every boundary type, grid-point nature and sign;
+    and that lbc_lnk is compared with the oracle's for every boundary type, grid-point nature and sign; the MULTI-RANK exchange
+    (mpp_lnk + mpp_nfd, gather and no-gather fold) runs from the reference's text on emulated MPI ranks against the oracle's;
   * the translator itself is unit-tested on Fortran snippets written here.
 
 Two findings are pinned as tests: (1) SIGN -- the reference's gfortran arch file defines key_nosignedzero, under which SIGN is
@@ -296,6 +297,57 @@ def test_reference_tra_adv_driver_equals_transports_plus_fct_of_the_oracle(jperi
         assert r2dt == want
         assert np.array_equal(tsa.view(np.uint64), ref.view(np.uint64)), (kt, neuler)
     w.close()
+
+
+@needs_reference
+@pytest.mark.parametrize("jperio", [0, 1, 4, 6, 7])
+def test_reference_multi_rank_exchange_equals_the_oracle(jperio):
+    """mpp_lnk_3d (mpp_lnk_generic.h90) with its north fold -- mpp_nfd_generic.h90 through MPI_ALLGATHER + lbc_nfd (ln_nnogather = F)
+    AND through the point-to-point no-gather path + lbc_nfd_nogather_generic.h90 (the reference's default) -- executed from the
+    reference's text on jpni x jpnj emulated MPI ranks (one thread each, mppsend / mpprecv as FIFO mailboxes), against the oracle's
+    multi-rank lbc_lnk: every nature, both signs, fold-INconsistent random data, even and odd jpiglo"""
+    rng = np.random.default_rng(40 + jperio)
+    for (G, GJ, K) in ((22, 17, 2), (23, 16, 1)):
+        for lay in ((2, 2), (3, 2), (4, 1), (1, 3)):
+            for nog in ((False, True) if jperio in (4, 6) else (True,)):
+                try:
+                    w = O.World(G, GJ, K, jperio, lay[0], lay[1], ln_nnogather=nog)
+                except ValueError:
+                    continue                                   # a layout the reference cannot run (too many no-gather partners)
+                mw = R.MppWorld(w.doms, nog)
+                glob = rng.standard_normal((K, GJ, G))
+                for nat in "TUVWF":
+                    for sgn in (1.0, -1.0):
+                        a = w.scatter(glob)
+                        b = [x.copy() for x in a]
+                        w.lbc_lnk([a], nat, [sgn])
+                        mw.lbc_lnk(b, nat, sgn)
+                        for r, (x, y) in enumerate(zip(a, b)):
+                            assert np.array_equal(x.view(np.uint64), y.view(np.uint64)), (G, lay, nog, nat, sgn, r)
+                w.close()
+
+
+@needs_reference
+def test_reference_fold_partner_tables_equal_oracle_and_product(N):
+    """mpp_init_nfdcom (mppini.F90:1180-1240) from the reference's text, fed with the tables of ITS mpp_basic_decomposition: nsndto /
+    isendto (the no-gather fold partners, part of the product's domain descriptor) and nfsloop / nfeloop"""
+    for (gi, gj) in ((62, 40), (1442, 1207), (47, 33)):
+        for jperio in (4, 6):
+            for (ni, nj) in ((2, 1), (4, 2), (3, 2), (8, 1), (5, 3)):
+                try:
+                    w = O.World(gi, gj, 3, jperio, ni, nj)
+                except ValueError:
+                    continue
+                top = max(d.njmpp for d in w.doms)
+                for r, d in enumerate(w.doms):
+                    nsndto, isendto, nfsloop, nfeloop = R.mpp_init_nfdcom(gi, gj, jperio, ni, nj, r + 1, d.nlci, d.nldi, d.nlei)
+                    pd = N.mpp_init(gi, gj, 3, jperio, ni, nj, r + 1)
+                    assert (d.nsndto, d.isendto) == (nsndto, isendto) and (pd.nsndto, list(pd.isendto)[:pd.nsndto]) == (nsndto, isendto), (gi, jperio, ni, nj, r)
+                    if d.njmpp == top:
+                        assert (d.nfsloop, d.nfeloop) == (nfsloop, nfeloop)
+                    else:
+                        assert nsndto == 0
+                w.close()
 
 
 @needs_reference
