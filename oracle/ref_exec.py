@@ -361,3 +361,38 @@ class MppWorld:
             t.join(timeout=25)
         if err or any(t.is_alive() for t in th):
             raise RuntimeError("mpp_lnk failed or hung: %s" % (err[:1] or "timeout"))
+
+    def rank_lbc(self, r):
+        """the exchange as rank r's tracer routine calls it (to be used from that rank's own thread, all ranks running)"""
+        def lbc(items):
+            for a, nat, sgn in items:
+                a3 = a if a.ndim == 3 else a.reshape((1,) + a.shape)
+                self.ns[r]["mpp_lnk_3d"]("ref_exec", np.transpose(a3), nat, float(sgn))
+        return lbc
+
+
+def tra_adv_fct_mpp(world, gf, kjpt, kn_fct_h, kn_fct_v, ln_linssh, ln_isfcav, ln_nnogather=True):
+    """the reference's tra_adv_fct on EVERY rank of `world` (an oracle World, used for the decomposition scalars and to scatter the
+    global fields of `gf`), the ranks exchanging their halos through the reference's mpp_lnk / mpp_nfd (MppWorld): what `mpirun -np
+    jpnij nemo` does for this routine.  Returns the list of local pta arrays."""
+    mw = MppWorld(world.doms, ln_nnogather)
+    loc = {k: world.scatter(gf[k]) for k in DOM_ARRAYS + DOM_INT_ARRAYS + ("pun", "pvn", "pwn", "ptb", "ptn", "pta")}
+    out, err = [None] * mw.n, []
+
+    def run(r):
+        try:
+            d = world.doms[r]
+            g = {k: loc[k][r] for k in loc}
+            g["p2dt"] = gf["p2dt"]
+            out[r] = tra_adv_fct(g, d.jpi, d.jpj, d.jpk, kjpt, kn_fct_h, kn_fct_v, ln_linssh, ln_isfcav, mw.rank_lbc(r))
+        except Exception:                 # noqa: BLE001
+            import traceback
+            err.append((r, traceback.format_exc()))
+    th = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(mw.n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=240)
+    if err or any(t.is_alive() for t in th):
+        raise RuntimeError("tra_adv_fct_mpp failed or hung: %s" % (err[:1] or "timeout"))
+    return out

@@ -328,6 +328,21 @@ def test_reference_multi_rank_exchange_equals_the_oracle(jperio):
 
 
 @needs_reference
+@pytest.mark.parametrize("jperio,lay,nog,h,v", [(4, (2, 2), True, 4, 4), (6, (3, 2), False, 4, 4), (1, (2, 1), True, 2, 2), (4, (4, 1), True, 2, 4)])
+def test_reference_tra_adv_fct_on_emulated_mpi_ranks_equals_the_mono_domain_oracle(jperio, lay, nog, h, v):
+    """what `mpirun -np jpnij nemo` does for this routine, from the reference's text only: tra_adv_fct on every rank, halos and north
+    fold through mpp_lnk / mpp_nfd on emulated MPI ranks; the assembled interiors are the mono-domain oracle's result bit for bit"""
+    G, GJ, K, kjpt = 26, 21, 6, 2
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=800 + jperio)
+    ref, _, _ = H.oracle_fct(O, gf, G, GJ, K, jperio, 1, 1, kjpt, h, v)
+    w = O.World(G, GJ, K, jperio, lay[0], lay[1], ln_nnogather=nog)
+    loc = R.tra_adv_fct_mpp(w, gf, kjpt, h, v, False, False, nog)
+    glob = w.gather(loc, gf["pta"].copy())
+    w.close()
+    assert np.array_equal(glob.view(np.uint64), ref.view(np.uint64))
+
+
+@needs_reference
 def test_reference_fold_partner_tables_equal_oracle_and_product(N):
     """mpp_init_nfdcom (mppini.F90:1180-1240) from the reference's text, fed with the tables of ITS mpp_basic_decomposition: nsndto /
     isendto (the no-gather fold partners, part of the product's domain descriptor) and nfsloop / nfeloop"""
