@@ -94,6 +94,16 @@ def f_div(a, b):
         return np.float64(a) / np.float64(b)
 
 
+def _reduce(fn, empty, a, dim, mask):
+    """MAXVAL / MINVAL( a [, DIM=dim] [, MASK=mask] ): the value over an empty set is -HUGE / +HUGE"""
+    a = np.asarray(a)
+    if mask is not None:
+        a = np.where(mask, a, empty)
+    if a.size == 0:
+        return empty
+    return fn(a) if dim is None else fn(a, axis=int(dim) - 1)
+
+
 def f_ref(a, idx):
     """the storage of the Fortran-ordered array `a` from element `idx` (0-based) on, as a flat view: what a routine receives
     when it is handed an array element as the start of a buffer"""
@@ -107,7 +117,8 @@ def f_alloc(shape, integer=False):
 
 
 RUNTIME = dict(wp=8, f_ref=f_ref, f_max=f_max, f_min=f_min, f_abs=f_abs, f_sign=f_sign, f_real=f_real, f_mod=f_mod, f_int=f_int, f_nint=f_nint,
-               f_sqrt=math.sqrt, f_sum=np.sum, f_maxval=np.max, f_minval=np.min, f_div=f_div, f_alloc=f_alloc, np=np,
+               f_sqrt=math.sqrt, f_sum=np.sum, f_maxval=lambda a, dim=None, mask=None: _reduce(np.max, -np.finfo(np.float64).max, a, dim, mask),
+               f_minval=lambda a, dim=None, mask=None: _reduce(np.min, np.finfo(np.float64).max, a, dim, mask), f_div=f_div, f_alloc=f_alloc, np=np,
                f_trim=lambda s: s.rstrip(), f_present=lambda a: a is not None,
                f_size=lambda a, dim=None: a.size if dim is None else a.shape[dim - 1],
                f_cmplx=lambda re_, im=0.0, kind=None: complex(float(re_), float(im)), f_aimag=lambda z: z.imag)
@@ -371,7 +382,11 @@ class Translator:
                     if name in arrays or (name not in INTRINSICS and any(len(_split_top(a, ":")) > 1 for a in args)):
                         out.append("%s[%s]" % (name, self.index(args, arrays)))      # (a section can only be an array's)
                     elif name in INTRINSICS:
-                        out.append("%s(%s)" % (INTRINSICS[name], ", ".join(self.expr(a, arrays) for a in args)))
+                        conv = []
+                        for a in args:
+                            km = re.match(r"(dim|mask|kind)\s*=\s*(?!=)(.*)$", a)
+                            conv.append("%s=%s" % (km.group(1), self.expr(km.group(2), arrays)) if km else self.expr(a, arrays))
+                        out.append("%s(%s)" % (INTRINSICS[name], ", ".join(conv)))
                     else:
                         out.append("%s(%s)" % (name, ", ".join(self.expr(a, arrays) for a in args if a)))
                 else:
@@ -559,6 +574,7 @@ class Translator:
 
     def statement(self, st, arrays, body, depth, sel):
         ind = "    " * depth
+        st = re.sub(r"^\d+\s+", "", st)                   # a statement label (only ever the target of an I/O ERR= here)
         m = re.match(r"do\s+(\w+)\s*=\s*(.*)$", st)
         if m:
             parts = _split_top(m.group(2), ",")
@@ -650,7 +666,7 @@ class Translator:
                     dims = [self.expr(d, arrays) for d in _split_top(em.group(2), ",")]
                     body.append("%s%s = f_alloc((%s,), %s)" % (ind, em.group(1), ", ".join(dims), em.group(1) in self.int_names))
             return depth
-        if re.match(r"(deallocate|write|print|format)\b", st) or st == "continue":
+        if re.match(r"(deallocate|write|print|format|namelist|rewind|read|open|close)\b", st) or st == "continue":
             body.append(ind + "pass")
             return depth
         if st == "return":

@@ -396,3 +396,52 @@ def tra_adv_fct_mpp(world, gf, kjpt, kn_fct_h, kn_fct_v, ln_linssh, ln_isfcav, l
     if err or any(t.is_alive() for t in th):
         raise RuntimeError("tra_adv_fct_mpp failed or hung: %s" % (err[:1] or "timeout"))
     return out
+
+
+def dom_msk(doms, k_top, k_bot, ln_nnogather=True):
+    """the reference's dom_msk (src/OCE/DOM/dommsk.F90:66-290, free-slip: rn_shlat = 0, no BDY mask file) on every rank of a layout,
+    from its text: tmask from k_top / k_bot, lbc_lnk (mono-processor reference lbc_lnk, or the reference's mpp_lnk on emulated ranks),
+    umask / vmask / fmask, wmask, ssmask, tmask_h with the north-fold half row, tmask_i.  k_top, k_bot: lists over ranks of int32
+    (jpj, jpi).  Returns a list over ranks of dict(tmask, umask, vmask, wmask, tmask_i) as C-ordered arrays."""
+    n = len(doms)
+    mw = MppWorld(doms, ln_nnogather) if n > 1 else None
+    res, err = [None] * n, []
+
+    def run(r):
+        try:
+            d = doms[r]
+            jpi, jpj, jpk = d.jpi, d.jpj, d.jpk
+            lbc = mw.rank_lbc(r) if mw else reference_lbc(d.jperio, jpi, jpj)
+            a3 = lambda: np.full((jpi, jpj, jpk), np.nan, order="F")       # noqa: E731  (module arrays: ALLOCATEd, undefined)
+            a2 = lambda: np.full((jpi, jpj), np.nan, order="F")            # noqa: E731
+            ns = dict(jpi=jpi, jpj=jpj, jpk=jpk, jpim1=jpi - 1, jpjm1=jpj - 1, jpkm1=jpk - 1, jpiglo=d.jpiglo, jpjglo=d.jpjglo, jperio=d.jperio,
+                      nlci=d.nlci, nlcj=d.nlcj, nlej=d.nlej, nn_hls=1, lwp=False, lwm=False, numout=6, numond=7, numnam_ref=1, numnam_cfg=2,
+                      rn_shlat=0.0, ln_vorlat=False, ln_bdy=False, ln_mask_file=False, ios=0,
+                      mig=np.arange(1, jpi + 1, dtype=np.int32) + d.nimpp - 1, mjg=np.arange(1, jpj + 1, dtype=np.int32) + d.njmpp - 1,
+                      tmask=a3(), umask=a3(), vmask=a3(), fmask=a3(), wmask=a3(), wumask=a3(), wvmask=a3(), ssmask=a2(), ssumask=a2(),
+                      ssvmask=a2(), tmask_h=a2(), tmask_i=a2(), tpol=np.full(d.jpiglo, np.nan), fpol=np.full(d.jpiglo, np.nan),
+                      ctl_nam=lambda *a: None, usr_def_fmask=lambda *a: None, cn_cfg="none", nn_cfg=0)
+
+            def lbc_lnk(cdname, a, nat, sgn):
+                lbc([(np.transpose(a), nat, float(sgn))])
+
+            def lbc_lnk_multi(cdname, *t):
+                lbc([(np.transpose(t[i]), t[i + 1], float(t[i + 2])) for i in range(0, len(t), 3)])
+            ns.update(lbc_lnk=lbc_lnk, lbc_lnk_multi=lbc_lnk_multi)
+            defines = f90exec.cpp_defines(_read("src", "OCE", "vectopt_loop_substitute.h90"))
+            f90exec.load(_read("src", "OCE", "DOM", "dommsk.F90"), ns, defines=defines, only=("dom_msk",), int_arrays=("mig", "mjg"),
+                         arrays=("tmask", "umask", "vmask", "fmask", "wmask", "wumask", "wvmask", "ssmask", "ssumask", "ssvmask", "tmask_h",
+                                 "tmask_i", "tpol", "fpol", "bdytmask"))
+            ns["dom_msk"](np.transpose(np.ascontiguousarray(k_top[r], np.int32)), np.transpose(np.ascontiguousarray(k_bot[r], np.int32)))
+            res[r] = {k: np.ascontiguousarray(np.transpose(ns[k])) for k in ("tmask", "umask", "vmask", "wmask", "tmask_i")}
+        except Exception:                 # noqa: BLE001
+            import traceback
+            err.append((r, traceback.format_exc()))
+    th = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    if err or any(t.is_alive() for t in th):
+        raise RuntimeError("dom_msk failed or hung: %s" % (err[:1] or "timeout"))
+    return res

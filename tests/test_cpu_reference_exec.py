@@ -343,6 +343,27 @@ def test_reference_tra_adv_fct_on_emulated_mpi_ranks_equals_the_mono_domain_orac
 
 
 @needs_reference
+@pytest.mark.parametrize("jperio,lay", [(0, (1, 1)), (4, (1, 1)), (6, (1, 1)), (4, (2, 2)), (6, (3, 1)), (1, (2, 2))])
+def test_reference_dom_msk_equals_the_oracle(jperio, lay):
+    """dom_msk (dommsk.F90:66-290) from the reference's text, on one domain and on emulated ranks: tmask from the top / bottom
+    levels (with ice-shelf cavities), umask, vmask, wmask, and tmask_i with the halo rows and the north-fold half row masked"""
+    G, GJ, K = 24, 19, 6
+    rng = np.random.default_rng(2)
+    w = O.World(G, GJ, K, jperio, lay[0], lay[1])
+    kb = rng.integers(1, K, size=(GJ, G)).astype(np.int32)
+    kb[rng.random((GJ, G)) < 0.2] = 0
+    kt = np.minimum(1, kb).astype(np.int32)
+    kt[(rng.random((GJ, G)) < 0.2) & (kb >= 4)] = 2
+    lkt, lkb = [np.ascontiguousarray(a) for a in w.scatter(kt)], [np.ascontiguousarray(a) for a in w.scatter(kb)]
+    want = w.dom_msk(lkt, lkb)
+    got = R.dom_msk(w.doms, lkt, lkb)
+    for r in range(len(w.doms)):
+        for k in ("tmask", "umask", "vmask", "wmask", "tmask_i"):
+            assert np.array_equal(got[r][k].view(np.uint64), want[r][k].view(np.uint64)), (r, k)
+    w.close()
+
+
+@needs_reference
 def test_reference_fold_partner_tables_equal_oracle_and_product(N):
     """mpp_init_nfdcom (mppini.F90:1180-1240) from the reference's text, fed with the tables of ITS mpp_basic_decomposition: nsndto /
     isendto (the no-gather fold partners, part of the product's domain descriptor) and nfsloop / nfeloop"""
