@@ -31,7 +31,7 @@ import numpy as np
 
 INTRINSICS = {"max": "f_max", "min": "f_min", "abs": "f_abs", "sign": "f_sign", "real": "f_real", "mod": "f_mod", "int": "f_int",
               "nint": "f_nint", "sqrt": "f_sqrt", "sum": "f_sum", "maxval": "f_maxval", "minval": "f_minval", "present": "f_present",
-              "trim": "f_trim", "size": "f_size", "cmplx": "f_cmplx", "aimag": "f_aimag"}
+              "trim": "f_trim", "size": "f_size", "cmplx": "f_cmplx", "aimag": "f_aimag", "count": "f_count"}
 
 
 # ---- run-time support (the namespace translated code runs in) ---------------------------------------------------------------
@@ -121,7 +121,8 @@ RUNTIME = dict(wp=8, f_ref=f_ref, f_max=f_max, f_min=f_min, f_abs=f_abs, f_sign=
                f_minval=lambda a, dim=None, mask=None: _reduce(np.min, np.finfo(np.float64).max, a, dim, mask), f_div=f_div, f_alloc=f_alloc, np=np,
                f_trim=lambda s: s.rstrip(), f_present=lambda a: a is not None,
                f_size=lambda a, dim=None: a.size if dim is None else a.shape[dim - 1],
-               f_cmplx=lambda re_, im=0.0, kind=None: complex(float(re_), float(im)), f_aimag=lambda z: z.imag)
+               f_cmplx=lambda re_, im=0.0, kind=None: complex(float(re_), float(im)), f_aimag=lambda z: z.imag,
+               f_count=lambda a: int(np.count_nonzero(a)))
 
 
 # ---- source preparation --------------------------------------------------------------------------------------------------------
@@ -326,6 +327,7 @@ class Translator:
 
     def __init__(self, arrays=(), int_arrays=()):
         self.global_arrays = set(a.lower() for a in arrays) | set(a.lower() for a in int_arrays)
+        self.global_int_arrays = set(a.lower() for a in int_arrays)
         self.module_names = set()                         # variables declared at module level: `global` inside the routines
 
     def scan_module_level(self, sts):
@@ -501,7 +503,7 @@ class Translator:
         is_result_of = lambda n: n == getattr(self, "function_name", None)      # noqa: E731
         left, right = st.split("::", 1)
         attrs = [a.strip() for a in _split_top(left, ",")]
-        integer = attrs[0].startswith("integer")
+        integer = attrs[0].startswith("integer") or attrs[0].startswith("logical")
         dim = next((a for a in attrs if a.startswith("dimension")), None)
         allocatable = any(a.startswith("allocatable") for a in attrs)
         optional = any(a.startswith("optional") for a in attrs)
@@ -664,7 +666,7 @@ class Translator:
                 if em:
                     arrays.add(em.group(1))
                     dims = [self.expr(d, arrays) for d in _split_top(em.group(2), ",")]
-                    body.append("%s%s = f_alloc((%s,), %s)" % (ind, em.group(1), ", ".join(dims), em.group(1) in self.int_names))
+                    body.append("%s%s = f_alloc((%s,), %s)" % (ind, em.group(1), ", ".join(dims), em.group(1) in self.int_names or em.group(1) in self.global_int_arrays))
             return depth
         if re.match(r"(deallocate|write|print|format|namelist|rewind|read|open|close)\b", st) or st == "continue":
             body.append(ind + "pass")

@@ -21,11 +21,10 @@
  * oracle/ref_exec.py: IEEE binary64, key_nosignedzero as arch/arch-linux_gfortran.fcm:46 builds): tra_adv (driver,
  * transports), trc_adv, tra_adv_fct + nonosc + interp_4th_cpt, tra_adv_mus, tra_adv_cen, tra_nxt (+ _fix / _vvl), the mono-
  * processor lbc_lnk + lbc_nfd, the multi-rank mpp_lnk + mpp_nfd (gather and no-gather fold, on emulated MPI ranks),
- * mpp_basic_decomposition, mpp_init_nfdcom, dom_msk, glob_sum + DDPDD and SIGN agree with this restatement BIT FOR BIT
+ * mpp_init (+ mpp_basic_decomposition, mpp_init_nfdcom; all-ocean layouts), dom_msk, glob_sum + DDPDD and SIGN agree with this restatement BIT FOR BIT
  * (tests/test_cpu_reference_exec.py), and
  * the committed golden vectors carry the hashes of those executions (tests/golden/ref_exec_pins.json).  Not pinned
- * that way: the neighbour / boundary-flag tables of mpp_init (checked against the reference's partition tables
- * tests/BENCH/EXPREF/best_jpni_jpnj_*).
+ * that way: compiled-binary effects, land-subdomain elimination in mpp_init (out of scope).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use this.
  *

@@ -445,3 +445,40 @@ def dom_msk(doms, k_top, k_bot, ln_nnogather=True):
     if err or any(t.is_alive() for t in th):
         raise RuntimeError("dom_msk failed or hung: %s" % (err[:1] or "timeout"))
     return res
+
+
+MPP_INIT_SCALARS = ("jpi", "jpj", "jpk", "jpim1", "jpjm1", "jpkm1", "jpij", "jpnij", "jpimax", "jpjmax", "nreci", "nrecj", "l_iperio", "l_jperio",
+                    "noso", "nowe", "noea", "nono", "nlci", "nldi", "nlei", "nlcj", "nldj", "nlej", "nbondi", "nbondj", "nimpp", "njmpp", "npolj",
+                    "nproc", "nsndto", "nfsloop", "nfeloop", "l_north_nogather", "ndim_rank_north")
+MPP_INIT_TABLES = ("nfiimpp", "nfipproc", "nfilcit", "nimppt", "ibonit", "nlcit", "nlcjt", "njmppt", "ibonjt", "nldit", "nldjt", "nleit", "nlejt",
+                   "isendto", "nrank_north")
+
+
+def mpp_init(jpiglo, jpjglo, jpkglo, jperio, jpni, jpnj, narea, ln_nnogather=True):
+    """the reference's mpp_init (src/OCE/LBC/mppini.F90:110-692) for rank `narea` (1-based) of an all-ocean jpni x jpnj layout, from
+    its text (with ITS mpp_basic_decomposition and mpp_init_nfdcom): the decomposition scalars it leaves in dom_oce / lib_mpp -- sizes,
+    offsets, inner bounds, neighbour ranks, boundary flags, north-fold type, fold partners -- as a dict.  Stubbed: the search for the
+    best partition and for land subdomains (every subdomain holds ocean), the north communicator, IOIPSL, all printing."""
+    import types
+    def stop(*a):
+        raise ValueError("ctl_stop: " + " ".join(str(x) for x in a))
+    ns = dict(jpiglo=jpiglo, jpjglo=jpjglo, jpkglo=jpkglo, jperio=jperio, jpni=jpni, jpnj=jpnj, mppsize=jpni * jpnj, narea=narea, nn_hls=1,
+              lwp=False, ln_ctl=False, sn_cfctl=types.SimpleNamespace(l_layout=False), ln_read_cfg=False, ln_bdy=False, ln_mask_file=False,
+              ln_nnogather=bool(ln_nnogather), numnam_ref=1, numnam_cfg=2, numbot=-1, numbdy=-1, numout=6, ctmp1="", ctmp2="", ctmp3="", ctmp4="",
+              ctl_stop=stop, ctl_warn=lambda *a: None, ctl_nam=lambda *a: None, mpp_sum=lambda *a: None, mpp_init_ioipsl=lambda: None,
+              isendto=np.zeros(3, np.int32), ndim_rank_north=0, nrank_north=np.zeros(jpni, np.int32))
+    for k in MPP_INIT_SCALARS:
+        ns.setdefault(k, 0)
+    ns["mpp_init_bestpartition"] = lambda knbij, knbi=None, knbj=None, knbcnt=None, ldlist=None: {1: jpni, 2: jpnj, 3: 0}
+    ns["mpp_init_isoce"] = lambda knbi, knbj, ldisoce: ldisoce.__setitem__(Ellipsis, 1)
+
+    def mpp_ini_north():                                               # lib_mpp.F90: the ranks of the northern row, all ocean here
+        ns["ndim_rank_north"] = jpni
+        ns["nrank_north"] = np.arange((jpnj - 1) * jpni, jpnj * jpni, dtype=np.int32)
+    ns["mpp_ini_north"] = mpp_ini_north
+    f90exec.load(_read("src", "OCE", "LBC", "mppini.F90"), ns, int_arrays=MPP_INIT_TABLES, defined=("key_mpp_mpi",),
+                 only=("mpp_init", "mpp_basic_decomposition", "mpp_init_nfdcom"), module_vars=MPP_INIT_SCALARS + MPP_INIT_TABLES)
+    ns["mpp_init"]()
+    out = {k: ns[k] for k in MPP_INIT_SCALARS}
+    out["isendto"] = [int(x) for x in ns["isendto"][:ns["nsndto"]]]
+    return out

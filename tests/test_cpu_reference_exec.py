@@ -364,6 +364,31 @@ def test_reference_dom_msk_equals_the_oracle(jperio, lay):
 
 
 @needs_reference
+@pytest.mark.parametrize("jperio", [0, 1, 2, 4, 6, 7])
+def test_reference_mpp_init_equals_oracle_and_product(N, jperio):
+    """the whole mpp_init (mppini.F90:110-692, all-ocean layouts) from the reference's text against the oracle's restatement AND the
+    product's host code (nemo_mpp_init, csrc/layout.cpp): local sizes, global offsets, inner bounds, neighbour ranks (east-west and
+    north-south wrap, the fold partner of the top row), boundary flags, north-fold type, local periodicity, no-gather fold partners"""
+    keys = ("jpi", "jpj", "nimpp", "njmpp", "nlci", "nlcj", "nldi", "nlei", "nldj", "nlej", "nbondi", "nbondj", "noea", "nowe", "noso", "nono",
+            "npolj", "jpimax", "jpjmax")
+    for (gi, gj) in ((62, 40), (47, 33)):
+        for (ni, nj) in ((1, 1), (2, 1), (1, 2), (3, 2), (4, 2), (5, 3)):
+            try:
+                w = O.World(gi, gj, 4, jperio, ni, nj)
+            except ValueError:
+                continue
+            for r, d in enumerate(w.doms):
+                ref = R.mpp_init(gi, gj, 4, jperio, ni, nj, r + 1)
+                pd = N.mpp_init(gi, gj, 4, jperio, ni, nj, r + 1)
+                for k in keys:
+                    assert int(ref[k]) == int(getattr(d, k)) == int(getattr(pd, k)), (gi, gj, ni, nj, r, k)
+                assert bool(ref["l_iperio"]) == bool(d.l_Iperio) == bool(pd.l_Iperio) and bool(ref["l_jperio"]) == bool(d.l_Jperio) == bool(pd.l_Jperio)
+                if jperio in (4, 6) and ni > 1:               # (without a fold, or with jpni = 1, the reference fills the list too; nobody reads it)
+                    assert ref["isendto"] == d.isendto == list(pd.isendto)[:pd.nsndto], (gi, gj, ni, nj, r)
+            w.close()
+
+
+@needs_reference
 def test_reference_fold_partner_tables_equal_oracle_and_product(N):
     """mpp_init_nfdcom (mppini.F90:1180-1240) from the reference's text, fed with the tables of ITS mpp_basic_decomposition: nsndto /
     isendto (the no-gather fold partners, part of the product's domain descriptor) and nfsloop / nfeloop"""
