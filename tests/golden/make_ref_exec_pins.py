@@ -66,6 +66,18 @@ if __name__ == "__main__":
             ent["undefined_read"] = UNDEFINED_READS[name]
         pins["cases"][name] = ent
         print(name, ent["outputs"])
+    # BASELINE config C1 at FULL size (tests/BENCH 128x128x75, T+S, FCT 2/2, closed; BENCH's analytic fields): ~2.5 M tracer-points,
+    # a couple of minutes of translated Fortran.  tests/test_gpu_fct_parity.py::test_bench128_closed_T_S holds the CUDA path to the
+    # oracle on exactly these inputs; tests/test_cpu_reference_exec.py holds the oracle to this hash.
+    import time
+    import helpers as H
+    t0 = time.time()
+    gf = H.global_bench_fields(O, 128, 128, 75, 0, 2)
+    out = R.tra_adv_fct(gf, 128, 128, 75, 2, 2, 2, False, False, R.reference_lbc(0, 128, 128))
+    assert np.isfinite(out).all()
+    pins["full_size"] = {"c1_bench128": {"input_sha256": GC.input_hash(gf, {}), "outputs": {"pta": GC.digest(out)},
+                                         "reference_files": {f: file_sha(f) for f in FILES["fct"]}, "seconds": round(time.time() - t0, 1)}}
+    print("c1_bench128", pins["full_size"]["c1_bench128"])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_exec_pins.json")
     with open(path, "w") as f:
         json.dump(pins, f, indent=1, sort_keys=True)

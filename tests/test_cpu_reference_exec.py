@@ -48,6 +48,18 @@ def test_golden_vectors_are_what_the_reference_source_produced():
     assert [n for n, p in PINS["cases"].items() if "undefined_read" in p] == ["cen_h4v2_jperio0"]
 
 
+def test_c1_at_full_size_the_oracle_equals_the_reference_source():
+    """BASELINE config C1 (tests/BENCH 128x128x75, T+S, FCT 2/2, closed) at full size: the oracle's pta carries the sha256 of the
+    reference's tra_adv_fct text executed on the same BENCH fields (tests/golden/ref_exec_pins.json: full_size).  The GPU suite
+    compares the CUDA path with the oracle on exactly these inputs (test_gpu_fct_parity.py::test_bench128_closed_T_S)."""
+    pin = PINS["full_size"]["c1_bench128"]
+    gf = H.global_bench_fields(O, 128, 128, 75, 0, 2)
+    if GC.input_hash(gf, {}) != pin["input_sha256"]:
+        pytest.skip("the analytic BENCH fields (sin / cos through torch) differ in the last bit on this CPU")
+    ref, _, _ = H.oracle_fct(O, gf, 128, 128, 75, 0, 1, 1, 2, 2, 2)
+    assert GC.digest(ref) == pin["outputs"]["pta"]
+
+
 # ---- the translator, on snippets written here ------------------------------------------------------------------------------------
 def _run(src, **ns):
     f90exec.load(src, ns, arrays=ns.pop("_arrays", ()), int_arrays=ns.pop("_int_arrays", ()))
