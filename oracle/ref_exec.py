@@ -91,9 +91,15 @@ def reference_lbc(jperio, jpi, jpj):
     return lbc
 
 
-def tra_adv_fct(gf, jpi, jpj, jpk, kjpt, kn_fct_h, kn_fct_v, ln_linssh, ln_isfcav, lbc, cdtype="TRA", sign_mode="nosignedzero"):
-    """the reference's tra_adv_fct on the C-ordered fields of `gf` (helpers.random_fields); returns the new pta"""
+def tra_adv_fct(gf, jpi, jpj, jpk, kjpt, kn_fct_h, kn_fct_v, ln_linssh, ln_isfcav, lbc, cdtype="TRA", sign_mode="nosignedzero", trends=None):
+    """the reference's tra_adv_fct on the C-ordered fields of `gf` (helpers.random_fields); returns the new pta.  `trends`: a dict
+    that switches l_trdtra on and receives what the routine hands to trd_tra (traadv_fct.F90:96-112, 172-176, 299-308): C-ordered
+    copies of ztrdx / ztrdy / ztrdz under the keys (jn, 'x' | 'y' | 'z')."""
     dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, ln_isfcav, lbc, sign_mode)
+    if trends is not None:
+        dom.ns.update(l_trdtra=True, l_trdtrc=True, jptra_xad=1, jptra_yad=2, jptra_zad=3)
+        dom.ns["trd_tra"] = lambda kt, cd, jn, ktrd, ptrd, pu=None, ptra=None: trends.__setitem__(
+            (int(jn), "xyz"[int(ktrd) - 1]), np.ascontiguousarray(np.transpose(ptrd)).copy())
     dom.load("src", "OCE", "TRA", "traadv_fct.F90", only=("tra_adv_fct", "nonosc", "interp_4th_cpt"))
     pta = np.array(gf["pta"], copy=True)
     args = [F(np.ascontiguousarray(gf[k])) for k in ("pun", "pvn", "pwn", "ptb", "ptn")]

@@ -271,6 +271,39 @@ def test_reference_tra_adv_fct_equals_the_oracle(jperio, h, v):
 
 
 @needs_reference
+@pytest.mark.parametrize("jperio,h,v", [(0, 2, 2), (4, 4, 4)])
+def test_reference_trend_hooks_equal_the_oracle(jperio, h, v):
+    """l_trd: what tra_adv_fct hands to trd_tra (upstream + limited anti-diffusive fluxes, traadv_fct.F90:172-176, 299-308) -- the
+    arrays nemo_fct_set_trend_diag fills on the device -- from the reference's text against the oracle's"""
+    G, GJ, K, kjpt = 19, 15, 7, 2
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=90 + jperio)
+    w = O.World(G, GJ, K, jperio)
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS])
+    trd = [np.full((kjpt,) + d.shape3, np.nan) for _ in range(3)]
+    d.set_diag(*trd)
+    pta = gf["pta"].copy()
+    w.tra_adv_fct(gf["p2dt"], [gf["pun"]], [gf["pvn"]], [gf["pwn"]], [gf["ptb"]], [gf["ptn"]], [pta], kjpt, h, v)
+    w.close()
+    got = {}
+    out = R.tra_adv_fct(gf, G, GJ, K, kjpt, h, v, False, False, _lbc(jperio, G, GJ), trends=got)
+    assert np.array_equal(out.view(np.uint64), pta.view(np.uint64))
+    assert sorted(got) == [(jn, c) for jn in (1, 2) for c in "xyz"]
+    for jn in (1, 2):
+        for c, ref in zip("xyz", trd):
+            a, b = got[(jn, c)], ref[jn - 1]
+            undefined = np.isnan(a)
+            # ztrdx(:,:,:) = zwx(:,:,:) copies the last column / row of zwx, zwy, which the FIRST tracer has not defined yet (the loops
+            # stop at jpim1 / jpjm1 and the first lbc_lnk on them comes later, :119-135 vs :172-176): undefined memory in the reference,
+            # outside what trd_tra differences.  Everywhere else, and for every later tracer, the values are the oracle's.
+            if undefined.any():
+                assert jn == 1 and c in "xy"
+                idx = np.argwhere(undefined)
+                assert ((idx[:, 2] == G - 1) | (idx[:, 1] == GJ - 1)).all()
+            assert np.array_equal(a[~undefined].view(np.uint64), b[~undefined].view(np.uint64)), (jn, c)
+
+
+@needs_reference
 def test_sign_of_zero_is_the_only_trace_of_the_ieee_sign_intrinsic():
     """Without key_nosignedzero the intrinsic SIGN(0.5, -0.0) is -0.5: the limiter then picks the other beta for fluxes that are
     exactly -0.0, which changes nothing but the sign of zeros (on land and where every flux vanishes)."""
