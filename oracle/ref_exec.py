@@ -143,10 +143,10 @@ def tra_adv_cen(gf, jpi, jpj, jpk, kjpt, kn_cen_h, kn_cen_v, ln_linssh, ln_isfca
     return pta
 
 
-def tra_nxt(gf, extra, jpi, jpj, jpk, kt, nit000, neuler, rdt, atfp, r1_rau0, ln_linssh, lbc):
+def tra_nxt(gf, extra, jpi, jpj, jpk, kt, nit000, neuler, rdt, atfp, r1_rau0, ln_linssh, lbc, flags=None):
     """the reference's tra_nxt driver (src/OCE/TRA/tranxt.F90:65-177: lbc_lnk on tsa, tra_nxt_fix or tra_nxt_vvl, lbc_lnk on tsb, tsn,
-    tsa) on tsb / tsn / tsa = the case's ptb / ptn / pta (jpts = 2), without solar penetration, runoffs, ice shelves, BDY, AGRIF
-    or trend diagnostics; returns (tsb, tsn, tsa)"""
+    tsa) on tsb / tsn / tsa = the case's ptb / ptn / pta (jpts = 2); `flags` (ln_traqsr, ln_rnf, ln_isf, ln_rnf_depth, nksr) switch on
+    the forcings whose arrays `extra` then holds; no BDY, AGRIF or trend diagnostics; returns (tsb, tsn, tsa)"""
     dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, False, lbc)
     ts = {k: np.array(gf[s], copy=True) for k, s in (("tsb", "ptb"), ("tsn", "ptn"), ("tsa", "pta"))}
     ns = dom.ns
@@ -158,6 +158,14 @@ def tra_nxt(gf, extra, jpi, jpj, jpk, kt, nit000, neuler, rdt, atfp, r1_rau0, ln
     for k in ("emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf"):
         ns[k] = F(np.ascontiguousarray(extra[k]))
     ns["sbc_tsc"], ns["sbc_tsc_b"] = F(np.ascontiguousarray(extra["sbc"])), F(np.ascontiguousarray(extra["sbc_b"]))
+    # the optional forcings of tra_nxt_vvl (tranxt.F90:262-343): solar penetration, runoffs (surface or over depth), ice shelves
+    ns.update({k: (int(v) if k == "nksr" else bool(v)) for k, v in (flags or {}).items()})
+    for k in ("h_rnf", "r1_hisf_tbl", "ralpha", "rnf_tsc", "rnf_tsc_b", "risf_tsc", "risf_tsc_b", "qsr_hc", "qsr_hc_b"):
+        if k in extra:
+            ns[k] = F(np.ascontiguousarray(extra[k]))
+    for k in NXT_INT_ARRAYS:
+        if k in extra:
+            ns[k] = F(np.ascontiguousarray(extra[k], dtype=np.int32))
     text = _read("src", "OCE", "TRA", "tranxt.F90")
     f90exec.load(text, ns, arrays=DOM_ARRAYS + NXT_ARRAYS, int_arrays=DOM_INT_ARRAYS + NXT_INT_ARRAYS, defines=dom.defines, module_vars=("r2dt",))
     ns["tra_nxt"](kt)

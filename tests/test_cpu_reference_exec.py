@@ -571,6 +571,39 @@ def test_reference_tra_adv_cen_4th_order_reads_an_undefined_row():
 
 
 @needs_reference
+@pytest.mark.parametrize("flags", [dict(ln_traqsr=1, ln_rnf=1, ln_isf=1), dict(ln_rnf_depth=1, ln_rnf=1), dict(ln_traqsr=1)])
+def test_reference_tra_nxt_vvl_forcings_equal_the_oracle(flags):
+    """tra_nxt_vvl with its optional forcings (tranxt.F90:300-343): solar penetration down to nksr, runoffs at the surface or spread
+    over depth, ice-shelf melting between misfkt and misfkb -- the reference's text against the oracle's restatement"""
+    G, GJ, K, jperio, isf = 22, 17, 8, 4, bool(flags.get("ln_isf"))
+    rng = np.random.default_rng(77)
+    gf = H.random_fields(O, G, GJ, K, jperio, 2, seed=91, ln_linssh=False, ln_isfcav=isf)
+    w = O.World(G, GJ, K, jperio)
+    f2 = {k: rng.standard_normal((1, GJ, G)) * 1e-4 for k in ("emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf")}
+    w.lbc_lnk([[a] for a in f2.values()], "T" * 6, [1.0] * 6)
+    extra = {k: np.ascontiguousarray(v[0]) for k, v in f2.items()}
+    extra.update(h_rnf=10.0 + 50.0 * rng.random((GJ, G)), r1_hisf_tbl=1.0 / (20.0 + 10.0 * rng.random((GJ, G))), ralpha=rng.random((GJ, G)))
+    for k in ("sbc", "sbc_b", "rnf_tsc", "rnf_tsc_b", "risf_tsc", "risf_tsc_b"):
+        extra[k] = rng.standard_normal((2, GJ, G)) * 1e-5
+    for k in ("qsr_hc", "qsr_hc_b"):
+        extra[k] = rng.standard_normal((K, GJ, G)) * 1e-5
+    mikt, mbkt = gf["mikt"], gf["mbkt"]
+    extra.update(nk_rnf=np.minimum(mikt + 2, np.maximum(mbkt, 1)).astype(np.int32), misfkt=mikt.astype(np.int32).copy(),
+                 misfkb=np.minimum(mikt + 1, np.maximum(mbkt, 1)).astype(np.int32))
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS], ln_linssh=False, ln_isfcav=isf)
+    tb, tn, ta = gf["ptb"].copy(), gf["ptn"].copy(), gf["pta"].copy()
+    forc = O.NxtForcing(atfp=0.1, r1_rau0=1.0 / 1026.0, nksr=5, **flags,
+                        **{k: extra[k] for k in extra if k not in ("sbc", "sbc_b")})
+    w.tra_nxt(4, 1, False, 900.0, "TRA", [forc], [tb], [tn], [ta], 2, [extra["sbc"]], [extra["sbc_b"]])
+    w.close()
+    got = R.tra_nxt(gf, extra, G, GJ, K, 4, 1, 1, 900.0, 0.1, 1.0 / 1026.0, False, _lbc(jperio, G, GJ), flags=dict(flags, nksr=5))
+    for a, b, nm in zip(got, (tb, tn, ta), ("tsb", "tsn", "tsa")):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), nm
+    assert not np.array_equal(got[0], gf["ptb"])
+
+
+@needs_reference
 @pytest.mark.parametrize("jperio,lin,kt,neuler", [(1, True, 5, 1), (4, False, 5, 1), (6, False, 1, 0), (0, True, 1, 0)])
 def test_reference_tra_nxt_equals_the_oracle(jperio, lin, kt, neuler):
     """the whole tra_nxt driver: lbc_lnk on tsa, Euler swap at nit000 (neuler = 0) or tra_nxt_fix / tra_nxt_vvl + lbc_lnk on all three"""
