@@ -85,8 +85,9 @@ def reference_lbc(jperio, jpi, jpj):
     ns["lbc_nfd"] = ns["lbc_nfd_3d"]                                   # INTERFACE lbc_nfd (lbcnfd.F90:27-31)
 
     def lbc(items):
-        for a, nat, sgn in items:                                      # a: C-ordered [jpk][jpj][jpi] (or [jpj][jpi])
-            a3 = a if a.ndim == 3 else a.reshape((1,) + a.shape)
+        for a, nat, sgn in items:                                      # a: C-ordered [...][jpj][jpi]: 2-D, 3-D or 4-D
+            a3 = a.reshape((-1,) + a.shape[-2:])                       # (a 4-D field is a 3-D field with jpk * kjpt levels)
+            assert np.shares_memory(a3, a)
             ns["lbc_lnk_3d"]("ref_exec", np.transpose(a3), nat, float(sgn))
     return lbc
 
@@ -380,7 +381,8 @@ class MppWorld:
         """the exchange as rank r's tracer routine calls it (to be used from that rank's own thread, all ranks running)"""
         def lbc(items):
             for a, nat, sgn in items:
-                a3 = a if a.ndim == 3 else a.reshape((1,) + a.shape)
+                a3 = a.reshape((-1,) + a.shape[-2:])
+                assert np.shares_memory(a3, a)
                 self.ns[r]["mpp_lnk_3d"]("ref_exec", np.transpose(a3), nat, float(sgn))
         return lbc
 
@@ -496,3 +498,28 @@ def mpp_init(jpiglo, jpjglo, jpkglo, jperio, jpni, jpnj, narea, ln_nnogather=Tru
     out = {k: ns[k] for k in MPP_INIT_SCALARS}
     out["isendto"] = [int(x) for x in ns["isendto"][:ns["nsndto"]]]
     return out
+
+
+def trc_nxt(gf, trb, trn, tra, sbc_trc, sbc_trc_b, extra, jpi, jpj, jpk, kt, nittrc000, neuler, rdttrc, atfp, r1_rau0, ln_linssh, lbc,
+            ln_top_euler=False):
+    """the reference's trc_nxt driver (src/TOP/TRP/trcnxt.F90:56-183) from its text: lbc_lnk on tra, then the Euler swap (trn = tra,
+    trb = trn) or tra_nxt_fix / tra_nxt_vvl of tranxt.F90 with cdtype = 'TRC' (no solar, runoff or ice-shelf terms) + lbc_lnk on
+    trb, trn, tra.  Arrays C-ordered [jptra][jpk][jpj][jpi]; returns (trb, trn, tra)."""
+    dom = RefDomain(gf, jpi, jpj, jpk, ln_linssh, False, lbc)
+    ns = dom.ns
+    t = {"trb": np.array(trb, copy=True), "trn": np.array(trn, copy=True), "tra": np.array(tra, copy=True)}
+    for k, a in t.items():
+        ns[k] = F(a)
+    ns.update(jptra=t["tra"].shape[0], jp_tem=1, jp_sal=2, nittrc000=nittrc000, neuler=neuler, rdttrc=float(rdttrc), r2dttrc=2.0 * float(rdttrc),
+              atfp=float(atfp), r1_rau0=float(r1_rau0), ln_timing=False, ln_bdy=False, ln_traldf_iso=False, ln_ctl=False, l_offline=False,
+              ln_top_euler=bool(ln_top_euler), ln_traqsr=False, ln_rnf=False, ln_isf=False, ln_rnf_depth=False, nksr=0,
+              sbc_trc=F(np.ascontiguousarray(sbc_trc)), sbc_trc_b=F(np.ascontiguousarray(sbc_trc_b)))
+    for k in ("emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf"):
+        ns[k] = F(np.ascontiguousarray(extra[k]))
+    arrays = DOM_ARRAYS + NXT_ARRAYS + ("trb", "trn", "tra", "sbc_trc", "sbc_trc_b")
+    f90exec.load(_read("src", "OCE", "TRA", "tranxt.F90"), ns, arrays=arrays, int_arrays=DOM_INT_ARRAYS + NXT_INT_ARRAYS, defines=dom.defines,
+                 only=("tra_nxt_fix", "tra_nxt_vvl"))
+    f90exec.load(_read("src", "TOP", "TRP", "trcnxt.F90"), ns, arrays=arrays, int_arrays=DOM_INT_ARRAYS + NXT_INT_ARRAYS, defines=dom.defines,
+                 only=("trc_nxt",), defined=("key_top",))
+    ns["trc_nxt"](kt)
+    return t["trb"], t["trn"], t["tra"]

@@ -571,6 +571,34 @@ def test_reference_tra_adv_cen_4th_order_reads_an_undefined_row():
 
 
 @needs_reference
+@pytest.mark.parametrize("jperio,lin,kt,neuler", [(4, False, 5, 1), (1, True, 5, 1), (6, False, 1, 0)])
+def test_reference_trc_nxt_equals_the_oracle(jperio, lin, kt, neuler):
+    """trc_nxt (trcnxt.F90:56-183): lbc_lnk on tra, the Euler swap of BOTH now and before fields at nittrc000, or the Asselin filter
+    through tra_nxt_fix / tra_nxt_vvl with cdtype = 'TRC', for 5 passive tracers"""
+    G, GJ, K, jptra = 20, 15, 6, 5
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=1, seed=720 + jperio, ln_linssh=lin)
+    rng = np.random.default_rng(8)
+    w = O.World(G, GJ, K, jperio)
+    f2 = {k: rng.standard_normal((1, GJ, G)) * 1e-4 for k in ("emp_b", "emp", "fwfisf_b", "fwfisf", "rnf_b", "rnf")}
+    w.lbc_lnk([[a] for a in f2.values()], "T" * 6, [1.0] * 6)
+    sbc, sbc_b = rng.standard_normal((jptra, GJ, G)) * 1e-5, rng.standard_normal((jptra, GJ, G)) * 1e-5
+    w.lbc_lnk([[sbc], [sbc_b]], "TT", [1.0, 1.0])
+    extra = {k: np.ascontiguousarray(v[0]) for k, v in f2.items()}
+    trb = np.ascontiguousarray(np.stack([gf["ptb"][0] * (1 + 0.1 * n) for n in range(jptra)]))
+    trn = np.ascontiguousarray(np.stack([gf["ptn"][0] * (1 + 0.1 * n) for n in range(jptra)]))
+    tra = np.ascontiguousarray(np.stack([gf["ptn"][0] * (1.01 + 0.1 * n) + gf["pta"][0] for n in range(jptra)]))
+    d = w.doms[0]
+    d.set_fields(*[gf[k] for k in H.DOM_KEYS], ln_linssh=lin)
+    ob, on, oa = trb.copy(), trn.copy(), tra.copy()
+    forc = O.NxtForcing(atfp=0.1, r1_rau0=1.0 / 1026.0, **extra)
+    w.tra_nxt(kt, 1, neuler == 0 and kt == 1, 900.0, "TRC", [forc], [ob], [on], [oa], jptra, [sbc], [sbc_b])
+    w.close()
+    got = R.trc_nxt(gf, trb, trn, tra, sbc, sbc_b, extra, G, GJ, K, kt, 1, neuler, 900.0, 0.1, 1.0 / 1026.0, lin, _lbc(jperio, G, GJ))
+    for a, b, nm in zip(got, (ob, on, oa), ("trb", "trn", "tra")):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), nm
+
+
+@needs_reference
 @pytest.mark.parametrize("flags", [dict(ln_traqsr=1, ln_rnf=1, ln_isf=1), dict(ln_rnf_depth=1, ln_rnf=1), dict(ln_traqsr=1)])
 def test_reference_tra_nxt_vvl_forcings_equal_the_oracle(flags):
     """tra_nxt_vvl with its optional forcings (tranxt.F90:300-343): solar penetration down to nksr, runoffs at the surface or spread
