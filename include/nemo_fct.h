@@ -292,17 +292,23 @@ int nemo_fct_comm_report(nemo_fct_handle h, long long *n_exchanges, long long *b
 int nemo_fct_set_profiling(nemo_fct_handle h, int on);
 int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int name_stride, double *total_ms,
                           long long *calls);
-/* Select the kernel schedule (results are identical, bit for bit):
+/* Select the kernel schedule.  Schedules 0 - 3 return the same bits as the CPU restatement of the reference; schedule 4 returns the
+ * same VALUE at every cell and the same bits at every ocean cell -- on land cells, where the trend is +-0, it may return the zero
+ * with the other sign (its sign-bit forms of MAX(0,f) / MIN(0,f) / SIGN take -0.0 for negative; the reference built with
+ * key_nosignedzero takes it for positive): tests/test_cpu_reference_exec.py.
  *   0 = reference pass structure: one kernel per pass group on the whole interior, exchanges X1..X4 as in
  *       traadv_fct.F90:209,280,400,426;
  *   1 = fused inner region (P1-P5 with in-place Laplacian; nonosc + final trend in one shared-memory kernel) on the main
  *       stream, boundary frame + X1..X4 on a side stream; per-thread cp.async prefetch;
- *   2 = (default) as 1 with TMA-staged tiles for the inner kernels when jpi is even, else falls back to 1.
+ *   2 = as 1 with TMA-staged tiles for the inner kernels when jpi is even, else falls back to 1 (round-1 default).
  *   3 = as 2, and the fused nonosc kernel also fed by a 2-stage TMA ring (measured slower than 2 on B200: kept for study).
+ *   4 = (default) the whole step of the inner region in ONE kernel (k_fct_fused, csrc/fct_fused_kernel.cuh) + the tiled
+ *       interp_4th_cpt; falls back to 2 where its tiles do not fit (odd jpi, unaligned arrays, no room to split).
  * Subdomains smaller than 20 x 20 always use 0.                                                                    */
 int nemo_fct_set_schedule(nemo_fct_handle h, int schedule);
 /* Arithmetic of the one-kernel schedule (4).  STRICT (default): every REAL(wp) operation of traadv_fct.F90 as an IEEE operation
- * in the reference's order, no FMA contraction: bit-identical to the CPU restatement.  FAST: the six divisions per point (:164,
+ * in the reference's order, no FMA contraction: the values of the CPU restatement (see nemo_fct_set_schedule for the sign of zero
+ * on land).  FAST: the six divisions per point (:164,
  * :166, :393-396, :294) become a multiplication by a refined reciprocal (<= 1 ulp instead of <= 0.5 ulp); measured -12 % .. -32 %
  * kernel time, max relative difference 5e-11 on near-zero trends (above the 1e-12 bar: opt-in only).                      */
 #define NEMO_FCT_ARITH_STRICT 0

@@ -304,6 +304,32 @@ def test_reference_trend_hooks_equal_the_oracle(jperio, h, v):
 
 
 @needs_reference
+@pytest.mark.parametrize("G,GJ,K,jperio,kjpt,h,v,lin,isf", [(40, 30, 7, 0, 2, 2, 2, False, False), (44, 38, 9, 4, 2, 4, 4, False, False),
+                                                           (66, 40, 13, 6, 1, 4, 2, True, True)])
+def test_the_product_kernels_compiled_for_the_host_equal_the_reference_source(G, GJ, K, jperio, kjpt, h, v, lin, isf):
+    """No oracle in this loop: the PRODUCT's CUDA kernel source in its default schedule (k_fct_fused + tiled interp_4th_cpt + the
+    frame chain, compiled for the host by tests/emu with TMA / mbarriers / shared memory emulated) against the REFERENCE's
+    tra_adv_fct text executed by translation, both exchanging halos through the reference's lbc_lnk / lbc_nfd text: equal at every
+    cell, bit for bit at every ocean cell (see below for the sign of zero on land).  (The oracle only generates the random input fields.)"""
+    import emu_api
+    emu = emu_api.load()
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt, seed=1300 + G + K, ln_linssh=lin, ln_isfcav=isf)
+    ref_lbc = _lbc(jperio, G, GJ)
+    pta, plan = emu_api.fct_step_one_kernel(emu, gf, kjpt, h, v, lin, isf, 1, lambda trip: ref_lbc(list(trip)), jperio in (3, 4, 5, 6))
+    assert pta is not None and plan["split"]
+    want = R.tra_adv_fct(gf, G, GJ, K, kjpt, h, v, lin, isf, ref_lbc)
+    assert not np.array_equal(want, gf["pta"])
+    assert np.array_equal(pta, want)                                  # the same VALUE at every cell ...
+    differ = pta.view(np.uint64) != want.view(np.uint64)
+    tmask = np.broadcast_to(gf["tmask"][None], pta.shape)
+    # ... and the same BITS at every ocean cell.  On land, where pta is +-0, k_fct_fused may return the zero with the other sign: its
+    # sign-bit forms of MAX(0,f) / MIN(0,f) / SIGN take -0.0 for negative, the reference's key_nosignedzero SIGN takes it for positive,
+    # and the limiter then multiplies a zero flux by the other (possibly negative, land-side) beta.  The three-kernel and the
+    # reference-structured schedules keep the reference's zero signs too (golden hashes, test_vectors_golden.py).
+    assert (want[differ] == 0.0).all() and (tmask[differ] == 0.0).all()
+
+
+@needs_reference
 def test_sign_of_zero_is_the_only_trace_of_the_ieee_sign_intrinsic():
     """Without key_nosignedzero the intrinsic SIGN(0.5, -0.0) is -0.5: the limiter then picks the other beta for fluxes that are
     exactly -0.0, which changes nothing but the sign of zeros (on land and where every flux vanishes)."""
