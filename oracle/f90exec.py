@@ -1,8 +1,13 @@
 """f90exec -- ORACLE-SIDE TEST INFRASTRUCTURE (never imported by the product).
 
 Executes the reference's OWN Fortran source text: a line-by-line translator from the restricted Fortran 90 subset the NEMO
-tracer routines are written in (DO / IF / SELECT CASE, array elements and sections, MAX / MIN / ABS / SIGN, CALL) to Python,
-which is then exec'ed on numpy arrays.  There is no Fortran compiler in this image or on the GPU box (oracle/_ref_recipe/),
+tracer, boundary-condition and decomposition routines are written in to Python, which is then exec'ed on numpy arrays.
+Understood: SUBROUTINE / FUNCTION, declarations (explicit-shape locals, ALLOCATABLE + ALLOCATE, OPTIONAL dummies, module variables),
+DO (with step) / IF - ELSE IF - ELSE (block and one-line) / SELECT CASE, assignments to scalars, elements, sections and whole arrays,
+array-valued expressions, integer division, MAX / MIN / ABS / SIGN / MOD / SIZE / MAXVAL / MINVAL / COUNT / REAL / CMPLX / AIMAG,
+CALL with keyword arguments, scalar INTENT(out / inout) arguments (handed back by position), message buffers passed by their first
+element, RETURN / STOP; I/O, NAMELIST and FORMAT statements are skipped.  `cpp` is a small C preprocessor (conditionals, object- and
+function-like macros) for the generic .h90 files.  There is no Fortran compiler in this image or on the GPU box (oracle/_ref_recipe/),
 so this is the nearest thing to "the reference run here": the arithmetic expressions, loop bounds and statement order come
 from the reference's file, character for character, not from anybody's reading of it.  It is used to pin oracle/*.c
 (tests/test_cpu_reference_exec.py) and to generate tests/golden/ref_exec_*.npz (oracle/_ref_recipe/make_ref_exec_golden.py).
