@@ -5,7 +5,8 @@ a test (needs the reference tree; minutes of translated Fortran):
 
 Part 1: tra_adv_fct on random small domains (every jperio 0-7, 2nd / 4th order, ln_linssh / ln_isfcav, 1-3 tracers, land fraction up
 to 0.9, CFL up to 0.9, jpk down to 3).  Part 2: the multi-rank exchange (mpp_lnk + mpp_nfd, gather and no-gather) on random layouts
-up to 5 x 3 ranks, every nature, random sign.  Round 2: 1623 FCT cases and 2835 exchanges, 0 mismatches (bit for bit)."""
+up to 5 x 3 ranks, every nature, random sign.  Part 3: tra_adv_mus (with and without the upstream indicator) and tra_adv_cen (2nd order
+horizontal, 2nd / compact vertical).  Round 2: 1623 FCT cases, 2835 exchanges and 2217 MUSCL / centred cases, 0 mismatches (bit for bit)."""
 import argparse
 import os
 import sys
@@ -69,6 +70,32 @@ def sweep_exchange(seconds, rng):
     return bad
 
 
+def sweep_mus_cen(seconds, rng):
+    t0, n, bad = time.time(), 0, 0
+    while time.time() - t0 < seconds and bad < 5:
+        G, GJ, K, kjpt = int(rng.integers(8, 26)), int(rng.integers(8, 22)), int(rng.integers(3, 9)), int(rng.integers(1, 4))
+        jperio, lin, isf, ups = int(rng.integers(0, 8)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        land, seed = float(rng.choice([0.0, 0.15, 0.6])), int(rng.integers(0, 10 ** 6))
+        gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=seed, land=land, ln_linssh=lin, ln_isfcav=isf)
+        mx = H.mus_extra_fields(O, gf, G, GJ, K, jperio, seed=seed, runoff=True)
+        lbc = R.reference_lbc(jperio, G, GJ)
+        ref, _ = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, 1, 1, kjpt, ln_linssh=lin, ln_isfcav=isf, ld_msc_ups=ups)
+        n += 1
+        if not same(R.tra_adv_mus(gf, mx, G, GJ, K, kjpt, lin, isf, ups, lbc), ref):
+            bad += 1
+            print("MUS MISMATCH", G, GJ, K, kjpt, jperio, lin, isf, ups, land, seed, flush=True)
+        if isf:
+            continue                                   # tra_adv_cen is run without cavities here
+        v = int(rng.choice([2, 4]))
+        ref, _ = H.oracle_cen(O, gf, G, GJ, K, jperio, 1, 1, kjpt, 2, v)
+        n += 1
+        if not same(R.tra_adv_cen(gf, G, GJ, K, kjpt, 2, v, False, False, lbc), ref):
+            bad += 1
+            print("CEN MISMATCH", G, GJ, K, kjpt, jperio, v, seed, flush=True)
+    print("tra_adv_mus / tra_adv_cen: %d cases, %d mismatches, %.0f s" % (n, bad, time.time() - t0))
+    return bad
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=420.0)
@@ -76,4 +103,4 @@ if __name__ == "__main__":
     a = ap.parse_args()
     assert R.available(), "the reference tree is not on this machine"
     rng = np.random.default_rng(a.seed)
-    sys.exit(1 if sweep_fct(a.seconds * 0.6, rng) + sweep_exchange(a.seconds * 0.4, rng) else 0)
+    sys.exit(1 if sweep_fct(a.seconds * 0.5, rng) + sweep_exchange(a.seconds * 0.3, rng) + sweep_mus_cen(a.seconds * 0.2, rng) else 0)
