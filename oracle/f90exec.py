@@ -36,7 +36,8 @@ import numpy as np
 
 INTRINSICS = {"max": "f_max", "min": "f_min", "abs": "f_abs", "sign": "f_sign", "real": "f_real", "mod": "f_mod", "int": "f_int",
               "nint": "f_nint", "sqrt": "f_sqrt", "sum": "f_sum", "maxval": "f_maxval", "minval": "f_minval", "present": "f_present",
-              "trim": "f_trim", "size": "f_size", "cmplx": "f_cmplx", "aimag": "f_aimag", "count": "f_count"}
+              "trim": "f_trim", "size": "f_size", "cmplx": "f_cmplx", "aimag": "f_aimag", "count": "f_count",
+              "maxloc": "f_maxloc", "minloc": "f_minloc", "isnan": "f_isnan", "nint": "f_nint"}
 
 
 # ---- run-time support (the namespace translated code runs in) ---------------------------------------------------------------
@@ -106,7 +107,24 @@ def _reduce(fn, empty, a, dim, mask):
         a = np.where(mask, a, empty)
     if a.size == 0:
         return empty
+    if a.dtype.kind == "f" and np.isnan(a).any():          # gfortran: NaN operands are skipped unless every operand is one
+        if np.isnan(a).all():
+            return np.float64(np.nan)
+        a = np.where(np.isnan(a), empty, a)
     return fn(a) if dim is None else fn(a, axis=int(dim) - 1)
+
+
+def _loc(a, mask, want_max):
+    """MAXLOC / MINLOC( a [, MASK=mask] ): 1-based indices of the FIRST extremum in array element order (0, ... for an empty set);
+    NaN operands are skipped, as gfortran does"""
+    a = np.asarray(a, dtype=np.float64)
+    ok = ~np.isnan(a) if mask is None else (np.asarray(mask) & ~np.isnan(a))
+    if not ok.any():
+        return np.zeros(a.ndim, dtype=np.int64)
+    v = np.where(ok, a, -np.inf if want_max else np.inf)
+    flat = v.ravel(order="F")
+    k = int(np.argmax(flat) if want_max else np.argmin(flat))
+    return np.array(np.unravel_index(k, a.shape, order="F"), dtype=np.int64) + 1
 
 
 def f_ref(a, idx):
@@ -127,7 +145,8 @@ RUNTIME = dict(wp=8, f_ref=f_ref, f_max=f_max, f_min=f_min, f_abs=f_abs, f_sign=
                f_trim=lambda s: s.rstrip(), f_present=lambda a: a is not None,
                f_size=lambda a, dim=None: a.size if dim is None else a.shape[dim - 1],
                f_cmplx=lambda re_, im=0.0, kind=None: complex(float(re_), float(im)), f_aimag=lambda z: z.imag,
-               f_count=lambda a: int(np.count_nonzero(a)))
+               f_count=lambda a: int(np.count_nonzero(a)), f_isnan=lambda x: bool(np.isnan(x)),
+               f_maxloc=lambda a, mask=None: _loc(a, mask, True), f_minloc=lambda a, mask=None: _loc(a, mask, False))
 
 
 # ---- source preparation --------------------------------------------------------------------------------------------------------
@@ -398,6 +417,10 @@ class Translator:
                         out.append("%s(%s)" % (name, ", ".join(self.expr(a, arrays) for a in args if a)))
                 else:
                     out.append(name)
+            elif s.startswith("(/", i):                                  # array constructor (/ a, b, ... /)
+                k = s.index("/)", i)
+                out.append("np.array([%s])" % ", ".join(self.expr(a, arrays) for a in _split_top(s[i + 2:k], ",")))
+                i = k + 2
             elif ch == "(":
                 k = self._match_paren(s, i)
                 out.append("(" + self.expr(s[i + 1:k], arrays) + ")")

@@ -21,7 +21,7 @@
  * oracle/ref_exec.py: IEEE binary64, key_nosignedzero as arch/arch-linux_gfortran.fcm:46 builds): tra_adv (driver,
  * transports), trc_adv, tra_adv_fct + nonosc + interp_4th_cpt, tra_adv_mus, tra_adv_cen, tra_nxt (+ _fix / _vvl), the mono-
  * processor lbc_lnk + lbc_nfd, the multi-rank mpp_lnk + mpp_nfd (gather and no-gather fold, on emulated MPI ranks),
- * mpp_init (+ mpp_basic_decomposition, mpp_init_nfdcom; all-ocean layouts), dom_msk, glob_sum + DDPDD and SIGN agree with this restatement BIT FOR BIT
+ * mpp_init (+ mpp_basic_decomposition, mpp_init_nfdcom; all-ocean layouts), dom_msk, stp_ctl, glob_sum + DDPDD and SIGN agree with this restatement BIT FOR BIT
  * (tests/test_cpu_reference_exec.py), and
  * the committed golden vectors carry the hashes of those executions (tests/golden/ref_exec_pins.json).  Not pinned
  * that way: compiled-binary effects, land-subdomain elimination in mpp_init (out of scope).

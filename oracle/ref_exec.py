@@ -523,3 +523,25 @@ def trc_nxt(gf, trb, trn, tra, sbc_trc, sbc_trc_b, extra, jpi, jpj, jpk, kt, nit
                  only=("trc_nxt",), defined=("key_top",))
     ns["trc_nxt"](kt)
     return t["trb"], t["trn"], t["tra"]
+
+
+def stp_ctl(dom, sshn, un, tsn, tmask, umask, kt=1):
+    """the reference's stp_ctl (src/OCE/stpctl.F90:58-196) on one subdomain from its text, in the branch without ln_ctl: the extrema
+    zmax(1:6), the error condition (kindic = -3 and ctl_stop) and, when it fires, the MAXLOC / MINLOC positions.  The files it
+    would write (time.step, run.stat, output.abort) are not opened (lwm = .false.).  dom: the decomposition scalars (nimpp, njmpp,
+    narea); arrays C-ordered.  Returns dict(zmax[6], kindic, and ih, iu, is1, is2 when kindic = -3)."""
+    import types
+    stopped = []
+    ssmask = np.ascontiguousarray(np.max(tmask, axis=0))               # dommsk.F90: ssmask = MAXVAL( tmask, DIM=3 )
+    ns = dict(sshn=F(np.ascontiguousarray(sshn)), un=F(np.ascontiguousarray(un)), tsn=F(np.ascontiguousarray(tsn)), tmask=F(np.ascontiguousarray(tmask)),
+              umask=F(np.ascontiguousarray(umask)), ssmask=F(ssmask), jp_tem=1, jp_sal=2, nit000=kt, nitend=kt + 10, lwp=False, lwm=False,
+              ln_ctl=False, lk_mpp=True, ll_wd=False, ln_zad_aimp=False, nstop=0, numout=6, numstp=7, numrun=8, narea=dom.narea,
+              nimpp=dom.nimpp, njmpp=dom.njmpp, sn_cfctl=types.SimpleNamespace(ptimincr=1, l_runstat=False),
+              ctl_stop=lambda *a: stopped.append(a), dia_wri_state=lambda *a: None, **{"ctmp%d" % i: "" for i in range(1, 11)})
+    f90exec.load(_read("src", "OCE", "stpctl.F90"), ns, arrays=("sshn", "un", "tsn", "tmask", "umask", "ssmask", "wi", "cu_adv", "wmask"),
+                 only=("stp_ctl",), module_vars=("zmax", "ih", "iu", "is1", "is2", "nstop"))
+    out = ns["stp_ctl"](kt, 0)
+    res = dict(zmax=[float(x) for x in ns["zmax"][:6]], kindic=int(out["kindic"]), stopped=bool(stopped))
+    if res["kindic"]:
+        res.update(ih=[int(x) for x in ns["ih"]], iu=[int(x) for x in ns["iu"]], is1=[int(x) for x in ns["is1"]], is2=[int(x) for x in ns["is2"]])
+    return res

@@ -3,6 +3,7 @@
  * Restates the extrema test and the error condition of stp_ctl, src/OCE/stpctl.F90:115-124 (zmax(1:6), ll_wd = .false.),
  * :149-166 (the condition and the MAXLOC / MINLOC of the branch without ln_ctl), :184 (kindic = -3).  The files it opens
  * (time.step, run.stat, output.abort) and the ln_zad_Aimp pair zmax(8:9) are not restated.
+ * PARITY PIN: bit-identical to the reference's own stp_ctl text executed by translation (tests/test_cpu_reference_exec.py).
  * MAXVAL / MAXLOC with NaN operands are processor dependent in Fortran; gfortran skips NaN unless every operand is one.  The
  * restatement does the same (comparisons with NaN are false) and reports separately whether a NaN was met.
  */

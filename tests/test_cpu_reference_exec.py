@@ -531,6 +531,47 @@ def test_reference_glob_sum_and_ddpdd_equal_the_oracle(jperio):
 
 
 @needs_reference
+@pytest.mark.parametrize("case", ["clean", "ties", "u", "s0", "s100", "ssh"])
+def test_reference_stp_ctl_equals_the_oracle(case):
+    """stp_ctl (stpctl.F90:58-196, branch without ln_ctl) from the reference's text on the four subdomains of a 2 x 2 layout: zmax(1:6),
+    the error condition (kindic = -3 + ctl_stop) and the MAXLOC / MINLOC positions as global indices, against the oracle's restatement
+    (to which tests/test_gpu_stp_ctl.py holds nemo_stp_ctl_dev)"""
+    G, GJ, K, jperio = 21, 16, 6, 4
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=2, seed=5)
+    rng = np.random.default_rng(1)
+    tm = gf["tmask"]
+    sshn = np.ascontiguousarray(0.5 * rng.standard_normal((GJ, G)) * tm[0])
+    un = np.ascontiguousarray(0.3 * rng.standard_normal((K, GJ, G)) * gf["umask"])
+    tem, sal = (10 + rng.standard_normal((K, GJ, G))) * tm, (35 + rng.standard_normal((K, GJ, G))) * tm
+    wet = np.argwhere(tm == 1.0)
+    (k, j, i), (k2, j2, i2) = wet[len(wet) // 3], wet[2 * len(wet) // 3]
+    if case == "ties":
+        sal[k, j, i] = sal[k2, j2, i2] = 41.0
+        un[k, j, i], un[k2, j2, i2] = -7.0, 7.0
+    if case == "u":
+        un[k, j, i] = -11.5
+    if case == "s0":
+        sal[k, j, i] = -0.25
+    if case == "s100":
+        sal[k, j, i] = 100.0
+    if case == "ssh":
+        sshn[j, i] = 23.0
+    w = O.World(G, GJ, K, jperio, 2, 2)
+    fired = 0
+    for r, d in enumerate(w.doms):
+        loc = lambda a: np.ascontiguousarray(w.scatter(np.ascontiguousarray(a))[r])      # noqa: E731
+        lts = np.ascontiguousarray(np.stack([loc(tem), loc(sal)]))
+        want = O.stp_ctl(d, loc(sshn), loc(un), lts, loc(tm))
+        got = R.stp_ctl(d, loc(sshn), loc(un), lts, loc(tm), loc(gf["umask"]))
+        assert got["zmax"] == want["zmax"] and got["kindic"] == want["kindic"] and got["stopped"] == bool(want["kindic"]), (r, got, want)
+        if got["kindic"]:
+            fired += 1
+            assert all(got[q] == want[q] for q in ("ih", "iu", "is1", "is2")), (r, got, want)
+    w.close()
+    assert (fired > 0) == (case not in ("clean", "ties"))
+
+
+@needs_reference
 def test_reference_trc_adv_with_many_passive_tracers_equals_the_oracle():
     """trc_adv -> tra_adv_fct(..., 'TRC', r2dttrc, ..., jptra, ...) (trcadv.F90:127): the batched-tracer call of BASELINE config 5"""
     G, GJ, K, jperio, jptra = 20, 15, 6, 4, 7
