@@ -48,7 +48,15 @@ constexpr size_t kFusedSmemBytes = (size_t)FSTAGES * kFStageBytes + (size_t)kFPl
 
 struct FusedMaps { CUtensorMap h[FH_COUNT]; CUtensorMap p[FP_COUNT]; };
 
+#ifdef NEMO_FCT_SIGN_BY_COMPARE
+// Experiment, built by tests/emu only (never by the product Makefile): -0.0 counts as positive, as in the reference's key_nosignedzero
+// SIGN (lib_fortran.F90:339-351).  It removes nearly all of the zero-sign differences on land cells (207 -> 1 cells in the first
+// case of tests/test_cpu_reference_exec.py; the rest comes from selecting a beta instead of forming zcu*zau + (1-zcu)*zbu); it has
+// not been timed on a GPU (one DSETP per test instead of an integer compare).
+__device__ __forceinline__ bool sign_clear(double x) { return x >= 0.0; }
+#else
 __device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
+#endif
 
 // one thread: all TMA boxes of level `lev` into stage lev % FSTAGES (kept out of line: called from every copy of the level loop).
 // The issuing thread sits in the LAST warp of the block: the first and last rows of the tile only run stage A, so the ~150

@@ -20,6 +20,13 @@ def load():
     return _L
 
 
+def load_signcmp():
+    """the fused kernel alone, built with -DNEMO_FCT_SIGN_BY_COMPARE (an experiment: sign tests by comparison, see fct_fused_kernel.cuh)"""
+    d = os.path.join(HERE, "emu")
+    subprocess.check_call(["make", "-C", d, "libemu_signcmp.so"], stdout=subprocess.DEVNULL)
+    return C.CDLL(os.path.join(d, "libemu_signcmp.so"))
+
+
 def p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -115,7 +122,7 @@ def fct_fused(L, out, nk, f, work, kjpt, h, v, lin, isf, masks_from_t):
                            p(f["mikt"]), p(f["mbkt"]), int(masks_from_t))
 
 
-def fct_step_one_kernel(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, nk_fused=1):
+def fct_step_one_kernel(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, nk_fused=1, fused_lib=None):
     """tra_adv_fct in schedule 4 (run_fct): k_fct_fused on K2's rectangle straight from the inputs; the band of K1 (which
     leaves pta alone inside that rectangle) and the frame chain with X1..X4 as in the other fused schedules.  Returns
     (pta, plan) or (None, plan) where the product falls back (no split possible, odd jpi)."""
@@ -149,7 +156,7 @@ def fct_step_one_kernel(L, f, kjpt, h, v, lin, isf, nk, lbc, fold, nk_fused=1):
     lbc([(work["zlx"], "U", -1.0), (work["zly"], "V", -1.0)])                         # X4 on the limited copies
     on("fin", 4, work)
     # the fused kernel is independent of all of the above (main stream): run it last to prove it reads inputs only
-    rc = fct_fused(L, plan["k2_out"], nk_fused, f, frame, kjpt, h, v, lin, isf, True)
+    rc = fct_fused(fused_lib or L, plan["k2_out"], nk_fused, f, frame, kjpt, h, v, lin, isf, True)
     assert rc == 0, "TMA box origin rule violated / kernel refused: %d" % rc
     return work["pta"], plan
 

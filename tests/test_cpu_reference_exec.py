@@ -327,6 +327,14 @@ def test_the_product_kernels_compiled_for_the_host_equal_the_reference_source(G,
     # and the limiter then multiplies a zero flux by the other (possibly negative, land-side) beta.  The three-kernel and the
     # reference-structured schedules keep the reference's zero signs too (golden hashes, test_vectors_golden.py).
     assert (want[differ] == 0.0).all() and (tmask[differ] == 0.0).all()
+    # Experiment (not the shipped build, not timed on a GPU): with the sign tests of k_fct_fused done by comparison, -0.0 counting as
+    # positive like the reference's SIGN, nearly all of those zeros get the reference's sign (what is left comes from selecting a
+    # beta where the reference forms zcu*zau + (1-zcu)*zbu, whose zero can have the other sign).
+    pta2, _ = emu_api.fct_step_one_kernel(emu, gf, kjpt, h, v, lin, isf, 1, lambda trip: ref_lbc(list(trip)), jperio in (3, 4, 5, 6),
+                                          fused_lib=emu_api.load_signcmp())
+    differ2 = pta2.view(np.uint64) != want.view(np.uint64)
+    assert np.array_equal(pta2, want) and (want[differ2] == 0.0).all() and (tmask[differ2] == 0.0).all()
+    assert differ.sum() > 50 and differ2.sum() * 20 <= differ.sum()
 
 
 @needs_reference
