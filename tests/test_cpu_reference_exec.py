@@ -468,6 +468,34 @@ def test_reference_mpp_init_equals_oracle_and_product(N, jperio):
 
 
 @needs_reference
+@pytest.mark.parametrize("jperio", [0, 1, 4, 6, 7])
+def test_the_product_exchange_plan_equals_the_reference_exchange(N, jperio):
+    """No oracle exchange code in this loop: the PRODUCT's compiled lbc_lnk plan (host C++, csrc/layout.cpp -- the tables the device
+    pack / unpack kernels execute), applied in numpy, against the REFERENCE's mpp_lnk + mpp_nfd text (MPI_ALLGATHER fold, the
+    semantics the product implements, INTEGRATION.md par. 4) on emulated MPI ranks: every cell of every rank, halos and corners
+    included, on fold-inconsistent random data.  (The oracle's mpp_init only supplies the decomposition scalars of the emulated
+    ranks, themselves pinned to the reference's mpp_init above.)"""
+    from test_cpu_lbc_plan import run_plan
+    rng = np.random.default_rng(60 + jperio)
+    for (G, GJ) in ((22, 17), (21, 16)):
+        for (ni, nj) in ((2, 2), (3, 2), (4, 1), (1, 2)):
+            try:
+                w = O.World(G, GJ, 2, jperio, ni, nj, ln_nnogather=False)
+                doms = [N.mpp_init(G, GJ, 2, jperio, ni, nj, r + 1) for r in range(ni * nj)]
+            except (ValueError, N.NemoFctError):
+                continue
+            mw = R.MppWorld(w.doms, False)
+            for nat, sgn in (("T", 1.0), ("U", -1.0), ("V", -1.0), ("W", 1.0), ("F", -1.0), ("F", 1.0)):
+                fields = [rng.standard_normal((2, d.jpj, d.jpi)) for d in doms]
+                ref = [f.copy() for f in fields]
+                mw.lbc_lnk(ref, nat, sgn)
+                got = run_plan(N, doms, fields, nat, sgn)
+                for r in range(len(doms)):
+                    assert np.array_equal(ref[r].view(np.uint64), got[r].view(np.uint64)), ((G, GJ), (ni, nj), nat, sgn, r)
+            w.close()
+
+
+@needs_reference
 def test_reference_fold_partner_tables_equal_oracle_and_product(N):
     """mpp_init_nfdcom (mppini.F90:1180-1240) from the reference's text, fed with the tables of ITS mpp_basic_decomposition: nsndto /
     isendto (the no-gather fold partners, part of the product's domain descriptor) and nfsloop / nfeloop"""
