@@ -177,29 +177,32 @@ def test_translator_resolves_cpp_conditionals_and_flags_literals():
 
 
 def test_cpp_function_like_macros_as_in_the_generic_h90_files():
+    """the generic .h90 files of the reference define their array accessors, sizes and declarations as function-like macros under
+    nested conditionals; the same mechanisms on a snippet written here"""
     src = """
-#if defined MULTI
-#   define ARRAY_IN(i,j,k,l,f)   ptab(f)%pt3d(i,j,k)
+#if defined VIA_POINTERS
+#   define FIELD_AT(a,b,c,d,n)   pfld(n)%p3(a,b,c)
 #else
-#   define NAT_IN(k)             cd_nat
-#   if defined DIM_3d
-#      define ARRAY_IN(i,j,k,l,f)   ptab(i,j,k)
-#      define K_SIZE(ptab)          SIZE(ptab,3)
+#   define KIND_OF(n)            cd_kind
+#   if defined RANK_3
+#      define FIELD_AT(a,b,c,d,n)   pfld(a,b,c)
+#      define NLEV(pfld)            SIZE(pfld,3)
 #   endif
-#   define ARRAY_TYPE(i,j,k,l,f)    REAL(wp),INTENT(inout)::ARRAY_IN(i,j,k,l,f)
+#   define FIELD_DECL(a,b,c,d,n)    REAL(wp),INTENT(inout)::FIELD_AT(a,b,c,d,n)
+#   define NO_ARG
 #endif
-   SUBROUTINE ROUTINE_X( ptab, cd_nat )
-      ARRAY_TYPE(:,:,:,:,:)
-      CHARACTER(len=1) , INTENT(in   ) ::   NAT_IN(:)
+   SUBROUTINE ROUTINE_X( pfld, cd_kind )
+      FIELD_DECL(:,:,:,:,:)
+      CHARACTER(len=1) , INTENT(in   ) ::   KIND_OF(:)
       INTEGER :: ji
-      DO ji = 1, K_SIZE(ptab)
-         IF( NAT_IN(jf) == 'T' )   ARRAY_IN(1,2,ji,:,jf) = -ARRAY_IN(2, 2 ,ji,:,jf)
+      DO ji = 1, NLEV(pfld)
+         IF( KIND_OF(jf) == 'T' )   FIELD_AT(1,2,ji,:,jf) = -FIELD_AT(2, 2 ,ji,:,jf) NO_ARG
       END DO
    END SUBROUTINE ROUTINE_X
-#undef ARRAY_IN
+#undef FIELD_AT
 """
-    txt = f90exec.cpp(src, defined=("DIM_3d",), macros={"ROUTINE_X": "flip_3d"})
-    assert "#" not in txt and "ptab(1,2,ji) = -ptab(2,2,ji)" in txt and "REAL(wp),INTENT(inout)::ptab(:,:,:)" in txt
+    txt = f90exec.cpp(src, defined=("RANK_3",), macros={"ROUTINE_X": "flip_3d"})
+    assert "#" not in txt and "pfld(1,2,ji) = -pfld(2,2,ji)" in txt and "REAL(wp),INTENT(inout)::pfld(:,:,:)" in txt
     ns = {}
     f90exec.load(txt, ns)
     a = np.arange(24, dtype=np.float64).reshape(2, 3, 4)
