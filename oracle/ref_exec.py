@@ -291,7 +291,7 @@ class _Mpi:
         self._q((src, dst, tag)).put(np.array(data, copy=True))
 
     def recv(self, src, dst, tag):
-        return self._q((src, dst, tag)).get(timeout=10)
+        return self._q((src, dst, tag)).get(timeout=60)
 
 
 class MppWorld:
@@ -373,7 +373,7 @@ class MppWorld:
         for t in th:
             t.start()
         for t in th:
-            t.join(timeout=25)
+            t.join(timeout=120)
         if err or any(t.is_alive() for t in th):
             raise RuntimeError("mpp_lnk failed or hung: %s" % (err[:1] or "timeout"))
 
