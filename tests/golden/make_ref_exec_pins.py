@@ -78,6 +78,17 @@ if __name__ == "__main__":
     pins["full_size"] = {"c1_bench128": {"input_sha256": GC.input_hash(gf, {}), "outputs": {"pta": GC.digest(out)},
                                          "reference_files": {f: file_sha(f) for f in FILES["fct"]}, "seconds": round(time.time() - t0, 1)}}
     print("c1_bench128", pins["full_size"]["c1_bench128"])
+    # BASELINE config C5 at FULL size (ORCA2_ICE_PISCES-shaped 182x149x31, 26 tracers in one call as trcadv.F90:127 makes it, FCT 2/2,
+    # T-pivot fold; the seeded random fields of tests/test_gpu_fct_one_kernel.py::test_one_kernel_orca2_pisces_shape_26_tracers):
+    # 21.8 M tracer-points, about a quarter of an hour of translated Fortran.
+    t0 = time.time()
+    gf = H.random_fields(O, 182, 149, 31, 4, kjpt=26, seed=460)
+    out = R.tra_adv_fct(gf, 182, 149, 31, 26, 2, 2, False, False, R.reference_lbc(4, 182, 149), cdtype="TRC")
+    assert np.isfinite(out).all()
+    pins["full_size"]["c5_orca2_pisces_26_tracers"] = {"input_sha256": GC.input_hash(gf, {}), "outputs": {"pta": GC.digest(out)},
+                                                       "reference_files": {f: file_sha(f) for f in FILES["fct"]},
+                                                       "seconds": round(time.time() - t0, 1)}
+    print("c5_orca2_pisces_26_tracers", pins["full_size"]["c5_orca2_pisces_26_tracers"])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_exec_pins.json")
     with open(path, "w") as f:
         json.dump(pins, f, indent=1, sort_keys=True)

@@ -60,6 +60,18 @@ def test_c1_at_full_size_the_oracle_equals_the_reference_source():
     assert GC.digest(ref) == pin["outputs"]["pta"]
 
 
+def test_c5_at_full_size_the_oracle_equals_the_reference_source():
+    """BASELINE config C5 (ORCA2_ICE_PISCES-shaped 182x149x31, T-pivot fold, 26 tracers in ONE call as trc_adv makes it, FCT 2/2) at
+    full size: the oracle's pta carries the sha256 of the reference's tra_adv_fct text executed on the same seeded fields
+    (a quarter of an hour of translated Fortran, tests/golden/make_ref_exec_pins.py).  The GPU suite compares the CUDA path with the
+    oracle on exactly these inputs (test_gpu_fct_one_kernel.py::test_one_kernel_orca2_pisces_shape_26_tracers)."""
+    pin = PINS["full_size"]["c5_orca2_pisces_26_tracers"]
+    gf = H.random_fields(O, 182, 149, 31, 4, kjpt=26, seed=460)
+    assert GC.input_hash(gf, {}) == pin["input_sha256"], "the seeded input generator changed (numpy RNG stream?)"
+    ref, _, _ = H.oracle_fct(O, gf, 182, 149, 31, 4, 1, 1, 26, 2, 2)
+    assert GC.digest(ref) == pin["outputs"]["pta"]
+
+
 # ---- the translator, on snippets written here ------------------------------------------------------------------------------------
 def _run(src, **ns):
     f90exec.load(src, ns, arrays=ns.pop("_arrays", ()), int_arrays=ns.pop("_int_arrays", ()))
