@@ -545,3 +545,33 @@ def stp_ctl(dom, sshn, un, tsn, tmask, umask, kt=1):
     if res["kindic"]:
         res.update(ih=[int(x) for x in ns["ih"]], iu=[int(x) for x in ns["iu"]], is1=[int(x) for x in ns["is1"]], is2=[int(x) for x in ns["is2"]])
     return res
+
+
+def tra_adv_mus_mpp(world, gf, mx, kjpt, ln_linssh, ln_isfcav, ld_msc_ups, ln_nnogather=True):
+    """the reference's tra_adv_mus on EVERY rank of `world`, halos through the reference's mpp_lnk / mpp_nfd on emulated MPI ranks
+    (as tra_adv_fct_mpp).  Returns the list of local pta arrays."""
+    mw = MppWorld(world.doms, ln_nnogather)
+    loc = {k: world.scatter(gf[k]) for k in DOM_ARRAYS + DOM_INT_ARRAYS + ("pun", "pvn", "pwn", "ptb", "pta")}
+    lx = {k: world.scatter(mx[k]) for k in ("r1_e1e2u", "r1_e1e2v", "e3u_n", "e3v_n", "e3w_n") + (("rnfmsk",) if ld_msc_ups else ())}
+    out, err = [None] * mw.n, []
+
+    def run(r):
+        try:
+            d = world.doms[r]
+            g = {k: loc[k][r] for k in loc}
+            g["p2dt"] = gf["p2dt"]
+            m = {k: lx[k][r] for k in lx}
+            if ld_msc_ups:
+                m["rnfmsk_z"] = mx["rnfmsk_z"]
+            out[r] = tra_adv_mus(g, m, d.jpi, d.jpj, d.jpk, kjpt, ln_linssh, ln_isfcav, ld_msc_ups, mw.rank_lbc(r))
+        except Exception:                 # noqa: BLE001
+            import traceback
+            err.append((r, traceback.format_exc()))
+    th = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(mw.n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=240)
+    if err or any(t.is_alive() for t in th):
+        raise RuntimeError("tra_adv_mus_mpp failed or hung: %s" % (err[:1] or "timeout"))
+    return out

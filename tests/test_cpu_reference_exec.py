@@ -526,6 +526,22 @@ def test_the_product_exchange_plan_equals_the_reference_exchange(N, jperio):
 
 
 @needs_reference
+@pytest.mark.parametrize("jperio,lay,nog,ups", [(4, (2, 2), True, True), (6, (3, 1), False, False)])
+def test_reference_tra_adv_mus_on_emulated_mpi_ranks_equals_the_mono_domain_oracle(jperio, lay, nog, ups):
+    """tra_adv_mus (the scheme BENCH uses for its passive tracers) from the reference's text on every emulated rank, with its two
+    exchanges through mpp_lnk / mpp_nfd: the assembled interiors are the mono-domain oracle's result bit for bit"""
+    G, GJ, K, kjpt = 26, 21, 6, 2
+    gf = H.random_fields(O, G, GJ, K, jperio, kjpt=kjpt, seed=850 + jperio)
+    mx = H.mus_extra_fields(O, gf, G, GJ, K, jperio, seed=850 + jperio, runoff=True)
+    ref, _ = H.oracle_mus(O, gf, mx, G, GJ, K, jperio, 1, 1, kjpt, ld_msc_ups=ups)
+    w = O.World(G, GJ, K, jperio, lay[0], lay[1], ln_nnogather=nog)
+    loc = R.tra_adv_mus_mpp(w, gf, mx, kjpt, False, False, ups, nog)
+    glob = w.gather(loc, gf["pta"].copy())
+    w.close()
+    assert np.array_equal(glob.view(np.uint64), ref.view(np.uint64))
+
+
+@needs_reference
 def test_reference_fold_partner_tables_equal_oracle_and_product(N):
     """mpp_init_nfdcom (mppini.F90:1180-1240) from the reference's text, fed with the tables of ITS mpp_basic_decomposition: nsndto /
     isendto (the no-gather fold partners, part of the product's domain descriptor) and nfsloop / nfeloop"""
