@@ -292,7 +292,8 @@ int nemo_fct_comm_report(nemo_fct_handle h, long long *n_exchanges, long long *b
 int nemo_fct_set_profiling(nemo_fct_handle h, int on);
 int nemo_fct_profile_read(nemo_fct_handle h, int max_entries, char *names, int name_stride, double *total_ms,
                           long long *calls);
-/* Select the kernel schedule.  Schedules 0 - 3 return the same bits as the CPU restatement of the reference; schedule 4 returns the
+/* Select the kernel schedule.  Schedules 0 - 3 return the same bits as the CPU restatement of the reference (checked by sha256 for 0
+ * and 2; 1 and 3 share their arithmetic); schedule 4 returns the
  * same VALUE at every cell and the same bits at every ocean cell -- on land cells, where the trend is +-0, it may return the zero
  * with the other sign (its sign-bit forms of MAX(0,f) / MIN(0,f) / SIGN take -0.0 for negative; the reference built with
  * key_nosignedzero takes it for positive): tests/test_cpu_reference_exec.py.
