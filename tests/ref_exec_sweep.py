@@ -6,7 +6,7 @@ a test (needs the reference tree; minutes of translated Fortran):
 Part 1: tra_adv_fct on random small domains (every jperio 0-7, 2nd / 4th order, ln_linssh / ln_isfcav, 1-3 tracers, land fraction up
 to 0.9, CFL up to 0.9, jpk down to 3).  Part 2: the multi-rank exchange (mpp_lnk + mpp_nfd, gather and no-gather) on random layouts
 up to 5 x 3 ranks, every nature, random sign.  Part 3: tra_adv_mus (with and without the upstream indicator) and tra_adv_cen (2nd order
-horizontal, 2nd / compact vertical).  Round 2: 1623 FCT cases, 2835 exchanges and 2217 MUSCL / centred cases, 0 mismatches (bit for bit)."""
+horizontal, 2nd / compact vertical).  Round 2 (seeds 12345 and 999): 6230 FCT cases, 9480 exchanges and 5677 MUSCL / centred cases, 0 mismatches (bit for bit)."""
 import argparse
 import os
 import sys
