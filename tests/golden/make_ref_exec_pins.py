@@ -102,6 +102,10 @@ if __name__ == "__main__":
                                      "reference_files": {f: file_sha(f) for f in FILES["fct"]}, "seconds": round(time.time() - t0, 1)}
     print("c2_orca1", pins["full_size"]["c2_orca1"])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_exec_pins.json")
+    if os.path.exists(path):                           # the sampled C3 check has its own script (tests/golden/c3_windows.py, 48 GB of memory)
+        old = json.load(open(path))
+        if "c3_windows" in old:
+            pins["c3_windows"] = old["c3_windows"]
     with open(path, "w") as f:
         json.dump(pins, f, indent=1, sort_keys=True)
     print(path, os.path.getsize(path), "bytes")
