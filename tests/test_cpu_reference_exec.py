@@ -90,10 +90,11 @@ def test_c2_at_full_size_the_oracle_equals_the_reference_source():
 def test_c3_windows_of_the_headline_config_equal_the_reference_source():
     """BASELINE config C3 (ORCA025-like, the headline benchmark) sampled: for five 48 x 40-column windows cut out of the actual global
     fields the reference's tra_adv_fct text, run on the window as a closed domain, equals the FULL-SIZE oracle result 6 cells inside
-    the window, bit for bit (tests/golden/c3_windows.py; recorded in ref_exec_pins.json).  Recomputed here with NEMO_C3_WINDOWS=1 (48 GB
-    of host memory, 2.5 minutes); tests/test_gpu_full_size.py holds the CUDA path to the same full-size oracle result."""
+    the window, bit for bit -- and so do the northernmost 16 rows over the full width, run as a T-pivot domain of their own
+    (tests/golden/c3_windows.py; recorded in ref_exec_pins.json).  Recomputed here with NEMO_C3_WINDOWS=1 (48 GB of host memory, 8 minutes); tests/test_gpu_full_size.py holds the CUDA path to the same full-size oracle result."""
     rec = PINS["c3_windows"]
-    assert len(rec["windows"]) == 5 and all(w["equal_to_full_size_oracle"] and w["changed"] for w in rec["windows"].values())
+    assert len(rec["windows"]) == 6 and all(w["equal_to_full_size_oracle"] and w["changed"] for w in rec["windows"].values())
+    assert any(k.startswith("fold_band") for k in rec["windows"])      # the northernmost rows over the full width: seam and T-pivot fold
     if os.environ.get("NEMO_C3_WINDOWS") == "1" and R.available():
         import c3_windows
         now = c3_windows.run()
